@@ -1,0 +1,164 @@
+/*
+ * vitae_b200.h -- C ABI of libvitae_b200.so: the sm_100a kernels behind the 3D ViT masked-autoencoder
+ * training path of ViT-AE++ (reference: chinmay5/vit_ae_plus_plus, pure PyTorch).
+ *
+ * The reference has no native interface: its "FFI" for this path is torch's ATen dispatch (nn.Conv3d,
+ * nn.Linear, nn.LayerNorm, softmax, nn.GELU, argsort/gather, elementwise loss).  Each entry point below names the
+ * reference call site(s) it replaces (paths relative to the reference root).  INTEGRATION.md shows the ctypes
+ * binding a reference maintainer adds.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes; every pointer is a DEVICE pointer borrowed for the duration of the enqueue;
+ *   - `stream` is a cudaStream_t passed as void*; work is only enqueued -- no allocation, no synchronisation,
+ *     CUDA-graph capturable;
+ *   - returns 0 on success, negative on error; vitae_last_error() returns a thread-local message;
+ *   - row-major contiguous layouts unless a leading dimension is given; bf16 = __nv_bfloat16 bit pattern;
+ *   - "rows" index arrays are int32.
+ */
+#ifndef VITAE_B200_H
+#define VITAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITAE_ABI_VERSION 1
+
+int vitae_abi_version(void);
+const char* vitae_last_error(void);
+/* 0 when the current device is compute capability 10.x (B200); negative otherwise. */
+int vitae_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Dense contraction on the 5th-gen tensor cores (tcgen05.mma, TMA-staged 128B-swizzled tiles, TMEM accumulator).
+ * Replaces every nn.Linear on the path -- model/vit.py:107,114 (qkv), :109,122 (proj), :84-86,91-95 (fc1/fc2),
+ * model/vit_autoenc.py:40,181 (decoder_embed), :52,198 (decoder_pred) -- the im2col form of the Conv3d patch embed
+ * (model/vit.py:65,72) and their autograd backward (dgrad / wgrad) run by loss.backward() (utils/misc.py:258).
+ *
+ *   acc[m,n] = sum_k A(m,k) * B(n,k)                      bf16 x bf16 -> fp32
+ *   A: a_mn_major == 0: stored [M, K] row-major, leading dim lda;   == 1: stored [K, M] row-major (A transposed)
+ *   B: b_mn_major == 0: stored [N, K] row-major (nn.Linear weight); == 1: stored [K, N] row-major
+ *   forward  y = x W^T : A=x (0), B=W (0)           dgrad dx = dy W : A=dy (0), B=W (1)
+ *   wgrad    dW = dy^T x: A=dy (1), B=x (1)
+ *
+ * Epilogue, per element (r = out_rows ? out_rows[m] : m,  ra = add_rows ? add_rows[m] : m):
+ *   v = alpha * (alpha_ptr ? *alpha_ptr : 1) * acc + (bias ? bias[n] : 0) + (addend ? addend[ra*ldadd + n] : 0)
+ *   if dgelu_src: v *= gelu'(dgelu_src[m*ld_dgelu + n])            (erf GELU derivative)
+ *   if out_f32 : out_f32[r*ld_f32 + n]  = (accumulate ? old : 0) + v
+ *   if out_bf16: out_bf16[r*ld_bf16 + n] = bf16(v)
+ *   if out_gelu_bf16: out_gelu_bf16[r*ld_bf16 + n] = bf16(gelu(v))   (erf GELU, model/vit.py:81,92)
+ * Requirements: N % 8 == 0, leading dims % 8 == 0, 16-byte aligned base pointers.
+ * split_k > 1 needs workspace >= split_k*M*N*4 bytes (deterministic slab reduction, no atomics).
+ */
+typedef struct vitae_gemm_epilogue {
+    float alpha;
+    const float* alpha_ptr;
+    const float* bias;
+    const float* addend;
+    const int32_t* add_rows;
+    int32_t ldadd;
+    const void* dgelu_src; /* bf16 */
+    int32_t ld_dgelu;
+    float* out_f32;
+    int32_t ld_f32;
+    int32_t accumulate;
+    void* out_bf16;      /* bf16 */
+    void* out_gelu_bf16; /* bf16 */
+    int32_t ld_bf16;
+    const int32_t* out_rows;
+} vitae_gemm_epilogue;
+
+int vitae_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M, int N,
+                    int K, const vitae_gemm_epilogue* ep, int tile_n, int split_k, void* workspace,
+                    size_t workspace_bytes, void* stream);
+size_t vitae_gemm_workspace_bytes(int M, int N, int split_k);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * LayerNorm (biased variance, eps inside sqrt) -- nn.LayerNorm at model/vit.py:131,135,140-143 and
+ * model/vit_autoenc.py:36,51,174,195.  x fp32 [rows, D]; y bf16 [rows, D] (GEMM operand) and/or y_f32; mean/rstd
+ * fp32 [rows] saved for backward.  Warp-shuffle row statistics.
+ */
+int vitae_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
+                        float* mean, float* rstd, int rows, int D, float eps, void* stream);
+/* dx_out = (dx_in ? dx_in : 0) + LN'(dy); dy is bf16 (dy_bf16) or fp32 (dy_f32); also emits a bf16 copy of dx_out
+ * (operand of the next dgrad/wgrad GEMM) when dx_out_bf16 != NULL.  dgamma/dbeta partial sums go to
+ * partials [2, nblocks, D] (nblocks = vitae_layernorm_bwd_blocks(rows)); reduce them with vitae_colsum. */
+int vitae_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* gamma,
+                        const float* mean, const float* rstd, const float* dx_in, float* dx_out, void* dx_out_bf16,
+                        float* partials, int rows, int D, void* stream);
+int vitae_layernorm_bwd_blocks(int rows);
+
+/* Column sums: out[c] = (accumulate ? out[c] : 0) + sum_r in[r*ld + c]  (bias gradients; LN partial reduction).
+ * Exactly one of in_bf16 / in_f32 is non-NULL.  workspace: fp32 [vitae_colsum_blocks(rows) * cols]. */
+int vitae_colsum(const void* in_bf16, const float* in_f32, int rows, int cols, int ld, float* out, int accumulate,
+                 float* workspace, void* stream);
+int vitae_colsum_blocks(int rows);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused multi-head self-attention, flash-style (scores never leave the SM) -- model/vit.py:112-121:
+ *   qkv bf16 [B, N, 3, H, hd] (the qkv Linear output as-is), out bf16 [B, N, H*hd], lse fp32 [B, H, N].
+ *   softmax(q k^T * scale) v, online softmax in fp32 with warp-shuffle row reductions.  hd in {16, 32, 64}.
+ */
+int vitae_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int hd, float scale,
+                        void* stream);
+/* dqkv bf16 [B, N, 3, H, hd]; delta fp32 [B, H, N] is scratch (rowsum(dout*out)). */
+int vitae_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
+                        void* dqkv, int B, int N, int H, int hd, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Per-sample random masking -- model/vit_autoenc.py:130-155: ids_shuffle = argsort(noise) (stable), ids_restore =
+ * argsort(ids_shuffle), mask[b, l] = 1 if patch l is removed.  noise fp32 [B, L]; outputs int32 / fp32 [B, L].
+ */
+int vitae_random_masking(const float* noise, int32_t* ids_shuffle, int32_t* ids_restore, float* mask, int B, int L,
+                         int len_keep, void* stream);
+
+/* Patch gather for the Conv3d(k=s=p) patch embed -- model/vit.py:65,72 + the torch.gather of kept tokens at
+ * model/vit_autoenc.py:147: row (b*keep + j) of `cols` (bf16 [B*keep, C*p^3], K order (c,pz,py,px) = conv weight
+ * order) is patch ids_shuffle[b, j] of volume b.  vol fp32 [B, C, V, V, V]. */
+int vitae_im2col_patches(const float* vol, const int32_t* ids_shuffle, void* cols_bf16, int B, int C, int V, int p,
+                         int L, int keep, void* stream);
+
+/* Token assembly helpers (model/vit_autoenc.py:168-170 cls prepend, :184-190 mask tokens + unshuffle + pos). */
+/* dst[row_idx[i] (or i), :] = src0[(src0_rows ? src0_rows[i] : 0), :] + src1[(src1_rows ? src1_rows[i] : 0), :] */
+int vitae_fill_rows(float* dst, const int32_t* row_idx, int nrows, int D, const float* src0, const int32_t* src0_rows,
+                    const float* src1, const int32_t* src1_rows, void* stream);
+/* dst_bf16[i, :] = bf16(src[row_idx[i], :])  (gathers gradient rows into a GEMM operand); dst_f32 optional */
+int vitae_gather_rows(const float* src, const int32_t* row_idx, int nrows, int D, void* dst_bf16, float* dst_f32,
+                      void* stream);
+/* out[:] = (accumulate ? out : 0) + sum_i src[row_idx[i], :]  (cls_token / mask_token gradients), single block */
+int vitae_sum_rows(const float* src, const int32_t* row_idx, int nrows, int D, float* out, int accumulate,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Masked patch-reconstruction loss -- model/vit_autoenc.py:100-113 (patchify) + :226-227 (masked MSE), without
+ * materialising the patchified target: pred [B, Nd=L+1, P] (row 0 of each sample = cls, ignored; bf16 or fp32),
+ * vol fp32 [B, C, V, V, V], P = p^3*C ordered (pz,py,px,c).  loss_out[0] = sum_masked mean_P (pred-target)^2 / sum(mask),
+ * loss_out[1] = sum(mask) (consumed by the backward as mask_sum).  patch_sums: fp32 scratch [B*L].
+ */
+int vitae_masked_mse_fwd(const void* pred, int pred_is_bf16, const float* vol, const float* mask, float* patch_sums,
+                         float* loss_out, int B, int C, int V, int p, void* stream);
+/* dpred[b, 1+l, :] = mask[b,l] * 2 (pred - target) / (P * sum(mask)) * (*dloss); cls rows and kept patches are
+ * written as zeros.  dpred bf16 [B, Nd, P]. */
+int vitae_masked_mse_bwd(const void* pred, int pred_is_bf16, const float* vol, const float* mask,
+                         const float* mask_sum, const float* dloss, void* dpred_bf16, int B, int C, int V, int p,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Parameter plumbing: fp32 master weights -> flat bf16 shadow (one launch for all tensors).
+ * table: device array of ntensors records {uint64 src_ptr, uint64 dst_elem_offset, uint64 numel}. */
+int vitae_cast_params_bf16(const void* table, int ntensors, void* dst_bf16, long long total_elems, void* stream);
+
+/* Fused AdamW over a flat fp32 parameter/gradient/moment buffer (torch.optim.AdamW semantics,
+ * k_fold_cross_valid_combined_brats.py:168-169): grad is first multiplied by (*inv_scale) (GradScaler unscale);
+ * if (*found_inf != 0) the step is skipped.  wd_mask[i]==0 => no weight decay for element block. */
+int vitae_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16,
+                     long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                     float bias_corr1, float bias_corr2, const float* inv_scale, const float* found_inf, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITAE_B200_H */

@@ -1,0 +1,96 @@
+"""ctypes binding of libvitae_b200.so (C ABI declared in include/vitae_b200.h).
+
+The product path has NO fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_longlong, c_size_t, c_void_p
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libvitae_b200.so")
+
+
+class VitaeError(RuntimeError):
+    pass
+
+
+class GemmEpilogue(Structure):
+    # mirrors struct vitae_gemm_epilogue (include/vitae_b200.h)
+    _fields_ = [
+        ("alpha", c_float),
+        ("alpha_ptr", c_void_p),
+        ("bias", c_void_p),
+        ("addend", c_void_p),
+        ("add_rows", c_void_p),
+        ("ldadd", c_int32),
+        ("dgelu_src", c_void_p),
+        ("ld_dgelu", c_int32),
+        ("out_f32", c_void_p),
+        ("ld_f32", c_int32),
+        ("accumulate", c_int32),
+        ("out_bf16", c_void_p),
+        ("out_gelu_bf16", c_void_p),
+        ("ld_bf16", c_int32),
+        ("out_rows", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/vitae_b200.h
+SIGNATURES = {
+    "vitae_abi_version": (c_int, []),
+    "vitae_last_error": (c_char_p, []),
+    "vitae_check_device": (c_int, []),
+    "vitae_gemm_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                POINTER(GemmEpilogue), c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "vitae_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "vitae_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                    c_float, c_void_p]),
+    "vitae_layernorm_bwd": (c_int, [c_void_p] * 10 + [c_int, c_int, c_void_p]),
+    "vitae_layernorm_bwd_blocks": (c_int, [c_int]),
+    "vitae_colsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "vitae_colsum_blocks": (c_int, [c_int]),
+    "vitae_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "vitae_attention_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "vitae_random_masking": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vitae_im2col_patches": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "vitae_fill_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vitae_gather_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "vitae_sum_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "vitae_masked_mse_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_void_p]),
+    "vitae_masked_mse_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                     c_int, c_int, c_void_p]),
+    "vitae_cast_params_bf16": (c_int, [c_void_p, c_int, c_void_p, c_longlong, c_void_p]),
+    "vitae_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float,
+                                 c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Loads the library (once).  Raises VitaeError when it has not been built: there is no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VitaeError(
+            f"{LIB_PATH} not found: build it with `python -m vit_ae_plus_plus_b200.build` "
+            "(nvcc, sm_100a).  This package has no CPU / PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    if lib.vitae_abi_version() != 1:
+        raise VitaeError("libvitae_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().vitae_last_error().decode(errors="replace")
+        raise VitaeError(f"{what} failed (rc={rc}): {msg}")

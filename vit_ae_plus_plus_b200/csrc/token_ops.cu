@@ -1,0 +1,291 @@
+// Index / gather kernels of the MAE path: per-sample random masking (argsort of noise), kept-patch im2col for the
+// patch embed, token assembly (cls / mask-token rows), gradient row gathers, multi-tensor bf16 cast, fused AdamW.
+// All HBM- or latency-bound; coalesced, vectorised where the layout allows.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vitae {
+
+// ---------------------------------------------------------------------------------------------------------------
+// random masking: one CTA per sample, bitonic sort of (noise bits, index) 64-bit keys in shared memory.
+// noise in [0,1) => the fp32 bit pattern orders like the value; the index in the low word makes the sort stable
+// (== torch.argsort(stable=True); torch's default argsort is only unspecified on exact ties).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+random_masking_kernel(const float* __restrict__ noise, int* __restrict__ ids_shuffle, int* __restrict__ ids_restore,
+                      float* __restrict__ mask, int L, int Lpow2, int len_keep) {
+    extern __shared__ unsigned long long keys[];
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < Lpow2; i += blockDim.x) {
+        unsigned long long k = ~0ull;  // padding sorts last
+        if (i < L) {
+            float v = noise[static_cast<size_t>(b) * L + i];
+            unsigned int u = __float_as_uint(v);
+            u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // total order for any finite float
+            k = (static_cast<unsigned long long>(u) << 32) | static_cast<unsigned int>(i);
+        }
+        keys[i] = k;
+    }
+    __syncthreads();
+    for (int size = 2; size <= Lpow2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < Lpow2 / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool asc = (lo & size) == 0;
+                const unsigned long long a = keys[lo], c = keys[hi];
+                if ((a > c) == asc) {
+                    keys[lo] = c;
+                    keys[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int rank = threadIdx.x; rank < L; rank += blockDim.x) {
+        const int idx = static_cast<int>(keys[rank] & 0xffffffffu);
+        ids_shuffle[static_cast<size_t>(b) * L + rank] = idx;
+        ids_restore[static_cast<size_t>(b) * L + idx] = rank;
+        mask[static_cast<size_t>(b) * L + idx] = rank < len_keep ? 0.f : 1.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// im2col of the kept patches: cols[(b*keep + j), (c, pz, py, px)] = vol[b, c, gz*p+pz, gy*p+py, gx*p+px]
+// one thread moves 4 consecutive px (float4 load, 8-byte bf16 store); p % 4 == 0.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+im2col_patches_kernel(const float* __restrict__ vol, const int* __restrict__ ids_shuffle, __nv_bfloat16* __restrict__ cols,
+                      int C, int V, int p, int g, int L, int keep) {
+    const int row = blockIdx.x;  // b*keep + j
+    const int b = row / keep, j = row % keep;
+    const int patch = ids_shuffle[static_cast<size_t>(b) * L + j];
+    const int gz = patch / (g * g), gy = (patch / g) % g, gx = patch % g;
+    const int p4 = p >> 2;
+    const int per_patch = C * p * p * p4;  // float4 chunks
+    const size_t vol_b = static_cast<size_t>(b) * C * V * V * V;
+    __nv_bfloat16* dst = cols + static_cast<size_t>(row) * C * p * p * p;
+    for (int i = threadIdx.x; i < per_patch; i += blockDim.x) {
+        const int x4 = i % p4;
+        const int py = (i / p4) % p;
+        const int pz = (i / (p4 * p)) % p;
+        const int c = i / (p4 * p * p);
+        const size_t src = vol_b + ((static_cast<size_t>(c) * V + (gz * p + pz)) * V + (gy * p + py)) * V + gx * p + x4 * 4;
+        const float4 v = *reinterpret_cast<const float4*>(vol + src);
+        uint2 pk;
+        pk.x = pack_bf16(v.x, v.y);
+        pk.y = pack_bf16(v.z, v.w);
+        *reinterpret_cast<uint2*>(dst + static_cast<size_t>(i) * 4) = pk;
+    }
+}
+
+// dst[row_idx[i] or i, :] = src0[src0_rows ? src0_rows[i] : 0, :] + src1[src1_rows ? src1_rows[i] : 0, :]
+__global__ void __launch_bounds__(128)
+fill_rows_kernel(float* __restrict__ dst, const int* __restrict__ row_idx, int D, const float* __restrict__ src0,
+                 const int* __restrict__ src0_rows, const float* __restrict__ src1, const int* __restrict__ src1_rows) {
+    const int i = blockIdx.x;
+    const int r = row_idx ? row_idx[i] : i;
+    const float* a = src0 + static_cast<size_t>(src0_rows ? src0_rows[i] : 0) * D;
+    const float* c = src1 ? src1 + static_cast<size_t>(src1_rows ? src1_rows[i] : 0) * D : nullptr;
+    for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {
+        float4 v = *reinterpret_cast<const float4*>(a + d);
+        if (c) {
+            const float4 w = *reinterpret_cast<const float4*>(c + d);
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+        *reinterpret_cast<float4*>(dst + static_cast<size_t>(r) * D + d) = v;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ row_idx, int D, __nv_bfloat16* __restrict__ dst16,
+                   float* __restrict__ dst32) {
+    const int i = blockIdx.x;
+    const float* a = src + static_cast<size_t>(row_idx ? row_idx[i] : i) * D;
+    for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(a + d);
+        if (dst16) {
+            uint2 pk;
+            pk.x = pack_bf16(v.x, v.y);
+            pk.y = pack_bf16(v.z, v.w);
+            *reinterpret_cast<uint2*>(dst16 + static_cast<size_t>(i) * D + d) = pk;
+        }
+        if (dst32) *reinterpret_cast<float4*>(dst32 + static_cast<size_t>(i) * D + d) = v;
+    }
+}
+
+// out[d] (+)= sum_i src[row_idx[i], d]; grid over column chunks, rows summed in fixed order (deterministic)
+__global__ void __launch_bounds__(128)
+sum_rows_kernel(const float* __restrict__ src, const int* __restrict__ row_idx, int nrows, int D, float* __restrict__ out,
+                int accumulate) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    float s = 0.f;
+    for (int i = 0; i < nrows; ++i) s += src[static_cast<size_t>(row_idx ? row_idx[i] : i) * D + d];
+    out[d] = accumulate ? out[d] + s : s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 master parameters -> flat bf16 shadow, all tensors in one launch
+// ---------------------------------------------------------------------------------------------------------------
+struct CastRecord {
+    unsigned long long src;
+    unsigned long long dst_off;
+    unsigned long long numel;
+};
+constexpr int CAST_CHUNK = 4096;  // elements per work item
+
+__global__ void __launch_bounds__(256)
+cast_params_kernel(const CastRecord* __restrict__ table, int ntensors, __nv_bfloat16* __restrict__ dst) {
+    // blockIdx.y = tensor, blockIdx.x strides over that tensor's chunks
+    const CastRecord rec = table[blockIdx.y];
+    const float* src = reinterpret_cast<const float*>(rec.src);
+    __nv_bfloat16* out = dst + rec.dst_off;
+    const unsigned long long n = rec.numel;
+    const bool vec_ok = ((rec.src & 15ull) == 0) && ((rec.dst_off & 7ull) == 0);
+    for (unsigned long long base = static_cast<unsigned long long>(blockIdx.x) * CAST_CHUNK; base < n;
+         base += static_cast<unsigned long long>(gridDim.x) * CAST_CHUNK) {
+        const unsigned long long end = min(n, base + CAST_CHUNK);
+        if (vec_ok) {
+            for (unsigned long long i = base + threadIdx.x * 8ull; i < end; i += 256ull * 8ull) {
+                if (i + 8 <= end) {
+                    const float4 a = *reinterpret_cast<const float4*>(src + i);
+                    const float4 b = *reinterpret_cast<const float4*>(src + i + 4);
+                    uint4 pk;
+                    pk.x = pack_bf16(a.x, a.y); pk.y = pack_bf16(a.z, a.w);
+                    pk.z = pack_bf16(b.x, b.y); pk.w = pack_bf16(b.z, b.w);
+                    *reinterpret_cast<uint4*>(out + i) = pk;
+                } else {
+                    for (unsigned long long k = i; k < end; ++k) out[k] = __float2bfloat16(src[k]);
+                }
+            }
+        } else {
+            for (unsigned long long i = base + threadIdx.x; i < end; i += 256) out[i] = __float2bfloat16(src[i]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused AdamW (decoupled weight decay, torch.optim.AdamW update order) over a flat buffer
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             __nv_bfloat16* __restrict__ p16, long long n, float lr, float b1, float b2, float eps, float wd, float bc1,
+             float bc2, const float* __restrict__ inv_scale, const float* __restrict__ found_inf) {
+    if (found_inf && *found_inf != 0.f) return;
+    const float is = inv_scale ? *inv_scale : 1.f;
+    const float step_size = lr / bc1;
+    const float inv_sqrt_bc2 = rsqrtf(bc2);
+    for (long long i = (blockIdx.x * 256ll + threadIdx.x) * 4; i < n; i += gridDim.x * 256ll * 4) {
+        if (i + 4 <= n) {
+            float4 pp = *reinterpret_cast<float4*>(p + i);
+            const float4 gg = *reinterpret_cast<const float4*>(g + i);
+            float4 mm = *reinterpret_cast<float4*>(m + i);
+            float4 vv = *reinterpret_cast<float4*>(v + i);
+            float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float gr = ga[k] * is;
+                pa[k] *= (1.f - lr * wd);
+                ma[k] = b1 * ma[k] + (1.f - b1) * gr;
+                va[k] = b2 * va[k] + (1.f - b2) * gr * gr;
+                pa[k] -= step_size * ma[k] / (sqrtf(va[k]) * inv_sqrt_bc2 + eps);
+            }
+            *reinterpret_cast<float4*>(p + i) = pp;
+            *reinterpret_cast<float4*>(m + i) = mm;
+            *reinterpret_cast<float4*>(v + i) = vv;
+            if (p16) {
+                uint2 pk;
+                pk.x = pack_bf16(pp.x, pp.y);
+                pk.y = pack_bf16(pp.z, pp.w);
+                *reinterpret_cast<uint2*>(p16 + i) = pk;
+            }
+        } else {
+            for (long long k = i; k < n; ++k) {
+                const float gr = g[k] * is;
+                float pv = p[k] * (1.f - lr * wd);
+                const float mv = b1 * m[k] + (1.f - b1) * gr;
+                const float vv2 = b2 * v[k] + (1.f - b2) * gr * gr;
+                pv -= step_size * mv / (sqrtf(vv2) * inv_sqrt_bc2 + eps);
+                p[k] = pv; m[k] = mv; v[k] = vv2;
+                if (p16) p16[k] = __float2bfloat16(pv);
+            }
+        }
+    }
+}
+
+}  // namespace vitae
+
+using namespace vitae;
+
+extern "C" int vitae_random_masking(const float* noise, int32_t* ids_shuffle, int32_t* ids_restore, float* mask, int B,
+                                    int L, int len_keep, void* stream) {
+    VITAE_REQUIRE(noise && ids_shuffle && ids_restore && mask, "random_masking: null pointer");
+    VITAE_REQUIRE(B > 0 && L > 0 && L <= 8192 && len_keep >= 0 && len_keep <= L, "random_masking: bad sizes B=%d L=%d keep=%d", B, L, len_keep);
+    int lp = 2;
+    while (lp < L) lp <<= 1;
+    const int threads = std::min(1024, std::max(32, lp / 2));
+    random_masking_kernel<<<B, threads, lp * sizeof(unsigned long long), as_stream(stream)>>>(noise, ids_shuffle, ids_restore, mask, L, lp, len_keep);
+    VITAE_CHECK_LAUNCH("random_masking");
+    return 0;
+}
+
+extern "C" int vitae_im2col_patches(const float* vol, const int32_t* ids_shuffle, void* cols_bf16, int B, int C, int V,
+                                    int p, int L, int keep, void* stream) {
+    VITAE_REQUIRE(vol && ids_shuffle && cols_bf16, "im2col: null pointer");
+    VITAE_REQUIRE(p % 4 == 0 && V % p == 0 && keep > 0, "im2col: need p %% 4 == 0 and V %% p == 0 (V=%d p=%d)", V, p);
+    const int g = V / p;
+    VITAE_REQUIRE(g * g * g == L, "im2col: L=%d does not match (V/p)^3", L);
+    im2col_patches_kernel<<<B * keep, 256, 0, as_stream(stream)>>>(vol, ids_shuffle, static_cast<__nv_bfloat16*>(cols_bf16), C, V, p, g, L, keep);
+    VITAE_CHECK_LAUNCH("im2col_patches");
+    return 0;
+}
+
+extern "C" int vitae_fill_rows(float* dst, const int32_t* row_idx, int nrows, int D, const float* src0,
+                               const int32_t* src0_rows, const float* src1, const int32_t* src1_rows, void* stream) {
+    VITAE_REQUIRE(dst && src0 && nrows >= 0 && D % 4 == 0, "fill_rows: bad arguments");
+    if (nrows == 0) return 0;
+    fill_rows_kernel<<<nrows, 128, 0, as_stream(stream)>>>(dst, row_idx, D, src0, src0_rows, src1, src1_rows);
+    VITAE_CHECK_LAUNCH("fill_rows");
+    return 0;
+}
+
+extern "C" int vitae_gather_rows(const float* src, const int32_t* row_idx, int nrows, int D, void* dst_bf16,
+                                 float* dst_f32, void* stream) {
+    VITAE_REQUIRE(src && (dst_bf16 || dst_f32) && nrows >= 0 && D % 4 == 0, "gather_rows: bad arguments");
+    if (nrows == 0) return 0;
+    gather_rows_kernel<<<nrows, 128, 0, as_stream(stream)>>>(src, row_idx, D, static_cast<__nv_bfloat16*>(dst_bf16), dst_f32);
+    VITAE_CHECK_LAUNCH("gather_rows");
+    return 0;
+}
+
+extern "C" int vitae_sum_rows(const float* src, const int32_t* row_idx, int nrows, int D, float* out, int accumulate,
+                              void* stream) {
+    VITAE_REQUIRE(src && out && nrows >= 0 && D > 0, "sum_rows: bad arguments");
+    sum_rows_kernel<<<ceil_div(D, 128), 128, 0, as_stream(stream)>>>(src, row_idx, nrows, D, out, accumulate);
+    VITAE_CHECK_LAUNCH("sum_rows");
+    return 0;
+}
+
+extern "C" int vitae_cast_params_bf16(const void* table, int ntensors, void* dst_bf16, long long total_elems, void* stream) {
+    VITAE_REQUIRE(table && dst_bf16 && ntensors > 0, "cast_params: bad arguments");
+    // enough x-blocks that the largest tensors are spread over the machine; small tensors exit after one chunk
+    const long long avg = total_elems / ntensors + 1;
+    int bx = static_cast<int>(std::min<long long>(64, std::max<long long>(1, (4 * avg) / CAST_CHUNK)));
+    dim3 grid(bx, ntensors);
+    cast_params_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const CastRecord*>(table), ntensors, static_cast<__nv_bfloat16*>(dst_bf16));
+    VITAE_CHECK_LAUNCH("cast_params");
+    return 0;
+}
+
+extern "C" int vitae_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16,
+                                long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                float bias_corr1, float bias_corr2, const float* inv_scale, const float* found_inf,
+                                void* stream) {
+    VITAE_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0, "adamw: bad arguments");
+    const int blocks = static_cast<int>(std::min<long long>(ceil_div<long long>(n, 1024), 148 * 8));
+    adamw_kernel<<<blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, static_cast<__nv_bfloat16*>(param_bf16), n, lr,
+                                                        beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, inv_scale, found_inf);
+    VITAE_CHECK_LAUNCH("adamw");
+    return 0;
+}

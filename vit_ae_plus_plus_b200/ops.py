@@ -1,0 +1,218 @@
+"""Thin torch-tensor front end over the C ABI (include/vitae_b200.h).  torch is only the allocator / stream
+provider here: every function enqueues one hand-written sm_100a kernel (or a fixed short sequence) on the current
+CUDA stream.  No fallbacks: a non-CUDA tensor or a missing library raises."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import GemmEpilogue, check
+
+_BF16 = torch.bfloat16
+_F32 = torch.float32
+_I32 = torch.int32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise _lib.VitaeError(f"{name}: expected a CUDA tensor (this package has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.VitaeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.VitaeError(f"{name}: expected a contiguous tensor")
+
+
+def gemm_config(M: int, N: int, K: int, n_sm: int = 148):
+    """Heuristic (tile_n, split_k): fill ~1 wave of 148 SMs; split K when the output grid is too small."""
+    tiles_m = (M + 127) // 128
+    num_kb = (K + 63) // 64
+    tile_n = 128
+    if tiles_m * ((N + 127) // 128) < n_sm and N % 64 == 0:
+        tile_n = 64
+    tiles = tiles_m * ((N + tile_n - 1) // tile_n)
+    split = 1
+    if tiles < n_sm // 2 and num_kb >= 8:
+        split = min(max(1, n_sm // tiles), max(1, num_kb // 4), 16)
+    return tile_n, split
+
+
+_gemm_ws = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _gemm_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _gemm_ws[key] = ws
+    return ws
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn_major: bool = False,
+         b_mn_major: bool = False, lda: Optional[int] = None, ldb: Optional[int] = None,
+         bias: Optional[torch.Tensor] = None, addend: Optional[torch.Tensor] = None,
+         add_rows: Optional[torch.Tensor] = None, ldadd: Optional[int] = None,
+         dgelu_src: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None,
+         ld_f32: Optional[int] = None, accumulate: bool = False, out_bf16: Optional[torch.Tensor] = None,
+         out_gelu_bf16: Optional[torch.Tensor] = None, ld_bf16: Optional[int] = None,
+         out_rows: Optional[torch.Tensor] = None, alpha: float = 1.0, alpha_ptr: Optional[torch.Tensor] = None,
+         tile_n: Optional[int] = None, split_k: Optional[int] = None) -> None:
+    """acc[m,n] = sum_k A(m,k) B(n,k) on tcgen05 + fused epilogue; see include/vitae_b200.h."""
+    lib = _lib.load()
+    _req(a, _BF16, "gemm A"); _req(b, _BF16, "gemm B")
+    if lda is None:
+        lda = M if a_mn_major else K
+    if ldb is None:
+        ldb = N if b_mn_major else K
+    ep = GemmEpilogue()
+    ep.alpha = alpha
+    ep.alpha_ptr = _ptr(alpha_ptr)
+    ep.bias = _ptr(bias)
+    ep.addend = _ptr(addend)
+    ep.add_rows = _ptr(add_rows)
+    ep.ldadd = ldadd if ldadd is not None else N
+    ep.dgelu_src = _ptr(dgelu_src)
+    ep.ld_dgelu = N
+    ep.out_f32 = _ptr(out_f32)
+    ep.ld_f32 = ld_f32 if ld_f32 is not None else N
+    ep.accumulate = 1 if accumulate else 0
+    ep.out_bf16 = _ptr(out_bf16)
+    ep.out_gelu_bf16 = _ptr(out_gelu_bf16)
+    ep.ld_bf16 = ld_bf16 if ld_bf16 is not None else N
+    ep.out_rows = _ptr(out_rows)
+    if tile_n is None or split_k is None:
+        tn, sk = gemm_config(M, N, K)
+        tile_n = tn if tile_n is None else tile_n
+        split_k = sk if split_k is None else split_k
+    ws_ptr, ws_bytes = None, 0
+    if split_k > 1:
+        ws_bytes = lib.vitae_gemm_workspace_bytes(M, N, split_k)
+        ws = _workspace(ws_bytes, a.device)
+        ws_ptr = ws.data_ptr()
+    check(lib.vitae_gemm_bf16(a.data_ptr(), lda, int(a_mn_major), b.data_ptr(), ldb, int(b_mn_major), M, N, K,
+                              ctypes.byref(ep), tile_n, split_k, ws_ptr, ws_bytes, _stream()), "vitae_gemm_bf16")
+
+
+def layernorm_fwd(x, gamma, beta, y_bf16, mean, rstd, eps: float, y_f32=None) -> None:
+    lib = _lib.load()
+    _req(x, _F32, "layernorm x")
+    rows, D = x.numel() // x.shape[-1], x.shape[-1]
+    check(lib.vitae_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(y_bf16), _ptr(y_f32),
+                                  _ptr(mean), _ptr(rstd), rows, D, eps, _stream()), "vitae_layernorm_fwd")
+
+
+def layernorm_bwd_blocks(rows: int) -> int:
+    return _lib.load().vitae_layernorm_bwd_blocks(rows)
+
+
+def colsum_blocks(rows: int) -> int:
+    return _lib.load().vitae_colsum_blocks(rows)
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dx_out, dx_out_bf16, partials) -> None:
+    lib = _lib.load()
+    rows, D = x.numel() // x.shape[-1], x.shape[-1]
+    dy16 = dy.data_ptr() if dy.dtype == _BF16 else None
+    dy32 = dy.data_ptr() if dy.dtype == _F32 else None
+    check(lib.vitae_layernorm_bwd(dy16, dy32, x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                  _ptr(dx_in), dx_out.data_ptr(), _ptr(dx_out_bf16), partials.data_ptr(), rows, D,
+                                  _stream()), "vitae_layernorm_bwd")
+
+
+def colsum(inp, rows: int, cols: int, out, workspace, accumulate: bool = False, ld: Optional[int] = None) -> None:
+    lib = _lib.load()
+    in16 = inp.data_ptr() if inp.dtype == _BF16 else None
+    in32 = inp.data_ptr() if inp.dtype == _F32 else None
+    check(lib.vitae_colsum(in16, in32, rows, cols, ld if ld is not None else cols, out.data_ptr(), int(accumulate),
+                           workspace.data_ptr(), _stream()), "vitae_colsum")
+
+
+def attention_fwd(qkv, out, lse, B: int, N: int, H: int, hd: int, scale: float) -> None:
+    lib = _lib.load()
+    _req(qkv, _BF16, "attention qkv")
+    check(lib.vitae_attention_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, hd, scale, _stream()),
+          "vitae_attention_fwd")
+
+
+def attention_bwd(qkv, out, dout, lse, delta, dqkv, B: int, N: int, H: int, hd: int, scale: float) -> None:
+    lib = _lib.load()
+    check(lib.vitae_attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+                                  dqkv.data_ptr(), B, N, H, hd, scale, _stream()), "vitae_attention_bwd")
+
+
+def random_masking(noise, ids_shuffle, ids_restore, mask, len_keep: int) -> None:
+    lib = _lib.load()
+    _req(noise, _F32, "noise")
+    B, L = noise.shape
+    check(lib.vitae_random_masking(noise.data_ptr(), ids_shuffle.data_ptr(), ids_restore.data_ptr(), mask.data_ptr(),
+                                   B, L, len_keep, _stream()), "vitae_random_masking")
+
+
+def im2col_patches(vol, ids_shuffle, cols, p: int, keep: int) -> None:
+    lib = _lib.load()
+    _req(vol, _F32, "volume")
+    B, C, V = vol.shape[0], vol.shape[1], vol.shape[2]
+    L = (V // p) ** 3
+    check(lib.vitae_im2col_patches(vol.data_ptr(), ids_shuffle.data_ptr(), cols.data_ptr(), B, C, V, p, L, keep,
+                                   _stream()), "vitae_im2col_patches")
+
+
+def fill_rows(dst, row_idx, nrows: int, D: int, src0, src0_rows=None, src1=None, src1_rows=None) -> None:
+    lib = _lib.load()
+    check(lib.vitae_fill_rows(dst.data_ptr(), _ptr(row_idx), nrows, D, src0.data_ptr(), _ptr(src0_rows), _ptr(src1),
+                              _ptr(src1_rows), _stream()), "vitae_fill_rows")
+
+
+def gather_rows(src, row_idx, nrows: int, D: int, dst_bf16=None, dst_f32=None) -> None:
+    lib = _lib.load()
+    check(lib.vitae_gather_rows(src.data_ptr(), _ptr(row_idx), nrows, D, _ptr(dst_bf16), _ptr(dst_f32), _stream()),
+          "vitae_gather_rows")
+
+
+def sum_rows(src, row_idx, nrows: int, D: int, out, accumulate: bool = False) -> None:
+    lib = _lib.load()
+    check(lib.vitae_sum_rows(src.data_ptr(), _ptr(row_idx), nrows, D, out.data_ptr(), int(accumulate), _stream()),
+          "vitae_sum_rows")
+
+
+def masked_mse_fwd(pred, vol, mask, patch_sums, loss_out, p: int) -> None:
+    lib = _lib.load()
+    B, C, V = vol.shape[0], vol.shape[1], vol.shape[2]
+    check(lib.vitae_masked_mse_fwd(pred.data_ptr(), int(pred.dtype == _BF16), vol.data_ptr(), mask.data_ptr(),
+                                   patch_sums.data_ptr(), loss_out.data_ptr(), B, C, V, p, _stream()),
+          "vitae_masked_mse_fwd")
+
+
+def masked_mse_bwd(pred, vol, mask, mask_sum, dloss, dpred, p: int) -> None:
+    lib = _lib.load()
+    B, C, V = vol.shape[0], vol.shape[1], vol.shape[2]
+    check(lib.vitae_masked_mse_bwd(pred.data_ptr(), int(pred.dtype == _BF16), vol.data_ptr(), mask.data_ptr(),
+                                   mask_sum.data_ptr(), dloss.data_ptr(), dpred.data_ptr(), B, C, V, p, _stream()),
+          "vitae_masked_mse_bwd")
+
+
+def cast_params_bf16(table, ntensors: int, dst, total: int) -> None:
+    lib = _lib.load()
+    check(lib.vitae_cast_params_bf16(table.data_ptr(), ntensors, dst.data_ptr(), total, _stream()),
+          "vitae_cast_params_bf16")
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, param_bf16, n: int, lr: float, beta1: float, beta2: float,
+               eps: float, weight_decay: float, step: int, inv_scale=None, found_inf=None) -> None:
+    lib = _lib.load()
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    check(lib.vitae_adamw_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                               _ptr(param_bf16), n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, _ptr(inv_scale),
+                               _ptr(found_inf), _stream()), "vitae_adamw_step")

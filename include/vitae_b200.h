@@ -115,6 +115,19 @@ int vitae_attention_bwd(const void* qkv, const void* out, const void* dout, cons
 int vitae_random_masking(const float* noise, int32_t* ids_shuffle, int32_t* ids_restore, float* mask, int B, int L,
                          int len_keep, void* stream);
 
+/* Row maps derived from ids_shuffle that express the reference's cat / gather / repeat token shuffling
+ * (model/vit_autoenc.py:147 keep-gather, :168-170 cls prepend, :184-190 mask tokens + unshuffle + pos) as row
+ * scatters in GEMM epilogues.  Ne = keep+1, Nd = L+1; all outputs int32:
+ *   enc_tok_rows[b*keep+j] = b*Ne+1+j              enc_cls_rows[b] = b*Ne
+ *   pe_pos_rows[b*keep+j]  = 1+ids_shuffle[b,j]    (row of pos_embed added to kept patch j)
+ *   dec_rows_of_enc[b*Ne+t]     = t==0 ? b*Nd : b*Nd+1+ids_shuffle[b,t-1]   (decoder row of encoder token t)
+ *   dec_pos_rows_of_enc[b*Ne+t] = t==0 ? 0    : 1+ids_shuffle[b,t-1]        (row of decoder_pos_embed)
+ *   masked_dec_rows[b*(L-keep)+i] = b*Nd+1+ids_shuffle[b,keep+i], masked_pos_rows[..] = 1+ids_shuffle[b,keep+i] */
+int vitae_build_row_maps(const int32_t* ids_shuffle, int B, int L, int keep, int32_t* enc_tok_rows,
+                         int32_t* enc_cls_rows, int32_t* pe_pos_rows, int32_t* dec_rows_of_enc,
+                         int32_t* dec_pos_rows_of_enc, int32_t* masked_dec_rows, int32_t* masked_pos_rows,
+                         void* stream);
+
 /* Patch gather for the Conv3d(k=s=p) patch embed -- model/vit.py:65,72 + the torch.gather of kept tokens at
  * model/vit_autoenc.py:147: row (b*keep + j) of `cols` (bf16 [B*keep, C*p^3], K order (c,pz,py,px) = conv weight
  * order) is patch ids_shuffle[b, j] of volume b.  vol fp32 [B, C, V, V, V]. */

@@ -79,6 +79,37 @@ im2col_patches_kernel(const float* __restrict__ vol, const int* __restrict__ ids
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Row maps that turn the reference's cat / gather / repeat token shuffling (model/vit_autoenc.py:147,168-170,184-190)
+// into GEMM-epilogue row scatters: everything is a function of ids_shuffle.  Ne = keep+1, Nd = L+1.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+build_row_maps_kernel(const int* __restrict__ ids_shuffle, int B, int L, int keep, int* __restrict__ enc_tok_rows,
+                      int* __restrict__ enc_cls_rows, int* __restrict__ pe_pos_rows, int* __restrict__ dec_rows_of_enc,
+                      int* __restrict__ dec_pos_rows_of_enc, int* __restrict__ masked_dec_rows,
+                      int* __restrict__ masked_pos_rows) {
+    const int Ne = keep + 1, Nd = L + 1, nmask = L - keep;
+    const int total = B * L;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int b = i / L, r = i % L;  // r = rank in the shuffled order
+        const int patch = ids_shuffle[i];
+        if (r < keep) {
+            enc_tok_rows[b * keep + r] = b * Ne + 1 + r;
+            pe_pos_rows[b * keep + r] = 1 + patch;
+            dec_rows_of_enc[b * Ne + 1 + r] = b * Nd + 1 + patch;
+            dec_pos_rows_of_enc[b * Ne + 1 + r] = 1 + patch;
+        } else {
+            masked_dec_rows[b * nmask + (r - keep)] = b * Nd + 1 + patch;
+            masked_pos_rows[b * nmask + (r - keep)] = 1 + patch;
+        }
+        if (r == 0) {
+            enc_cls_rows[b] = b * Ne;
+            dec_rows_of_enc[b * Ne] = b * Nd;
+            dec_pos_rows_of_enc[b * Ne] = 0;
+        }
+    }
+}
+
 // dst[row_idx[i] or i, :] = src0[src0_rows ? src0_rows[i] : 0, :] + src1[src1_rows ? src1_rows[i] : 0, :]
 __global__ void __launch_bounds__(128)
 fill_rows_kernel(float* __restrict__ dst, const int* __restrict__ row_idx, int D, const float* __restrict__ src0,
@@ -227,6 +258,20 @@ extern "C" int vitae_random_masking(const float* noise, int32_t* ids_shuffle, in
     const int threads = std::min(1024, std::max(32, lp / 2));
     random_masking_kernel<<<B, threads, lp * sizeof(unsigned long long), as_stream(stream)>>>(noise, ids_shuffle, ids_restore, mask, L, lp, len_keep);
     VITAE_CHECK_LAUNCH("random_masking");
+    return 0;
+}
+
+extern "C" int vitae_build_row_maps(const int32_t* ids_shuffle, int B, int L, int keep, int32_t* enc_tok_rows,
+                                    int32_t* enc_cls_rows, int32_t* pe_pos_rows, int32_t* dec_rows_of_enc,
+                                    int32_t* dec_pos_rows_of_enc, int32_t* masked_dec_rows, int32_t* masked_pos_rows,
+                                    void* stream) {
+    VITAE_REQUIRE(ids_shuffle && enc_tok_rows && enc_cls_rows && pe_pos_rows && dec_rows_of_enc && dec_pos_rows_of_enc &&
+                      masked_dec_rows && masked_pos_rows, "build_row_maps: null pointer");
+    VITAE_REQUIRE(B > 0 && L > 0 && keep > 0 && keep <= L, "build_row_maps: bad sizes B=%d L=%d keep=%d", B, L, keep);
+    const int blocks = std::min(ceil_div(B * L, 256), 148);
+    build_row_maps_kernel<<<blocks, 256, 0, as_stream(stream)>>>(ids_shuffle, B, L, keep, enc_tok_rows, enc_cls_rows, pe_pos_rows,
+                                                                 dec_rows_of_enc, dec_pos_rows_of_enc, masked_dec_rows, masked_pos_rows);
+    VITAE_CHECK_LAUNCH("build_row_maps");
     return 0;
 }
 

@@ -159,6 +159,26 @@ def random_masking(noise, ids_shuffle, ids_restore, mask, len_keep: int) -> None
                                    B, L, len_keep, _stream()), "vitae_random_masking")
 
 
+def build_row_maps(ids_shuffle, keep: int, out: Optional[dict] = None) -> dict:
+    """Row maps of include/vitae_b200.h::vitae_build_row_maps; allocates them unless ``out`` holds the buffers."""
+    lib = _lib.load()
+    _req(ids_shuffle, _I32, "ids_shuffle")
+    B, L = ids_shuffle.shape
+    Ne = keep + 1
+    if out is None:
+        dev = ids_shuffle.device
+        sizes = {"enc_tok_rows": B * keep, "enc_cls_rows": B, "pe_pos_rows": B * keep, "dec_rows_of_enc": B * Ne,
+                 "dec_pos_rows_of_enc": B * Ne, "masked_dec_rows": max(1, B * (L - keep)),
+                 "masked_pos_rows": max(1, B * (L - keep))}
+        out = {k: torch.empty(n, dtype=_I32, device=dev) for k, n in sizes.items()}
+    check(lib.vitae_build_row_maps(ids_shuffle.data_ptr(), B, L, keep, out["enc_tok_rows"].data_ptr(),
+                                   out["enc_cls_rows"].data_ptr(), out["pe_pos_rows"].data_ptr(),
+                                   out["dec_rows_of_enc"].data_ptr(), out["dec_pos_rows_of_enc"].data_ptr(),
+                                   out["masked_dec_rows"].data_ptr(), out["masked_pos_rows"].data_ptr(), _stream()),
+          "vitae_build_row_maps")
+    return out
+
+
 def im2col_patches(vol, ids_shuffle, cols, p: int, keep: int) -> None:
     lib = _lib.load()
     _req(vol, _F32, "volume")

@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Benchmark of the 3D ViT masked-autoencoder training step (BASELINE.json metric: volumes/sec, ViT-AE 128^3).
+
+  python bench.py --gpus N --steps K --warmup W            own arm (B200 kernels), one JSON line on rank 0
+  python bench.py --impl reference --gpus N --steps K ...  reference arm: the reference algorithm on the host CPU cores
+
+A step = forward + backward + AdamW update of one batch of synthetic BRaTS-shaped volumes (randn, z-scored-MRI-like)
+through the public module API.  `value` is measured with inputs resident in HBM; `e2e` copies every step's batch from
+pinned host memory inside the timed region and reads the loss back every step.  N>1: one process per GPU (torchrun),
+data parallel over volumes (weak scaling), gradient all-reduce over NCCL.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from functools import partial
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]/[2]: ViT-B/16 autoenc on 128^3 x 4, batch 4 per GPU
+    "vit_base_128": dict(model="mae_vit_base_patch16", volume_size=128, in_channels=4, patch_size=16, oracle="vit_base_128"),
+    # configs[3]: ViT-L/16 autoenc on 96^3 x 4
+    "vit_large_96": dict(model="mae_vit_large_patch16", volume_size=96, in_channels=4, patch_size=16, oracle="vit_large_96"),
+}
+METRIC = "training volumes/sec (fwd+bwd+AdamW), ViT-AE on synthetic 128^3x4 volumes"
+UNIT = "volumes/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="vit_base_128", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=4, help="volumes per GPU per step")
+    ap.add_argument("--mask-ratio", type=float, default=0.75)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="do not use CUDA graphs for the step")
+    ap.add_argument("--cpu-sample-steps", type=int, default=4)
+    return ap.parse_args()
+
+
+def model_args(w, a):
+    return argparse.Namespace(model=w["model"], volume_size=w["volume_size"], in_channels=w["in_channels"],
+                              patch_size=w["patch_size"], perceptual_weight=0, use_imagenet=False,
+                              mask_ratio=a.mask_ratio, accum_iter=1)
+
+
+def workload_name(w, a, n):
+    return (f"{w['model']} {w['volume_size']}^3x{w['in_channels']} patch {w['patch_size']}, batch {a.batch}/GPU x {n} GPU, "
+            f"mask {a.mask_ratio}, fwd+bwd+AdamW(betas .9/.95, wd .05)+GradScaler")
+
+
+# ---------------------------------------------------------------------------------------------------- CPU side
+def cpu_reference_rate(workload: dict, mask_ratio: float, batch: int, steps: int, warmup: int, threads: int):
+    """The reference algorithm (oracle/mae_oracle.py: functional restatement of model/vit_autoenc.py on torch CPU fp32,
+    pinned to the unmodified reference by tests/golden) forward + backward + AdamW on the host cores."""
+    from oracle import mae_oracle as O
+    torch.set_num_threads(threads)
+    cfg = O.CONFIGS[workload["oracle"]]
+    P = O.init_params(cfg, 0)
+    leaves = {k: v.clone().requires_grad_(k not in O.FROZEN) for k, v in P.items()}
+    opt = torch.optim.AdamW(O.weight_decay_groups(list(leaves.items()), 0.05), lr=1e-4, betas=(0.9, 0.95))
+    V, C = cfg["volume_size"], cfg["in_chans"]
+    _, L, _ = O.geometry(cfg)
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, C, V, V, V, generator=gen)
+    times = []
+    for it in range(warmup + steps):
+        noise = torch.rand(batch, L, generator=gen)
+        t0 = time.perf_counter()
+        losses, _, _, _ = O.forward(x, leaves, cfg, mask_ratio, noise, 0.0, with_edge=False)
+        opt.zero_grad(set_to_none=True)
+        losses[0].backward()
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return batch * len(times) / total, 1000.0 * total / len(times)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[a.workload]
+    cores = os.cpu_count() or 1
+    sample_batch = 1
+    rate, ms = cpu_reference_rate(w, a.mask_ratio, sample_batch, a.steps, max(1, min(a.warmup, 2)), cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(w, a, a.gpus),
+                   "note": "reference algorithm on host CPU cores; each step = 1 volume (bounded sample of the batch)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{a.steps} steps x {sample_batch} volume, torch CPU fp32, {cores} threads"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------- GPU side
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.tmp.read().splitlines():
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.tmp.name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                   "power_w_max": max(power)}
+        return out
+
+
+def run_ours(a):
+    import torch.distributed as dist
+    from vit_ae_plus_plus_b200 import _lib, ops
+    from vit_ae_plus_plus_b200.model import model_factory
+    from vit_ae_plus_plus_b200.utils import misc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == a.gpus or world == 1, f"--gpus {a.gpus} but WORLD_SIZE={world}"
+    lib = _lib.load()
+
+    w = WORKLOADS[a.workload]
+    margs = model_args(w, a)
+    torch.manual_seed(42 + rank)                                    # k_fold_cross_valid_combined_brats.py:57,87-89
+    model = model_factory.get_models("autoenc", margs).to(dev)
+    model.train(True)
+    model.pred_dtype = torch.float32
+    if hasattr(model, "use_cuda_graph"):
+        model.use_cuda_graph = not a.no_graph
+    eff_batch = a.batch * world
+    lr = 1.5e-4 * eff_batch / 256                                   # blr * eff_batch / 256 (brats.py:157-160)
+    opt = torch.optim.AdamW(misc.add_weight_decay(model, 0.05), lr=lr, betas=(0.9, 0.95))
+    scaler = misc.NativeScalerWithGradNormCount()
+    V, C, B = w["volume_size"], w["in_channels"], a.batch
+    n_pool = 3
+    pool = [torch.randn(B, C, V, V, V, device=dev) for _ in range(n_pool)]
+
+    def step(x):
+        losses, _pred, _mask = model(x, mask_ratio=a.mask_ratio, edge_map_weight=0)
+        scaler(losses[0], opt, parameters=model.parameters(), update_grad=True)
+        opt.zero_grad()
+        return losses[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM
+    for i in range(a.warmup):
+        step(pool[i % n_pool])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.vitae_launch_count() + getattr(model, "graph_replayed_launches", 0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        last = step(pool[i % n_pool])
+    e1.record()
+    barrier()
+    launches = lib.vitae_launch_count() + getattr(model, "graph_replayed_launches", 0) - n0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    value = eff_batch * a.steps / (ms_total / 1e3)
+    final_loss = last.item()
+
+    # ---- e2e: host buffers, H2D of the batch and D2H of the loss every step, through the same public calls
+    e2e = None
+    if not a.no_e2e:
+        host = [torch.randn(B, C, V, V, V).pin_memory() for _ in range(2)]
+        for i in range(2):
+            step(host[i % 2].to(dev, non_blocking=True)).item()
+        barrier()
+        e0.record()
+        for i in range(a.steps):
+            x = host[i % 2].to(dev, non_blocking=True)
+            step(x).item()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": eff_batch * a.steps / (t.item() / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": host[0].numel() * 4, "d2h_bytes_per_step": 4}
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM): replay the step's GEMM launches alone, CUDA events
+    roofline = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained"
+        eng = model.engine()
+        x = pool[0]
+        with torch.no_grad(), ops.record_gemms() as rec:
+            pl = eng.forward(x, torch.rand(B, eng.L, device=dev), int(eng.L * (1 - a.mask_ratio)), pred_f32=True)
+            eng.backward(pl, torch.ones(1, device=dev), accumulate=True)
+        for _ in range(3):
+            rec.replay()
+        torch.cuda.synchronize()
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            rec.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        gemm_ms = e0.elapsed_time(e1) / reps
+        achieved = rec.flops / (gemm_ms / 1e3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": achieved, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                    "launches_per_step": len(rec.calls), "avg_launch_us": 1e3 * gemm_ms / len(rec.calls),
+                    "gemm_ms_per_step": gemm_ms, "gemm_flops_per_step": rec.flops, "peak_source": peak_src}
+
+    # ---- CPU baseline (rank 0, bounded sample)
+    cpu = None
+    if rank == 0 and not a.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        rate, _ = cpu_reference_rate(w, a.mask_ratio, 1, a.cpu_sample_steps, 1, cores)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{a.cpu_sample_steps} steps x 1 volume of the same workload (oracle: reference algorithm, torch CPU fp32)"}
+
+    if rank == 0:
+        from oracle import mae_oracle as O
+        f_fwd, f_step = O.flops_per_volume(O.CONFIGS[w["oracle"]], a.mask_ratio, kept_only_embed=True)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(w, a, world), "per_gpu_batch": B, "global_batch": eff_batch,
+                       "l2": "working set (weights+grads+Adam state 2.4 GB, activations, 3 rotating input batches) >> 126 MB L2",
+                       "parallelism": f"dp{world}", "cuda_graph": bool(getattr(model, "use_cuda_graph", False)),
+                       "algorithmic_gflop_per_volume": f_step / 1e9,
+                       "step_tflops": value * f_step / 1e12},
+            "final_loss": final_loss, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

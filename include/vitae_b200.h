@@ -31,6 +31,8 @@ int vitae_abi_version(void);
 const char* vitae_last_error(void);
 /* 0 when the current device is compute capability 10.x (B200); negative otherwise. */
 int vitae_check_device(void);
+/* Number of kernels this library has enqueued in this process (diagnostic; bench.py's gpu_launches). */
+long long vitae_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Dense contraction on the 5th-gen tensor cores (tcgen05.mma, TMA-staged 128B-swizzled tiles, TMEM accumulator).

@@ -42,6 +42,7 @@ SIGNATURES = {
     "vitae_abi_version": (c_int, []),
     "vitae_last_error": (c_char_p, []),
     "vitae_check_device": (c_int, []),
+    "vitae_launch_count": (c_longlong, []),
     "vitae_gemm_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                 POINTER(GemmEpilogue), c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "vitae_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

@@ -3,6 +3,7 @@
 
 namespace vitae {
 static thread_local char g_err[512] = "";
+std::atomic<long long> g_launch_count{0};
 int set_error(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -14,6 +15,7 @@ int set_error(int code, const char* fmt, ...) {
 
 extern "C" int vitae_abi_version(void) { return VITAE_ABI_VERSION; }
 extern "C" const char* vitae_last_error(void) { return vitae::g_err; }
+extern "C" long long vitae_launch_count(void) { return vitae::g_launch_count.load(std::memory_order_relaxed); }
 extern "C" int vitae_check_device(void) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);

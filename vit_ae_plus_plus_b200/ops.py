@@ -48,6 +48,31 @@ def gemm_config(M: int, N: int, K: int, n_sm: int = 148):
 
 
 _gemm_ws = {}
+_gemm_log = None   # when a list: every gemm() call appends (flops, closure) -- bench.py's per-kernel roofline replay
+
+
+class record_gemms:
+    """Context manager: records the GEMM launches made inside it so that they can be replayed in isolation."""
+
+    def __init__(self):
+        self.calls = []
+
+    def __enter__(self):
+        global _gemm_log
+        _gemm_log = self.calls
+        return self
+
+    def __exit__(self, *exc):
+        global _gemm_log
+        _gemm_log = None
+
+    @property
+    def flops(self) -> float:
+        return float(sum(f for f, _ in self.calls))
+
+    def replay(self) -> None:
+        for _, fn in self.calls:
+            fn()
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
@@ -100,8 +125,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn_major
         ws_bytes = lib.vitae_gemm_workspace_bytes(M, N, split_k)
         ws = _workspace(ws_bytes, a.device)
         ws_ptr = ws.data_ptr()
-    check(lib.vitae_gemm_bf16(a.data_ptr(), lda, int(a_mn_major), b.data_ptr(), ldb, int(b_mn_major), M, N, K,
-                              ctypes.byref(ep), tile_n, split_k, ws_ptr, ws_bytes, _stream()), "vitae_gemm_bf16")
+    def launch():
+        check(lib.vitae_gemm_bf16(a.data_ptr(), lda, int(a_mn_major), b.data_ptr(), ldb, int(b_mn_major), M, N, K,
+                                  ctypes.byref(ep), tile_n, split_k, ws_ptr, ws_bytes, _stream()), "vitae_gemm_bf16")
+    launch()
+    if _gemm_log is not None:
+        _gemm_log.append((2.0 * M * N * K, launch))
 
 
 def layernorm_fwd(x, gamma, beta, y_bf16, mean, rstd, eps: float, y_f32=None) -> None:

@@ -1,0 +1,198 @@
+"""The pieces of the reference's ``utils/misc.py`` that the MAE pre-training loop touches, restated for a loop that does
+not synchronise the device every step: windowed meters (misc.py:24-100), the iteration logger (:102-167), the
+GradScaler wrapper the k-fold scripts construct (:251-277), the gradient norm (:280-292), the scalar all-reduce
+(:332-340) and the timm-0.5.4 weight-decay grouping used at the optimizer call site
+(k_fold_cross_valid_combined_brats.py:168).  Checkpoint helpers, SLURM / OpenMPI launch parsing and the print patch are
+glue outside this package's path: use the reference's own ``utils.misc`` for those."""
+from __future__ import annotations
+
+import datetime
+import time
+from collections import defaultdict, deque
+
+import torch
+import torch.distributed as dist
+
+
+def is_dist_avail_and_initialized() -> bool:
+    return dist.is_available() and dist.is_initialized()
+
+
+def get_world_size() -> int:
+    return dist.get_world_size() if is_dist_avail_and_initialized() else 1
+
+
+def get_rank() -> int:
+    return dist.get_rank() if is_dist_avail_and_initialized() else 0
+
+
+def is_main_process() -> bool:
+    return get_rank() == 0
+
+
+class SmoothedValue:
+    """Window median / mean plus the global average of a scalar series (reference misc.py:24-84)."""
+
+    def __init__(self, window_size=20, fmt=None):
+        self.fmt = fmt or "{median:.4f} ({global_avg:.4f})"
+        self.deque = deque(maxlen=window_size)
+        self.total = 0.0
+        self.count = 0
+
+    def update(self, value, n=1):
+        self.deque.append(value)
+        self.count += n
+        self.total += value * n
+
+    def synchronize_between_processes(self):
+        """Sums count / total over ranks (the window is left rank-local, like the reference)."""
+        if not is_dist_avail_and_initialized():
+            return
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([self.count, self.total], dtype=torch.float64, device=dev)
+        dist.barrier()
+        dist.all_reduce(t)
+        self.count, self.total = int(t[0].item()), t[1].item()
+
+    @property
+    def median(self):
+        return torch.tensor(list(self.deque)).median().item()
+
+    @property
+    def avg(self):
+        return torch.tensor(list(self.deque), dtype=torch.float32).mean().item()
+
+    @property
+    def global_avg(self):
+        return self.total / self.count
+
+    @property
+    def max(self):
+        return max(self.deque)
+
+    @property
+    def value(self):
+        return self.deque[-1]
+
+    def __str__(self):
+        return self.fmt.format(median=self.median, avg=self.avg, global_avg=self.global_avg, max=self.max,
+                               value=self.value)
+
+
+class MetricLogger:
+    def __init__(self, delimiter="\t"):
+        self.meters = defaultdict(SmoothedValue)
+        self.delimiter = delimiter
+
+    def update(self, **kwargs):
+        for name, v in kwargs.items():
+            if v is None:
+                continue
+            if isinstance(v, torch.Tensor):
+                v = v.item()
+            assert isinstance(v, (float, int))
+            self.meters[name].update(v)
+
+    def __getattr__(self, attr):
+        meters = self.__dict__.get("meters", {})
+        if attr in meters:
+            return meters[attr]
+        raise AttributeError(f"'{type(self).__name__}' object has no attribute '{attr}'")
+
+    def __str__(self):
+        return self.delimiter.join(f"{name}: {meter}" for name, meter in self.meters.items())
+
+    def synchronize_between_processes(self):
+        for meter in self.meters.values():
+            meter.synchronize_between_processes()
+
+    def add_meter(self, name, meter):
+        self.meters[name] = meter
+
+    def log_every(self, iterable, print_freq, header=None, before_print=None):
+        """Yields from ``iterable``; prints meters / eta / iteration time every ``print_freq`` items.  ``before_print`` is
+        called just before a line is printed (our loop uses it to flush its deferred device scalars)."""
+        header = header or ""
+        n = len(iterable)
+        iter_time, data_time = SmoothedValue(fmt="{avg:.4f}"), SmoothedValue(fmt="{avg:.4f}")
+        width = len(str(n))
+        start = end = time.time()
+        for i, obj in enumerate(iterable):
+            data_time.update(time.time() - end)
+            yield obj
+            iter_time.update(time.time() - end)
+            if i % print_freq == 0 or i == n - 1:
+                if before_print is not None:
+                    before_print()
+                eta = str(datetime.timedelta(seconds=int(iter_time.global_avg * (n - i))))
+                parts = [header, f"[{i:{width}d}/{n}]", f"eta: {eta}", str(self), f"time: {iter_time}", f"data: {data_time}"]
+                if torch.cuda.is_available():
+                    parts.append(f"max mem: {torch.cuda.max_memory_allocated() / 2 ** 20:.0f}")
+                print(self.delimiter.join(parts))
+            end = time.time()
+        total = time.time() - start
+        print(f"{header} Total time: {datetime.timedelta(seconds=int(total))} ({total / max(n, 1):.4f} s / it)")
+
+
+def get_grad_norm_(parameters, norm_type: float = 2.0) -> torch.Tensor:
+    """Global gradient norm (reference misc.py:280-292), one fused multi-tensor reduction instead of a launch per tensor."""
+    if isinstance(parameters, torch.Tensor):
+        parameters = [parameters]
+    grads = [p.grad.detach() for p in parameters if p.grad is not None]
+    if not grads:
+        return torch.tensor(0.)
+    if norm_type == float("inf"):
+        return torch.stack([g.abs().max() for g in grads]).max()
+    return torch.linalg.vector_norm(torch.stack(torch._foreach_norm(grads, norm_type)), norm_type)
+
+
+class NativeScalerWithGradNormCount:
+    """Same call contract as the reference's wrapper (misc.py:251-277): scale -> backward -> (unscale, norm | clip,
+    step, update) when ``update_grad``; returns the gradient norm or None."""
+    state_dict_key = "amp_scaler"
+
+    def __init__(self):
+        self._scaler = torch.amp.GradScaler("cuda")
+
+    def __call__(self, loss, optimizer, clip_grad=None, parameters=None, create_graph=False, update_grad=True):
+        self._scaler.scale(loss).backward(create_graph=create_graph)
+        if not update_grad:
+            return None
+        self._scaler.unscale_(optimizer)
+        if clip_grad is not None:
+            assert parameters is not None
+            norm = torch.nn.utils.clip_grad_norm_(parameters, clip_grad)
+        else:
+            norm = get_grad_norm_(parameters)
+        self._scaler.step(optimizer)
+        self._scaler.update()
+        return norm
+
+    def state_dict(self):
+        return self._scaler.state_dict()
+
+    def load_state_dict(self, state_dict):
+        self._scaler.load_state_dict(state_dict)
+
+
+def all_reduce_mean(x):
+    """Mean over ranks of a python scalar or 0-dim tensor (reference misc.py:332-340)."""
+    world = get_world_size()
+    if world == 1:
+        return x
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.as_tensor(x, dtype=torch.float32).detach().to(dev).clone()
+    dist.all_reduce(t)
+    return (t / world).item()
+
+
+def add_weight_decay(model, weight_decay=1e-5, skip_list=()):
+    """timm 0.5.4 ``optim_factory.add_weight_decay`` semantics, as called at k_fold_cross_valid_combined_brats.py:168:
+    frozen parameters are skipped; 1-D tensors, ``.bias`` and names in ``skip_list`` get no decay; everything else
+    (including the 3-D cls / mask tokens) is decayed."""
+    decay, no_decay = [], []
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        (no_decay if (p.ndim == 1 or name.endswith(".bias") or name in skip_list) else decay).append(p)
+    return [{"params": no_decay, "weight_decay": 0.}, {"params": decay, "weight_decay": weight_decay}]

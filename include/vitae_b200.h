@@ -86,18 +86,25 @@ size_t vitae_gemm_workspace_bytes(int M, int N, int split_k);
 int vitae_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
                         float* mean, float* rstd, int rows, int D, float eps, void* stream);
 /* dx_out = (dx_in ? dx_in : 0) + LN'(dy); dy is bf16 (dy_bf16) or fp32 (dy_f32); also emits a bf16 copy of dx_out
- * (operand of the next dgrad/wgrad GEMM) when dx_out_bf16 != NULL.  dgamma/dbeta partial sums go to
- * partials [2, nblocks, D] (nblocks = vitae_layernorm_bwd_blocks(rows)); reduce them with vitae_colsum. */
+ * (operand of the next dgrad/wgrad GEMM) when dx_out_bf16 != NULL.  Per-block partial sums go to
+ * partials [3, nblocks, D] (nblocks = vitae_layernorm_bwd_blocks(rows)): [0] dgamma, [1] dbeta, [2] column sums of
+ * dx_out (= gradient of the bias that was added to this residual stream: proj.bias / fc2.bias, model/vit.py:142-143).
+ * Finish them with ONE vitae_reduce_partials launch. */
 int vitae_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* gamma,
                         const float* mean, const float* rstd, const float* dx_in, float* dx_out, void* dx_out_bf16,
                         float* partials, int rows, int D, void* stream);
 int vitae_layernorm_bwd_blocks(int rows);
+/* out_k[c] = (accumulate ? out_k[c] : 0) + sum_blk partials[k][blk][c] for k = 0..2; NULL outputs are skipped. */
+int vitae_reduce_partials(const float* partials, int nblk, int D, float* out0, float* out1, float* out2,
+                          int accumulate, void* stream);
 
-/* Column sums: out[c] = (accumulate ? out[c] : 0) + sum_r in[r*ld + c]  (bias gradients; LN partial reduction).
- * Exactly one of in_bf16 / in_f32 is non-NULL.  workspace: fp32 [vitae_colsum_blocks(rows) * cols]. */
+/* Column sums in one launch: out[c] = (accumulate ? out[c] : 0) + sum_r in[r*ld + c]  (bias gradients of
+ * nn.Linear, model/vit.py:84-86,107-109).  Exactly one of in_bf16 / in_f32 is non-NULL; cols % 8 == 0, ld % 8 == 0.
+ * workspace: vitae_colsum_workspace_bytes(rows, cols) bytes, ZERO-FILLED before its first use (ticket counters;
+ * every call leaves them zero again) and not shared by calls that may run concurrently.  Deterministic. */
 int vitae_colsum(const void* in_bf16, const float* in_f32, int rows, int cols, int ld, float* out, int accumulate,
-                 float* workspace, void* stream);
-int vitae_colsum_blocks(int rows);
+                 void* workspace, void* stream);
+size_t vitae_colsum_workspace_bytes(int rows, int cols);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Fused multi-head self-attention, flash-style (scores never leave the SM) -- model/vit.py:112-121:
@@ -172,6 +179,24 @@ int vitae_cast_params_bf16(const void* table, int ntensors, void* dst_bf16, long
 int vitae_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16,
                      long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
                      float bias_corr1, float bias_corr2, const float* inv_scale, const float* found_inf, void* stream);
+
+/* Optimizer step over the flat buffers in three launches, replacing GradScaler.unscale_ /
+ * get_grad_norm_ / GradScaler.step(AdamW) / GradScaler.update (utils/misc.py:257-292) and torch.optim.AdamW built at
+ * k_fold_cross_valid_combined_brats.py:168-169.
+ * ctl: device fp32[8] = {[0] loss scale, [1] growth tracker, [2] found_inf of this step, [3] 1/scale used by this
+ * step, [4] unscaled global gradient L2 norm, [5] optimizer steps taken (skipped steps do not count)}.
+ * vitae_optim_prepare: one pass over grad -> ctl[2..4]; then GradScaler.update on ctl[0..1] (use_scaler != 0) and
+ * ctl[5] += 1 unless the step is skipped.  workspace: vitae_optim_workspace_bytes() bytes.
+ * vitae_adamw_flat: AdamW over [0, n) (n % 64 == 0); group_of_chunk[i >> 6] = parameter group of element i
+ * (>= ngroups: frozen / padding, left untouched); hyper: HOST fp32 [ngroups][8] = {lr, beta1, beta2, eps,
+ * weight_decay, 0, 0, 0}, copied into the launch parameters during the call (ngroups <= 8); bias corrections use ctl[5]; the step is skipped when ctl[2] != 0; also writes the bf16
+ * shadow param_bf16 (GEMM operands) when non-NULL. */
+int vitae_optim_prepare(const float* grad, long long n, float* ctl, float* workspace, float growth_factor,
+                        float backoff_factor, int growth_interval, int use_scaler, void* stream);
+size_t vitae_optim_workspace_bytes(void);
+int vitae_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16,
+                     long long n, const unsigned char* group_of_chunk, const float* hyper, int ngroups,
+                     const float* ctl, void* stream);
 
 #ifdef __cplusplus
 }

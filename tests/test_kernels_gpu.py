@@ -44,20 +44,23 @@ def test_layernorm_fwd_bwd(rows, D):
     assert _rel(y16.float().cpu(), y_ref.detach()) < 1e-2
 
     nb = ops.layernorm_bwd_blocks(rows)
-    partials = torch.empty(2, nb, D, device=DEV)
+    partials = torch.empty(3, nb, D, device=DEV)
     dx = torch.empty(rows, D, device=DEV)
     dx16 = torch.empty(rows, D, device=DEV, dtype=torch.bfloat16)
     for dyt, tol in ((dy.to(DEV), 2e-5), (dy.to(DEV).bfloat16(), 1e-2)):
         ops.layernorm_bwd(dyt, xd, gd, mean, rstd, dres.to(DEV), dx, dx16, partials)
-        ws = torch.empty(ops.colsum_blocks(nb) * D, device=DEV)
         dgamma = torch.empty(D, device=DEV)
-        dbeta = torch.empty(D, device=DEV)
-        ops.colsum(partials[0], nb, D, dgamma, ws)
-        ops.colsum(partials[1], nb, D, dbeta, ws)
+        dbeta = torch.full((D,), 3.0, device=DEV)
+        dbias = torch.empty(D, device=DEV)
+        ops.reduce_partials(partials, nb, D, dgamma, None, dbias)                 # NULL outputs are skipped
+        ops.reduce_partials(partials, nb, D, None, dbeta, None, accumulate=True)  # accumulate onto 3.0
         assert _rel(dx.cpu(), xr.grad + dres) < tol
         assert _rel(dx16.float().cpu(), xr.grad + dres) < 1e-2
         assert _rel(dgamma.cpu(), gr.grad) < max(tol, 1e-4)
-        assert _rel(dbeta.cpu(), br.grad) < max(tol, 1e-4)
+        assert _rel(dbeta.cpu() - 3.0, br.grad) < max(tol, 1e-4)
+        # third partial = column sums of dx_out = gradient of a bias added to the residual stream (vit.py:142-143)
+        ref_cs = (xr.grad + dres).double().sum(0)
+        assert (dbias.cpu().double() - ref_cs).abs().max().item() < max(tol, 1e-4) * (ref_cs.abs().max().item() + math.sqrt(rows))
     # dx_in = None
     ops.layernorm_bwd(dy.to(DEV), xd, gd, mean, rstd, None, dx, None, partials)
     assert _rel(dx.cpu(), xr.grad) < 2e-5
@@ -69,12 +72,26 @@ def test_colsum(rows, cols, dtype):
     from vit_ae_plus_plus_b200 import ops
     x = torch.randn(rows, cols, device=DEV).to(dtype)
     out = torch.full((cols,), 2.0, device=DEV)
-    ws = torch.empty(ops.colsum_blocks(rows) * cols, device=DEV)
+    ws = torch.zeros(ops.colsum_workspace_bytes(rows, cols), dtype=torch.uint8, device=DEV)
     ops.colsum(x, rows, cols, out, ws, accumulate=True)
     ref = 2.0 + x.double().sum(0)
     assert (out.double() - ref).abs().max().item() < 1e-4 * math.sqrt(rows) + 1e-5
-    ops.colsum(x, rows, cols, out, ws)
-    assert (out.double() - (ref - 2.0)).abs().max().item() < 1e-4 * math.sqrt(rows) + 1e-5
+    first = None
+    for _ in range(3):      # the ticket counters reset themselves; the slice order is fixed -> bit-identical reruns
+        ops.colsum(x, rows, cols, out, ws)
+        assert (out.double() - (ref - 2.0)).abs().max().item() < 1e-4 * math.sqrt(rows) + 1e-5
+        first = out.clone() if first is None else first
+        assert torch.equal(out, first)
+
+
+def test_colsum_strided_rows():
+    """ld > cols: column sums of a column block of a wider matrix."""
+    from vit_ae_plus_plus_b200 import ops
+    x = torch.randn(300, 512, device=DEV).bfloat16()
+    out = torch.empty(128, device=DEV)
+    ws = torch.zeros(ops.colsum_workspace_bytes(300, 128), dtype=torch.uint8, device=DEV)
+    ops.colsum(x[:, 256:], 300, 128, out, ws, ld=512)
+    assert (out.double() - x[:, 256:384].double().sum(0)).abs().max().item() < 2e-3
 
 
 # ------------------------------------------------------------------------------------------------ attention

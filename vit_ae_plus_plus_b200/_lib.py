@@ -50,8 +50,9 @@ SIGNATURES = {
                                     c_float, c_void_p]),
     "vitae_layernorm_bwd": (c_int, [c_void_p] * 10 + [c_int, c_int, c_void_p]),
     "vitae_layernorm_bwd_blocks": (c_int, [c_int]),
+    "vitae_reduce_partials": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "vitae_colsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
-    "vitae_colsum_blocks": (c_int, [c_int]),
+    "vitae_colsum_workspace_bytes": (c_size_t, [c_int, c_int]),
     "vitae_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "vitae_attention_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "vitae_random_masking": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -67,6 +68,10 @@ SIGNATURES = {
     "vitae_cast_params_bf16": (c_int, [c_void_p, c_int, c_void_p, c_longlong, c_void_p]),
     "vitae_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float,
                                  c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "vitae_optim_prepare": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_float, c_float, c_int, c_int, c_void_p]),
+    "vitae_optim_workspace_bytes": (c_size_t, []),
+    "vitae_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_int,
+                                 c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -6,8 +6,8 @@
 namespace vitae {
 
 constexpr int LN_WARPS = 8;        // rows per CTA iteration
-constexpr int LN_MAX_VEC = 8;      // float4 per lane -> D <= 1024
 constexpr int LN_BWD_MAX_BLOCKS = 148;
+// kernels are templated on LN_MAX_VEC = float4 per lane (D <= 128 * LN_MAX_VEC): registers follow the actual width
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -15,7 +15,8 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// x fp32 [rows, D] -> y (bf16 and/or fp32), mean, rstd.  D % 4 == 0, D <= 1024.
+// x fp32 [rows, D] -> y (bf16 and/or fp32), mean, rstd.  D % 4 == 0, D <= 128 * LN_MAX_VEC.
+template <int LN_MAX_VEC>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      __nv_bfloat16* __restrict__ y16, float* __restrict__ y32, float* __restrict__ mean,
@@ -73,7 +74,9 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 }
 
 // dx_out = dx_in + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
-// partials[0][blk][:] += dy * xhat (dgamma), partials[1][blk][:] += dy (dbeta)
+// partials[0][blk][:] = sum dy * xhat (dgamma), partials[1][blk][:] = sum dy (dbeta),
+// partials[2][blk][:] = sum dx_out (column sums of the residual gradient = gradient of the bias added to that stream)
+template <int LN_MAX_VEC>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ dy32, const float* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -82,11 +85,12 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
     __shared__ float red[LN_WARPS][32 * 4 + 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nvec = D >> 2;
-    float4 dg[LN_MAX_VEC], db[LN_MAX_VEC];
+    float4 dg[LN_MAX_VEC], db[LN_MAX_VEC], ds[LN_MAX_VEC];
 #pragma unroll
     for (int i = 0; i < LN_MAX_VEC; ++i) {
         dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
         const float mu = mean[row], rs = rstd[row];
@@ -131,6 +135,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
                     o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
                 }
                 reinterpret_cast<float4*>(dx_out + off)[c] = o;
+                ds[i].x += o.x; ds[i].y += o.y; ds[i].z += o.z; ds[i].w += o.w;
                 if (dx16) {
                     uint2 pk;
                     pk.x = pack_bf16(o.x, o.y);
@@ -143,11 +148,13 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
     // cross-warp reduction of the affine-gradient partials, one 128-column slab at a time
     float* pg = partials + static_cast<size_t>(blockIdx.x) * D;
     float* pb = partials + static_cast<size_t>(gridDim.x + blockIdx.x) * D;
+    float* ps = partials + static_cast<size_t>(2 * gridDim.x + blockIdx.x) * D;
 #pragma unroll
     for (int i = 0; i < LN_MAX_VEC; ++i) {
         if (32 * i >= nvec) break;
-        for (int pass = 0; pass < 2; ++pass) {
-            const float4 val = pass == 0 ? dg[i] : db[i];
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+            const float4 val = pass == 0 ? dg[i] : (pass == 1 ? db[i] : ds[i]);
             __syncthreads();
             red[warp][lane * 4 + 0] = val.x;
             red[warp][lane * 4 + 1] = val.y;
@@ -159,46 +166,139 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
 #pragma unroll
                 for (int w = 0; w < LN_WARPS; ++w) s += red[w][threadIdx.x];
                 const int col = 128 * i + threadIdx.x;
-                if (col < D) (pass == 0 ? pg : pb)[col] = s;
+                if (col < D) (pass == 0 ? pg : (pass == 1 ? pb : ps))[col] = s;
             }
         }
     }
 }
 
-constexpr int CS_ROWS_PER_BLOCK = 64;
-
-// stage 1: block (bx, by) sums rows [by*64, by*64+64) for 256 columns starting at bx*256 -> ws[by][col]
-template <typename T>
-__global__ void __launch_bounds__(256) colsum_stage1_kernel(const T* __restrict__ in, int rows, int cols, int ld,
-                                                            float* __restrict__ ws) {
+// out[part][col] (+)= sum_blk partials[part][blk][col]: finishes LayerNorm-backward partials (up to 3 outputs, 1 launch)
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partials, int nblk, int D, float* __restrict__ out0,
+                       float* __restrict__ out1, float* __restrict__ out2, int accumulate) {
     const int col = blockIdx.x * 256 + threadIdx.x;
-    if (col >= cols) return;
-    const int r0 = blockIdx.y * CS_ROWS_PER_BLOCK;
-    const int r1 = min(rows, r0 + CS_ROWS_PER_BLOCK);
-    float s = 0.f;
-    for (int r = r0; r < r1; ++r) s += static_cast<float>(in[static_cast<size_t>(r) * ld + col]);
-    ws[static_cast<size_t>(blockIdx.y) * cols + col] = s;
-}
-__global__ void __launch_bounds__(256) colsum_stage2_kernel(const float* __restrict__ ws, int nblk, int cols,
-                                                            float* __restrict__ out, int accumulate) {
-    const int col = blockIdx.x * 256 + threadIdx.x;
-    if (col >= cols) return;
-    float s = 0.f;
-    for (int b = 0; b < nblk; ++b) s += ws[static_cast<size_t>(b) * cols + col];
+    float* out = blockIdx.y == 0 ? out0 : (blockIdx.y == 1 ? out1 : out2);
+    if (col >= D || out == nullptr) return;
+    const float* p = partials + static_cast<size_t>(blockIdx.y) * nblk * D + col;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int b = 0;
+    for (; b + 4 <= nblk; b += 4) {
+        s0 += p[static_cast<size_t>(b) * D];
+        s1 += p[static_cast<size_t>(b + 1) * D];
+        s2 += p[static_cast<size_t>(b + 2) * D];
+        s3 += p[static_cast<size_t>(b + 3) * D];
+    }
+    for (; b < nblk; ++b) s0 += p[static_cast<size_t>(b) * D];
+    const float s = (s0 + s1) + (s2 + s3);
     out[col] = accumulate ? out[col] + s : s;
+}
+
+// Column sums in ONE launch.  Block (bx, by): 256 columns starting at bx*256 (lane = 8 consecutive columns, a warp
+// = one 256-column row segment), rows of slice by (warps stride the rows, 4 rows in flight per warp).  With more
+// than one row slice each block writes its partial row to the workspace and the last block to arrive (ticket
+// counter) adds the slices in fixed order -> deterministic; the counter is reset for the next call.
+constexpr int CS_COLS = 256;
+
+template <typename T>
+__device__ __forceinline__ void cs_load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void cs_load8<float>(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void cs_load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ in, int rows, int cols, int ld, float* __restrict__ out, int accumulate,
+              float* __restrict__ ws_partials, unsigned int* __restrict__ counters, int rows_per_slice) {
+    __shared__ float red[8][CS_COLS + 8];
+    __shared__ unsigned int ticket_sh;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * CS_COLS + lane * 8;
+    const int r0 = blockIdx.y * rows_per_slice;
+    const int r1 = min(rows, r0 + rows_per_slice);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c < cols) {
+        int r = r0 + warp;
+        for (; r + 24 < r1; r += 32) {
+            float v0[8], v1[8], v2[8], v3[8];
+            cs_load8<T>(in + static_cast<size_t>(r) * ld + c, v0);
+            cs_load8<T>(in + static_cast<size_t>(r + 8) * ld + c, v1);
+            cs_load8<T>(in + static_cast<size_t>(r + 16) * ld + c, v2);
+            cs_load8<T>(in + static_cast<size_t>(r + 24) * ld + c, v3);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += (v0[i] + v1[i]) + (v2[i] + v3[i]);
+        }
+        for (; r < r1; r += 8) {
+            float v0[8];
+            cs_load8<T>(in + static_cast<size_t>(r) * ld + c, v0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += v0[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+    __syncthreads();
+    const int col = blockIdx.x * CS_COLS + threadIdx.x;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    if (gridDim.y == 1) {
+        if (col < cols) out[col] = accumulate ? out[col] + s : s;
+        return;
+    }
+    if (col < cols) ws_partials[static_cast<size_t>(blockIdx.y) * cols + col] = s;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) ticket_sh = atomicAdd(&counters[blockIdx.x], 1u);
+    __syncthreads();
+    if (ticket_sh != gridDim.y - 1) return;
+    __threadfence();
+    if (col < cols) {
+        float t = 0.f;
+        for (int y = 0; y < static_cast<int>(gridDim.y); ++y) t += __ldcg(ws_partials + static_cast<size_t>(y) * cols + col);
+        out[col] = accumulate ? out[col] + t : t;
+    }
+    if (threadIdx.x == 0) counters[blockIdx.x] = 0u;
 }
 
 }  // namespace vitae
 
 using namespace vitae;
 
+static inline int ln_vec_class(int D) {
+    const int v = ceil_div(D, 128);
+    return v <= 1 ? 1 : (v <= 2 ? 2 : (v <= 4 ? 4 : (v <= 6 ? 6 : 8)));
+}
+
 extern "C" int vitae_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
                                    float* mean, float* rstd, int rows, int D, float eps, void* stream) {
     VITAE_REQUIRE(x && gamma && beta && (y_bf16 || y_f32), "layernorm_fwd: null pointer");
-    VITAE_REQUIRE(rows > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAX_VEC, "layernorm_fwd: unsupported D=%d rows=%d", D, rows);
+    VITAE_REQUIRE(rows > 0 && D > 0 && D % 4 == 0 && D <= 1024, "layernorm_fwd: unsupported D=%d rows=%d", D, rows);
     const int blocks = std::min(ceil_div(rows, LN_WARPS), 148 * 4);
-    layernorm_fwd_kernel<<<blocks, LN_WARPS * 32, 0, as_stream(stream)>>>(
-        x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, rows, D, eps);
+    auto* y16 = static_cast<__nv_bfloat16*>(y_bf16);
+    cudaStream_t st = as_stream(stream);
+#define VITAE_LN_FWD(V) layernorm_fwd_kernel<V><<<blocks, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y16, y_f32, mean, rstd, rows, D, eps)
+    switch (ln_vec_class(D)) {
+        case 1: VITAE_LN_FWD(1); break;
+        case 2: VITAE_LN_FWD(2); break;
+        case 4: VITAE_LN_FWD(4); break;
+        case 6: VITAE_LN_FWD(6); break;
+        default: VITAE_LN_FWD(8); break;
+    }
+#undef VITAE_LN_FWD
     VITAE_CHECK_LAUNCH("layernorm_fwd");
     return 0;
 }
@@ -210,29 +310,61 @@ extern "C" int vitae_layernorm_bwd(const void* dy_bf16, const float* dy_f32, con
                                    void* dx_out_bf16, float* partials, int rows, int D, void* stream) {
     VITAE_REQUIRE((dy_bf16 != nullptr) != (dy_f32 != nullptr), "layernorm_bwd: exactly one of dy_bf16/dy_f32");
     VITAE_REQUIRE(x && gamma && mean && rstd && dx_out && partials, "layernorm_bwd: null pointer");
-    VITAE_REQUIRE(rows > 0 && D > 0 && D % 4 == 0 && D <= 128 * LN_MAX_VEC, "layernorm_bwd: unsupported D=%d rows=%d", D, rows);
+    VITAE_REQUIRE(rows > 0 && D > 0 && D % 4 == 0 && D <= 1024, "layernorm_bwd: unsupported D=%d rows=%d", D, rows);
     const int blocks = vitae_layernorm_bwd_blocks(rows);
-    layernorm_bwd_kernel<<<blocks, LN_WARPS * 32, 0, as_stream(stream)>>>(
-        static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, gamma, mean, rstd, dx_in, dx_out,
-        static_cast<__nv_bfloat16*>(dx_out_bf16), partials, rows, D);
+    const auto* dy16 = static_cast<const __nv_bfloat16*>(dy_bf16);
+    auto* dx16 = static_cast<__nv_bfloat16*>(dx_out_bf16);
+    cudaStream_t st = as_stream(stream);
+#define VITAE_LN_BWD(V) layernorm_bwd_kernel<V><<<blocks, LN_WARPS * 32, 0, st>>>(dy16, dy_f32, x, gamma, mean, rstd, dx_in, dx_out, dx16, partials, rows, D)
+    switch (ln_vec_class(D)) {
+        case 1: VITAE_LN_BWD(1); break;
+        case 2: VITAE_LN_BWD(2); break;
+        case 4: VITAE_LN_BWD(4); break;
+        case 6: VITAE_LN_BWD(6); break;
+        default: VITAE_LN_BWD(8); break;
+    }
+#undef VITAE_LN_BWD
     VITAE_CHECK_LAUNCH("layernorm_bwd");
     return 0;
 }
 
-extern "C" int vitae_colsum_blocks(int rows) { return ceil_div(rows, CS_ROWS_PER_BLOCK); }
+extern "C" int vitae_reduce_partials(const float* partials, int nblk, int D, float* out0, float* out1, float* out2,
+                                     int accumulate, void* stream) {
+    VITAE_REQUIRE(partials && nblk > 0 && D > 0 && (out0 || out1 || out2), "reduce_partials: bad arguments");
+    dim3 grid(ceil_div(D, 256), 3);
+    reduce_partials_kernel<<<grid, 256, 0, as_stream(stream)>>>(partials, nblk, D, out0, out1, out2, accumulate);
+    VITAE_CHECK_LAUNCH("reduce_partials");
+    return 0;
+}
+
+static inline int colsum_slices(int rows, int cols) {
+    const int strips = ceil_div(cols, CS_COLS);
+    int s = std::max(1, (2 * 148) / strips);
+    s = std::min(s, std::max(1, rows / 32));
+    return s;
+}
+
+extern "C" size_t vitae_colsum_workspace_bytes(int rows, int cols) {
+    const int strips = ceil_div(cols, CS_COLS);
+    return static_cast<size_t>(strips) * sizeof(unsigned int) + 256 + static_cast<size_t>(colsum_slices(rows, cols)) * cols * sizeof(float);
+}
 
 extern "C" int vitae_colsum(const void* in_bf16, const float* in_f32, int rows, int cols, int ld, float* out,
-                            int accumulate, float* workspace, void* stream) {
+                            int accumulate, void* workspace, void* stream) {
     VITAE_REQUIRE((in_bf16 != nullptr) != (in_f32 != nullptr), "colsum: exactly one input");
     VITAE_REQUIRE(out && workspace && rows > 0 && cols > 0 && ld >= cols, "colsum: bad arguments");
-    const int nblk = vitae_colsum_blocks(rows);
-    dim3 grid(ceil_div(cols, 256), nblk);
+    VITAE_REQUIRE(cols % 8 == 0 && ld % 8 == 0, "colsum: cols and ld must be multiples of 8 (cols=%d ld=%d)", cols, ld);
+    const int strips = ceil_div(cols, CS_COLS);
+    const int slices = colsum_slices(rows, cols);
+    const int rows_per_slice = ceil_div(rows, slices);
+    const int eff_slices = ceil_div(rows, rows_per_slice);
+    auto* counters = static_cast<unsigned int*>(workspace);
+    auto* parts = reinterpret_cast<float*>(static_cast<char*>(workspace) + ((static_cast<size_t>(strips) * sizeof(unsigned int) + 255) / 256) * 256);
+    dim3 grid(strips, eff_slices);
     if (in_bf16)
-        colsum_stage1_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(in_bf16), rows, cols, ld, workspace);
+        colsum_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(in_bf16), rows, cols, ld, out, accumulate, parts, counters, rows_per_slice);
     else
-        colsum_stage1_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(in_f32, rows, cols, ld, workspace);
-    VITAE_CHECK_LAUNCH("colsum_stage1");
-    colsum_stage2_kernel<<<ceil_div(cols, 256), 256, 0, as_stream(stream)>>>(workspace, nblk, cols, out, accumulate);
-    VITAE_CHECK_LAUNCH("colsum_stage2");
+        colsum_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(in_f32, rows, cols, ld, out, accumulate, parts, counters, rows_per_slice);
+    VITAE_CHECK_LAUNCH("colsum");
     return 0;
 }

@@ -2,6 +2,8 @@
 // patch embed, token assembly (cls / mask-token rows), gradient row gathers, multi-tensor bf16 cast, fused AdamW.
 // All HBM- or latency-bound; coalesced, vectorised where the layout allows.
 #include "common.h"
+#include <string.h>
+
 #include "ptx.cuh"
 
 namespace vitae {
@@ -245,6 +247,133 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Optimizer step over the flat buffers: GradScaler.unscale_ + found_inf + get_grad_norm_
+// (utils/misc.py:259-292) as one reduction pass, then GradScaler.update + AdamW (both param groups) in one pass.
+// Control block ctl (device fp32[8]): [0] loss scale, [1] growth tracker, [2] found_inf, [3] 1/scale used by this step,
+// [4] unscaled global gradient L2 norm, [5] number of optimizer steps taken (skipped steps do not count).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+grad_sqnorm_kernel(const float* __restrict__ g, long long n, float* __restrict__ partials) {
+    __shared__ float sh[8];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const long long n4 = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += gridDim.x * 256ll) {
+        const float4 v = __ldcs(g4 + i);
+        a0 += v.x * v.x; a1 += v.y * v.y; a2 += v.z * v.z; a3 += v.w * v.w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (long long k = n4 << 2; k < n; ++k) a0 += g[k] * g[k];
+    float v = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        partials[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+optim_finalize_kernel(const float* __restrict__ partials, int nblk, float* __restrict__ ctl, float growth_factor,
+                      float backoff_factor, int growth_interval, int use_scaler) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nblk; i += 256) s += static_cast<double>(partials[i]);
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double tot = sh[0];
+        const float scale = use_scaler ? ctl[0] : 1.f;
+        const float inv = 1.f / scale;
+        const bool bad = !isfinite(tot) || !isfinite(static_cast<float>(tot));
+        ctl[2] = (use_scaler && bad) ? 1.f : 0.f;
+        ctl[3] = inv;
+        ctl[4] = static_cast<float>(sqrt(tot)) * inv;
+        if (use_scaler) {                        // torch.amp.GradScaler.update semantics
+            if (bad) {
+                ctl[0] = scale * backoff_factor;
+                ctl[1] = 0.f;
+            } else {
+                const float ok = ctl[1] + 1.f;
+                if (ok >= static_cast<float>(growth_interval)) {
+                    const float grown = scale * growth_factor;
+                    if (isfinite(grown)) ctl[0] = grown;
+                    ctl[1] = 0.f;
+                } else {
+                    ctl[1] = ok;
+                }
+            }
+        }
+        if (!(use_scaler && bad)) ctl[5] += 1.f;
+    }
+}
+
+// hyper (by value): [ngroups][8] = {lr, beta1, beta2, eps, weight_decay, -, -, -}; group_of_chunk[i >> 6] selects the
+// parameter group of element i (tensors start on 64-element boundaries).  torch.optim.AdamW update order.
+struct AdamHyper {
+    float h[8][8];
+};
+__global__ void __launch_bounds__(256)
+adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                  __nv_bfloat16* __restrict__ p16, long long n, const unsigned char* __restrict__ group_of_chunk,
+                  const AdamHyper hyper, int ngroups, const float* __restrict__ ctl) {
+    __shared__ float hs[8][8];   // per group: lr*wd factor, b1, b2, eps, step_size, inv_sqrt_bc2
+    if (ctl[2] != 0.f) return;   // inf / nan gradients: GradScaler skips the step
+    if (threadIdx.x < ngroups) {
+        const float* h = hyper.h[threadIdx.x];
+        const double step = static_cast<double>(ctl[5]);
+        const double bc1 = 1.0 - pow(static_cast<double>(h[1]), step);
+        const double bc2 = 1.0 - pow(static_cast<double>(h[2]), step);
+        hs[threadIdx.x][0] = 1.f - h[0] * h[4];
+        hs[threadIdx.x][1] = h[1];
+        hs[threadIdx.x][2] = h[2];
+        hs[threadIdx.x][3] = h[3];
+        hs[threadIdx.x][4] = static_cast<float>(static_cast<double>(h[0]) / bc1);
+        hs[threadIdx.x][5] = static_cast<float>(1.0 / sqrt(bc2));
+    }
+    __syncthreads();
+    const float is = ctl[3];
+    const long long n4 = n >> 2;   // n is a multiple of 64
+    for (long long i4 = blockIdx.x * 256ll + threadIdx.x; i4 < n4; i4 += gridDim.x * 256ll) {
+        const long long i = i4 << 2;
+        const int grp = group_of_chunk[i >> 6];
+        if (grp >= ngroups) continue;           // padding / frozen chunk
+        const float decay = hs[grp][0], b1 = hs[grp][1], b2 = hs[grp][2], eps = hs[grp][3], step_size = hs[grp][4],
+                    isb2 = hs[grp][5];
+        float4 pp = *reinterpret_cast<float4*>(p + i);
+        const float4 gg = __ldcs(reinterpret_cast<const float4*>(g + i));
+        float4 mm = *reinterpret_cast<float4*>(m + i);
+        float4 vv = *reinterpret_cast<float4*>(v + i);
+        float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gr = ga[k] * is;
+            pa[k] *= decay;
+            ma[k] = b1 * ma[k] + (1.f - b1) * gr;
+            va[k] = b2 * va[k] + (1.f - b2) * gr * gr;
+            pa[k] -= step_size * ma[k] / (sqrtf(va[k]) * isb2 + eps);
+        }
+        *reinterpret_cast<float4*>(p + i) = pp;
+        *reinterpret_cast<float4*>(m + i) = mm;
+        *reinterpret_cast<float4*>(v + i) = vv;
+        if (p16) {
+            uint2 pk;
+            pk.x = pack_bf16(pp.x, pp.y);
+            pk.y = pack_bf16(pp.z, pp.w);
+            *reinterpret_cast<uint2*>(p16 + i) = pk;
+        }
+    }
+}
+
 }  // namespace vitae
 
 using namespace vitae;
@@ -332,5 +461,36 @@ extern "C" int vitae_adamw_step(float* param, const float* grad, float* exp_avg,
     adamw_kernel<<<blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, static_cast<__nv_bfloat16*>(param_bf16), n, lr,
                                                         beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, inv_scale, found_inf);
     VITAE_CHECK_LAUNCH("adamw");
+    return 0;
+}
+
+constexpr int OPT_NORM_BLOCKS = 148 * 4;
+
+extern "C" size_t vitae_optim_workspace_bytes(void) { return OPT_NORM_BLOCKS * sizeof(float); }
+
+extern "C" int vitae_optim_prepare(const float* grad, long long n, float* ctl, float* workspace, float growth_factor,
+                                   float backoff_factor, int growth_interval, int use_scaler, void* stream) {
+    VITAE_REQUIRE(grad && ctl && workspace && n > 0, "optim_prepare: bad arguments");
+    VITAE_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0, "optim_prepare: grad must be 16-byte aligned");
+    const int blocks = static_cast<int>(std::min<long long>(ceil_div<long long>(n, 1024), OPT_NORM_BLOCKS));
+    grad_sqnorm_kernel<<<blocks, 256, 0, as_stream(stream)>>>(grad, n, workspace);
+    VITAE_CHECK_LAUNCH("grad_sqnorm");
+    optim_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(workspace, blocks, ctl, growth_factor, backoff_factor, growth_interval, use_scaler);
+    VITAE_CHECK_LAUNCH("optim_finalize");
+    return 0;
+}
+
+extern "C" int vitae_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16,
+                                long long n, const unsigned char* group_of_chunk, const float* hyper, int ngroups,
+                                const float* ctl, void* stream) {
+    VITAE_REQUIRE(param && grad && exp_avg && exp_avg_sq && group_of_chunk && hyper && ctl, "adamw_flat: null pointer");
+    VITAE_REQUIRE(n > 0 && n % 64 == 0 && ngroups > 0 && ngroups <= 8, "adamw_flat: n=%lld must be a multiple of 64, 1..8 groups", n);
+    const int blocks = static_cast<int>(std::min<long long>(ceil_div<long long>(n, 1024), 148 * 8));
+    AdamHyper hy;
+    memset(&hy, 0, sizeof(hy));
+    memcpy(hy.h, hyper, sizeof(float) * 8 * ngroups);   // host pointer, read during this call
+    adamw_flat_kernel<<<blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, static_cast<__nv_bfloat16*>(param_bf16), n,
+                                                             group_of_chunk, hy, ngroups, ctl);
+    VITAE_CHECK_LAUNCH("adamw_flat");
     return 0;
 }

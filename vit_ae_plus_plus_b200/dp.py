@@ -1,0 +1,57 @@
+"""Data-parallel plumbing of the training step: volumes are sharded over ranks, every rank
+holds a full replica, and the only exchange is one mean all-reduce of the flat gradient buffer per optimizer step
+(plus one broadcast of the flat parameter buffer at construction: the k-fold scripts seed ranks differently,
+k_fold_cross_valid_combined_brats.py:87, and never wrap the model in DDP, :154).
+
+The flat buffers are laid out in the order gradients complete during backward (engine.backward_param_order), so a
+bucket is a contiguous slice and buckets become ready front to back.  ``torch.distributed`` is the transport (NCCL over
+NVLink on the B200 box, gloo in the CPU tests)."""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world_size() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def bucket_slices(tensor_offsets: Sequence[Tuple[int, int]], total: int, bucket_elems: int) -> List[Tuple[int, int]]:
+    """Splits [0, total) into contiguous slices of about ``bucket_elems`` elements that end on tensor boundaries
+    (``tensor_offsets`` = (offset, numel) per tensor in layout order; a tensor larger than a bucket gets its own)."""
+    if total <= 0:
+        return []
+    cuts, start = [], 0
+    ends = [o + k for o, k in tensor_offsets]
+    for i, end in enumerate(ends):
+        last = i == len(ends) - 1
+        if last:
+            end = total
+        if end - start >= bucket_elems or last:
+            cuts.append((start, end))
+            start = end
+    return cuts
+
+
+def broadcast_flat(t: torch.Tensor, src: int = 0) -> None:
+    if world_size() > 1:
+        dist.broadcast(t, src=src)
+
+
+def allreduce_mean_(t: torch.Tensor, async_op: bool = False):
+    """In-place mean over ranks.  NCCL averages in the collective; gloo has no AVG, so sum then scale."""
+    w = world_size()
+    if w == 1:
+        return None
+    if dist.get_backend() == "nccl":
+        return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op)
+    work = dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=False)
+    t.div_(w)
+    return work
+
+
+def allreduce_mean_bucketed_(flat: torch.Tensor, slices: Sequence[Tuple[int, int]]) -> None:
+    for a, b in slices:
+        allreduce_mean_(flat[a:b])

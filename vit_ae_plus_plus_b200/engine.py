@@ -15,6 +15,13 @@ Data layout in HBM
   volume       the caller's fp32 NCDHW tensor is read in place by the patch gather and by the loss kernels
                (no patchify copy, model/vit_autoenc.py:100-113).
 
+Execution
+  one CUDA graph per (shape, input address) for the forward kernels and one for the backward kernels: ~500 kernel
+  nodes are replayed with a single launch each (a ViT-B step is ~2 ms of device time; launching its kernels one by one
+  from Python costs ~12 ms).  Inside the backward graph the weight-gradient GEMMs, bias column sums and LayerNorm
+  partial reductions run on a side stream (they are not on the dgrad critical path), with per-buffer events
+  guarding every read-after-write / write-after-read pair between the two lanes.
+
 Mixed precision: bf16 tensor-core operands, fp32 accumulation, fp32 residual stream / LayerNorm statistics /
 loss / gradients of parameters (BASELINE.json north_star tolerance for this mode: 1e-2 relative).
 """
@@ -26,7 +33,7 @@ from typing import Dict, List, Optional, Tuple
 
 import torch
 
-from . import ops
+from . import dp, ops
 
 _F32, _BF16, _I32 = torch.float32, torch.bfloat16, torch.int32
 _ALIGN = 64  # elements; keeps every tensor 128-byte aligned in the bf16 shadow (TMA needs 16)
@@ -94,21 +101,37 @@ class FlatParams:
                 named_params[n].data = self.v32[n]
         # one-record table for the cast kernel (the flat buffer is a single contiguous tensor)
         self.cast_table = torch.tensor([[self.p32.data_ptr(), 0, self.total]], dtype=torch.int64, device=device)
-        self.shadow_fresh = False
+        self.shadow_version = -1      # parameter version stamp the bf16 shadow was produced from (-1: never)
+        self._plist = [named_params[n] for n in order]
+        self.overwrite_grads = False  # set by mark_grads_consumed(): next backward overwrites instead of accumulating
 
     def still_aliased(self) -> bool:
         n = self.order[0]
         return self.params[n].data_ptr() == self.v32[n].data_ptr() and self.params[n].device == self.p32.device
 
-    def refresh_shadow(self) -> None:
-        """fp32 master -> bf16 shadow (one launch).  Skipped when the fused optimizer already wrote the shadow."""
-        if not self.shadow_fresh:
-            ops.cast_params_bf16(self.cast_table, 1, self.p16, self.total)
+    def _version(self) -> int:
+        # nn.Parameter.data = view gives every parameter its own version counter: in-place writes through torch
+        # (optimizer.step, load_state_dict, init) bump the parameter's, not the flat buffer's
+        return sum(p._version for p in self._plist) + self.p32._version
 
-    def grads_alias(self) -> Optional[bool]:
-        """True: every .grad is our view (accumulate in place); False: every .grad is None; None: mixed / foreign."""
+    def refresh_shadow(self) -> None:
+        """fp32 master -> bf16 shadow (one launch).  Skipped while nothing has written the master through torch since
+        the shadow was produced (the fused optimizer writes both copies itself)."""
+        v = self._version()
+        if self.shadow_version != v:
+            ops.cast_params_bf16(self.cast_table, 1, self.p16, self.total)
+            self.shadow_version = v
+
+    def stamp_shadow(self) -> None:
+        self.shadow_version = self._version()
+
+    def grads_alias(self, thorough: bool = False) -> Optional[bool]:
+        """True: every .grad is our view (accumulate in place); False: every .grad is None; None: mixed / foreign.
+        The per-step check looks at three sentinel tensors; ``thorough`` walks all of them."""
         state = None
-        for n in self.order:
+        names = self.order if thorough or len(self.order) < 4 else (self.order[0], self.order[len(self.order) // 2],
+                                                                    self.order[-1])
+        for n in names:
             g = self.params[n].grad
             s = False if g is None else (True if g.data_ptr() == self.vg[n].data_ptr() else None)
             if s is None:
@@ -118,6 +141,58 @@ class FlatParams:
             elif state != s:
                 return None
         return state
+
+
+class _Lanes:
+    """Main lane = torch's current stream; side lane = work off the critical path (weight gradients, bias sums).
+    Hazards between the lanes are ordered with events: ``side()`` starts after everything enqueued on main so far and
+    remembers which buffers it reads; ``before_write()`` makes main wait for the last side reader of a buffer."""
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.readers: Dict[object, torch.cuda.Event] = {}
+        self.dirty = False
+
+    def side(self, fn, reads=()) -> None:
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            fn()
+        done = torch.cuda.Event()
+        done.record(self.stream)
+        for k in reads:
+            self.readers[k] = done
+        self.dirty = True
+
+    def before_write(self, *keys) -> None:
+        main = torch.cuda.current_stream()
+        for k in keys:
+            ev = self.readers.pop(k, None)
+            if ev is not None:
+                main.wait_event(ev)
+
+    def join(self) -> None:
+        if self.dirty:
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            torch.cuda.current_stream().wait_event(ev)
+        self.readers.clear()
+        self.dirty = False
+
+
+class _GraphSlot:
+    """eager warm-up on first use, capture on the second, replay afterwards"""
+    __slots__ = ("graph", "launches", "calls")
+
+    def __init__(self):
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches = 0
+        self.calls = 0
+
+
+MAX_INPUT_ADDRESSES = 1   # input-volume addresses that get their own (zero-copy) graphs; others are copied (below)
 
 
 class _Arena:
@@ -178,19 +253,25 @@ class MAEPlan:
         self.dloss = a.new((1,), _F32)
         self.dpred = a.new((B, self.Nd, P), _BF16)
         self.dres = [a.new((Mmax * Dmax,), _F32), a.new((Mmax * Dmax,), _F32)]
-        self.dres16 = a.new((Mmax * Dmax,), _BF16)
+        # buffers read by the side lane are double-buffered so that the main lane never waits for recent side work
+        self.dres16 = [a.new((Mmax * Dmax,), _BF16), a.new((Mmax * Dmax,), _BF16)]
         self.d_d = a.new((Mmax * Dmax,), _BF16)
-        self.d_hid = a.new((Mmax * Hmax,), _BF16)
-        self.dqkv = a.new((Mmax * 3 * Dmax,), _BF16)
+        self.d_hid = [a.new((Mmax * Hmax,), _BF16), a.new((Mmax * Hmax,), _BF16)]
+        self.dqkv = [a.new((Mmax * 3 * Dmax,), _BF16), a.new((Mmax * 3 * Dmax,), _BF16)]
         self.delta = a.new((B * max(eng.enc.heads * self.Ne, eng.dec.heads * self.Nd),), _F32)
         nb = ops.layernorm_bwd_blocks(Mmax)
-        self.ln_partials = a.new((2 * nb * Dmax,), _F32)
-        cs_rows = max(Mmax, nb)
-        self.colsum_ws = a.new((ops.colsum_blocks(cs_rows) * max(P, 3 * Dmax, Hmax),), _F32)
+        self.ln_partials = [a.new((3 * nb * Dmax,), _F32), a.new((3 * nb * Dmax,), _F32)]
+        self.ln_calls = 0
+        cs_bytes = max(ops.colsum_workspace_bytes(r, c) for r in (self.Me, self.Md, B * keep)
+                       for c in (P, 3 * D, 3 * Dd, eng.enc.hidden, eng.dec.hidden, D, Dd))
+        self.colsum_ws = torch.zeros(cs_bytes, dtype=torch.uint8, device=dev)   # zero-filled: ticket counters
+        a.nbytes += cs_bytes
         self.g_embed = a.new((self.Me, Dd), _BF16)
         self.g_pe = a.new((B * keep, D), _BF16)
+        self.vol_static: Optional[torch.Tensor] = None   # copy target once too many distinct input addresses were seen
+        self.graphs: Dict[tuple, _GraphSlot] = {}
         self.nbytes = a.nbytes
-        self.vol: Optional[torch.Tensor] = None   # the caller's volume of the current step (read in place)
+        self.vol: Optional[torch.Tensor] = None   # the volume of the current step (read in place by the kernels)
 
     def pred_view(self, dtype) -> torch.Tensor:
         """The reference's ``pred`` [N, L, P] (cls row dropped, vit_autoenc.py:200-201) as a view of the workspace."""
@@ -248,7 +329,14 @@ class MAEEngine:
         self.pos = pos_embed.detach().reshape(self.L + 1, D).contiguous()
         self.dpos = decoder_pos_embed.detach().reshape(self.L + 1, Dd).contiguous()
         self.plans: Dict[Tuple[int, int], MAEPlan] = {}
-        self.kernel_launches = 0
+        self.lanes = _Lanes(dev)
+        self.ws_main, self.ws_side = ops.GrowBuf(dev), ops.GrowBuf(dev)
+        self.use_graphs = True
+        self.use_side_lane = True
+        self.graph_replayed_launches = 0   # kernels executed through graph replays (vitae_launch_count sees enqueues)
+        self.optim: Optional["FusedAdamW"] = None
+        self.grad_buckets = None
+        self.bucket_elems = 32 << 20       # 128 MB of fp32 gradients per all-reduce bucket
 
     # ------------------------------------------------------------------------------------------------ helpers
     def plan(self, B: int, keep: int) -> MAEPlan:
@@ -268,18 +356,72 @@ class MAEEngine:
     def _g(self, name):   # fp32 gradient
         return self.flat.vg[name]
 
+    def _side(self, fn, reads=()):
+        if self.use_side_lane:
+            self.lanes.side(fn, reads)
+        else:
+            fn()
+
+    def _run(self, pl: MAEPlan, key: tuple, fn) -> None:
+        """Runs ``fn`` (a fixed sequence of kernel enqueues over static buffers): eagerly the first time a key is seen,
+        captured into a CUDA graph the second time, replayed afterwards."""
+        if not self.use_graphs or torch.cuda.is_current_stream_capturing():
+            fn()
+            return
+        slot = pl.graphs.get(key)
+        if slot is None:
+            slot = pl.graphs[key] = _GraphSlot()
+        slot.calls += 1
+        if slot.calls == 1:
+            fn()
+            return
+        if slot.graph is None:
+            lib = ops._lib.load()
+            n0 = lib.vitae_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            slot.launches = lib.vitae_launch_count() - n0
+            self.graph_replayed_launches -= slot.launches    # the capture pass enqueued them without executing
+            slot.graph = g
+        slot.graph.replay()
+        self.graph_replayed_launches += slot.launches
+
+    def _resident(self, pl: MAEPlan, vol: torch.Tensor) -> torch.Tensor:
+        """The kernels read the caller's volume in place.  CUDA graphs bake its address in: the first address a plan
+        sees is used in place (a resident batch trains with zero copies); volumes at any other address are copied
+        into one static buffer (a device-to-device copy is ~40 us for 4 x 128^3 x 4 fp32, a graph capture ~100 ms)."""
+        if not self.use_graphs:
+            return vol
+        ptr = vol.data_ptr()
+        known = {k[1] for k in pl.graphs if k[0] == "fwd"}
+        if ptr in known or len(known) < MAX_INPUT_ADDRESSES:
+            return vol
+        if pl.vol_static is None:
+            pl.vol_static = torch.empty_like(vol)
+        if ptr != pl.vol_static.data_ptr():
+            pl.vol_static.copy_(vol)
+        return pl.vol_static
+
     # ------------------------------------------------------------------------------------------------ forward
     def forward(self, vol: torch.Tensor, noise: torch.Tensor, keep: int, want_loss: bool = True,
                 pred_f32: bool = False) -> MAEPlan:
         """vol fp32 [B,C,V,V,V] (contiguous, CUDA); noise fp32 [B,L].  Fills plan.pred / mask / loss_out."""
         B = vol.shape[0]
         pl = self.plan(B, keep)
+        vol = self._resident(pl, vol)
         pl.vol = vol
+        pl.noise.copy_(noise)
+        if pred_f32 and pl.pred32 is None:
+            pl.pred32 = torch.empty((pl.B, pl.Nd, self.P), dtype=_F32, device=self.device)
         self.flat.refresh_shadow()
-        self.encode(pl, vol, noise)
-        self.decode(pl, pred_f32)
-        if want_loss:
-            ops.masked_mse_fwd(pl.pred, vol, pl.mask, pl.patch_sums, pl.loss_out, self.p)
+
+        def body():
+            self.encode(pl, vol, pl.noise)
+            self.decode(pl, pred_f32)
+            if want_loss:
+                ops.masked_mse_fwd(pl.pred, vol, pl.mask, pl.patch_sums, pl.loss_out, self.p)
+        self._run(pl, ("fwd", vol.data_ptr(), pred_f32, want_loss), body)
         return pl
 
     def encode(self, pl: MAEPlan, vol: torch.Tensor, noise: torch.Tensor) -> None:
@@ -292,7 +434,7 @@ class MAEEngine:
         x0 = pl.enc.x[0]
         ops.gemm(pl.cols, self._w("patch_embed.proj.weight"), B * keep, D, self.Kpe,
                  bias=self._p("patch_embed.proj.bias"), addend=self.pos, add_rows=pl.maps["pe_pos_rows"], ldadd=D,
-                 out_f32=x0, out_rows=pl.maps["enc_tok_rows"])
+                 out_f32=x0, out_rows=pl.maps["enc_tok_rows"], workspace=self.ws_main)
         ops.fill_rows(x0, pl.maps["enc_cls_rows"], B, D, self._p("cls_token"), None, self.pos, None)
         self._stack_fwd(self.enc, pl.enc, pl.Me, B, pl.Ne)
         ops.layernorm_fwd(pl.enc.x[-1], self._p("norm.weight"), self._p("norm.bias"), pl.latent, pl.mean_n, pl.rstd_n,
@@ -306,7 +448,7 @@ class MAEEngine:
         xd0 = pl.dec.x[0]
         ops.gemm(pl.latent, self._w("decoder_embed.weight"), pl.Me, Dd, D, bias=self._p("decoder_embed.bias"),
                  addend=self.dpos, add_rows=pl.maps["dec_pos_rows_of_enc"], ldadd=Dd, out_f32=xd0,
-                 out_rows=pl.maps["dec_rows_of_enc"])
+                 out_rows=pl.maps["dec_rows_of_enc"], workspace=self.ws_main)
         if pl.nmask > 0:
             ops.fill_rows(xd0, pl.maps["masked_dec_rows"], B * pl.nmask, Dd, self._p("mask_token"), None, self.dpos,
                           pl.maps["masked_pos_rows"])
@@ -314,150 +456,283 @@ class MAEEngine:
         ops.layernorm_fwd(pl.dec.x[-1], self._p("decoder_norm.weight"), self._p("decoder_norm.bias"), pl.hN,
                           pl.mean_dn, pl.rstd_dn, self.eps)
         ops.gemm(pl.hN, self._w("decoder_pred.weight"), pl.Md, self.P, Dd, bias=self._p("decoder_pred.bias"),
-                 out_bf16=pl.pred.view(pl.Md, self.P), out_f32=pl.pred32.view(pl.Md, self.P) if pred_f32 else None)
+                 out_bf16=pl.pred.view(pl.Md, self.P), out_f32=pl.pred32.view(pl.Md, self.P) if pred_f32 else None,
+                 workspace=self.ws_main)
 
     def _stack_fwd(self, st: StackSpec, sb, M: int, B: int, N: int) -> None:
         """model/vit.py:139-144 (Block), :112-124 (Attention), :90-96 (Mlp3D)."""
         D, hid, H, hd = st.dim, st.hidden, st.heads, st.head_dim
         scale = hd ** -0.5
+        ws = self.ws_main
         for i in range(st.depth):
             pre = f"{st.prefix}.{i}"
             b, x_in, x_out = sb.blocks[i], sb.x[i], sb.x[i + 1]
             ops.layernorm_fwd(x_in, self._p(f"{pre}.norm1.weight"), self._p(f"{pre}.norm1.bias"), b.ln1, b.mean1,
                               b.rstd1, self.eps)
             ops.gemm(b.ln1, self._w(f"{pre}.attn.qkv.weight"), M, 3 * D, D, bias=self._p(f"{pre}.attn.qkv.bias"),
-                     out_bf16=b.qkv)
+                     out_bf16=b.qkv, workspace=ws)
             ops.attention_fwd(b.qkv, b.o, b.lse, B, N, H, hd, scale)
             ops.gemm(b.o, self._w(f"{pre}.attn.proj.weight"), M, D, D, bias=self._p(f"{pre}.attn.proj.bias"),
-                     addend=x_in, out_f32=b.xmid)
+                     addend=x_in, out_f32=b.xmid, workspace=ws)
             ops.layernorm_fwd(b.xmid, self._p(f"{pre}.norm2.weight"), self._p(f"{pre}.norm2.bias"), b.ln2, b.mean2,
                               b.rstd2, self.eps)
             ops.gemm(b.ln2, self._w(f"{pre}.mlp.fc1.weight"), M, hid, D, bias=self._p(f"{pre}.mlp.fc1.bias"),
-                     out_bf16=b.pre, out_gelu_bf16=b.act)
+                     out_bf16=b.pre, out_gelu_bf16=b.act, workspace=ws)
             ops.gemm(b.act, self._w(f"{pre}.mlp.fc2.weight"), M, D, hid, bias=self._p(f"{pre}.mlp.fc2.bias"),
-                     addend=b.xmid, out_f32=x_out)
+                     addend=b.xmid, out_f32=x_out, workspace=ws)
 
     # ------------------------------------------------------------------------------------------------ backward
     def backward(self, pl: MAEPlan, dloss: Optional[torch.Tensor], dpred_extra: Optional[torch.Tensor] = None,
                  accumulate: bool = False) -> None:
         """Gradient of (dloss * recon_loss [+ <dpred_extra, pred>]) w.r.t. every trainable parameter, written to
         (accumulate=False) or added into (True) the flat gradient buffer.  Hand-derived reverse of forward()."""
-        B, D, Dd, P = pl.B, self.enc.dim, self.dec.dim, self.P
-        acc = accumulate
-        ws = pl.colsum_ws
         if dloss is None:
             pl.dloss.zero_()
         else:
             pl.dloss.copy_(dloss.reshape(1))
+        if dpred_extra is not None:   # auxiliary torch-side terms that consume ``pred`` (edge-map loss): not graphed
+            self._backward_impl(pl, dpred_extra, accumulate)
+        else:
+            self._run(pl, ("bwd", pl.vol.data_ptr(), bool(accumulate)), lambda: self._backward_impl(pl, None, accumulate))
+
+    def _backward_impl(self, pl: MAEPlan, dpred_extra: Optional[torch.Tensor], acc: bool) -> None:
+        B, D, Dd, P = pl.B, self.enc.dim, self.dec.dim, self.P
+        cws, wsm, wss = pl.colsum_ws, self.ws_main, self.ws_side
+        lanes = self.lanes
         # ---- loss: d recon / d pred (model/vit_autoenc.py:226-227), zeros for kept patches and the cls row
+        lanes.before_write("dpred")
         ops.masked_mse_bwd(pl.pred, pl.vol, pl.mask, pl.loss_out[1:], pl.dloss, pl.dpred, self.p)
-        if dpred_extra is not None:   # gradient of auxiliary torch-side terms that consume ``pred`` (edge-map loss)
+        if dpred_extra is not None:
             pl.dpred[:, 1:, :].add_(dpred_extra.to(_BF16))
         dpred = pl.dpred.view(pl.Md, P)
         # ---- decoder_pred (vit_autoenc.py:198)
-        ops.gemm(dpred, pl.hN, P, Dd, pl.Md, a_mn_major=True, b_mn_major=True, out_f32=self._g("decoder_pred.weight"),
-                 accumulate=acc)
-        ops.colsum(dpred, pl.Md, P, self._g("decoder_pred.bias"), ws, accumulate=acc)
+
+        def side_pred():
+            ops.gemm(dpred, pl.hN, P, Dd, pl.Md, a_mn_major=True, b_mn_major=True,
+                     out_f32=self._g("decoder_pred.weight"), accumulate=acc, workspace=wss)
+            ops.colsum(dpred, pl.Md, P, self._g("decoder_pred.bias"), cws, accumulate=acc)
+        self._side(side_pred, reads=("dpred",))
         d_d = pl.d_d[:pl.Md * Dd].view(pl.Md, Dd)
-        ops.gemm(dpred, self._w("decoder_pred.weight"), pl.Md, Dd, P, b_mn_major=True, out_bf16=d_d)
-        cur = self._ln_bwd(pl, d_d, pl.dec.x[-1], "decoder_norm", pl.mean_dn, pl.rstd_dn, None, 0, pl.Md, Dd, acc)
+        ops.gemm(dpred, self._w("decoder_pred.weight"), pl.Md, Dd, P, b_mn_major=True, out_bf16=d_d, workspace=wsm)
+        last_dec = f"decoder_blocks.{self.dec.depth - 1}.mlp.fc2.bias" if self.dec.depth else None
+        cur = self._ln_bwd(pl, d_d, pl.dec.x[-1], "decoder_norm", pl.mean_dn, pl.rstd_dn, None, 0, pl.Md, Dd, acc,
+                           last_dec)
         cur = self._stack_bwd(self.dec, pl.dec, pl, pl.Md, B, pl.Nd, cur, acc)
         dxd = pl.dres[cur][:pl.Md * Dd].view(pl.Md, Dd)
         # ---- mask tokens, decoder_embed (vit_autoenc.py:181-190)
-        if pl.nmask > 0:
-            ops.sum_rows(dxd, pl.maps["masked_dec_rows"], B * pl.nmask, Dd, self._g("mask_token").view(-1), acc)
-        elif not acc:
-            self._g("mask_token").zero_()
+        lanes.before_write("g_embed")
         ops.gather_rows(dxd, pl.maps["dec_rows_of_enc"], pl.Me, Dd, pl.g_embed, None)
-        ops.gemm(pl.g_embed, pl.latent, Dd, D, pl.Me, a_mn_major=True, b_mn_major=True,
-                 out_f32=self._g("decoder_embed.weight"), accumulate=acc)
-        ops.colsum(pl.g_embed, pl.Me, Dd, self._g("decoder_embed.bias"), ws, accumulate=acc)
+
+        def side_embed():
+            if pl.nmask > 0:
+                ops.sum_rows(dxd, pl.maps["masked_dec_rows"], B * pl.nmask, Dd, self._g("mask_token").view(-1), acc)
+            elif not acc:
+                self._g("mask_token").zero_()
+            ops.gemm(pl.g_embed, pl.latent, Dd, D, pl.Me, a_mn_major=True, b_mn_major=True,
+                     out_f32=self._g("decoder_embed.weight"), accumulate=acc, workspace=wss)
+            ops.colsum(pl.g_embed, pl.Me, Dd, self._g("decoder_embed.bias"), cws, accumulate=acc)
+        self._side(side_embed, reads=("g_embed", ("dres", cur)))
         d_e = pl.d_d[:pl.Me * D].view(pl.Me, D)
-        ops.gemm(pl.g_embed, self._w("decoder_embed.weight"), pl.Me, D, Dd, b_mn_major=True, out_bf16=d_e)
+        ops.gemm(pl.g_embed, self._w("decoder_embed.weight"), pl.Me, D, Dd, b_mn_major=True, out_bf16=d_e,
+                 workspace=wsm)
         # ---- encoder norm + blocks (vit_autoenc.py:172-175)
-        cur = self._ln_bwd(pl, d_e, pl.enc.x[-1], "norm", pl.mean_n, pl.rstd_n, None, 0, pl.Me, D, acc)
+        last_enc = f"blocks.{self.enc.depth - 1}.mlp.fc2.bias" if self.enc.depth else None
+        cur = self._ln_bwd(pl, d_e, pl.enc.x[-1], "norm", pl.mean_n, pl.rstd_n, None, 0, pl.Me, D, acc, last_enc)
         cur = self._stack_bwd(self.enc, pl.enc, pl, pl.Me, B, pl.Ne, cur, acc)
         dx0 = pl.dres[cur][:pl.Me * D].view(pl.Me, D)
         # ---- cls token, patch embed (vit_autoenc.py:160-170); no input gradient for the volume
-        ops.sum_rows(dx0, pl.maps["enc_cls_rows"], B, D, self._g("cls_token").view(-1), acc)
+        lanes.before_write("g_pe")
         ops.gather_rows(dx0, pl.maps["enc_tok_rows"], B * pl.keep, D, pl.g_pe, None)
+        ops.sum_rows(dx0, pl.maps["enc_cls_rows"], B, D, self._g("cls_token").view(-1), acc)
         ops.gemm(pl.g_pe, pl.cols, D, self.Kpe, B * pl.keep, a_mn_major=True, b_mn_major=True,
-                 out_f32=self._g("patch_embed.proj.weight").view(D, self.Kpe), accumulate=acc)
-        ops.colsum(pl.g_pe, B * pl.keep, D, self._g("patch_embed.proj.bias"), ws, accumulate=acc)
+                 out_f32=self._g("patch_embed.proj.weight").view(D, self.Kpe), accumulate=acc, workspace=wsm)
+
+        def side_pe():
+            ops.colsum(pl.g_pe, B * pl.keep, D, self._g("patch_embed.proj.bias"), cws, accumulate=acc)
+        self._side(side_pe, reads=("g_pe",))
+        lanes.join()
 
     def _ln_bwd(self, pl: MAEPlan, dy: torch.Tensor, x: torch.Tensor, name: str, mean, rstd, dx_in_idx: Optional[int],
-                out_idx: int, M: int, D: int, acc: bool) -> int:
-        """LayerNorm backward: dres[out_idx] = (dres[dx_in_idx] if given) + LN'(dy); refreshes the bf16 copy dres16 and
-        the affine gradients.  Returns out_idx."""
+                out_idx: int, M: int, D: int, acc: bool, bias_name: Optional[str]) -> int:
+        """LayerNorm backward on the main lane: dres[out_idx] = (dres[dx_in_idx] if given) + LN'(dy), plus its bf16 copy
+        dres16[out_idx]; the affine gradients and ``bias_name`` (the bias whose gradient is the column sum of the new
+        residual gradient) are finished on the side lane.  Returns out_idx."""
         nb = ops.layernorm_bwd_blocks(M)
-        partials = pl.ln_partials[:2 * nb * D].view(2, nb, D)
+        k = pl.ln_calls & 1
+        pl.ln_calls += 1
+        partials = pl.ln_partials[k][:3 * nb * D].view(3, nb, D)
         dx_in = None if dx_in_idx is None else pl.dres[dx_in_idx][:M * D].view(M, D)
         dx_out = pl.dres[out_idx][:M * D].view(M, D)
-        dx16 = pl.dres16[:M * D].view(M, D)
+        dx16 = pl.dres16[out_idx][:M * D].view(M, D)
+        self.lanes.before_write(("dres", out_idx), ("dres16", out_idx), ("part", k))
         ops.layernorm_bwd(dy, x, self._p(f"{name}.weight"), mean, rstd, dx_in, dx_out, dx16, partials)
-        ops.colsum(partials[0], nb, D, self._g(f"{name}.weight"), pl.colsum_ws, accumulate=acc)
-        ops.colsum(partials[1], nb, D, self._g(f"{name}.bias"), pl.colsum_ws, accumulate=acc)
+        gb = self._g(bias_name) if bias_name is not None else None
+        self._side(lambda: ops.reduce_partials(partials, nb, D, self._g(f"{name}.weight"), self._g(f"{name}.bias"), gb,
+                                               accumulate=acc), reads=(("part", k),))
         return out_idx
 
     def _stack_bwd(self, st: StackSpec, sb, pl: MAEPlan, M: int, B: int, N: int, cur: int, acc: bool) -> int:
-        """Reverse of _stack_fwd.  On entry dres[cur] / dres16 hold the gradient w.r.t. the stack output."""
+        """Reverse of _stack_fwd.  On entry dres[cur] / dres16[cur] hold the gradient w.r.t. the stack output.
+        Main lane: dgrad GEMMs, attention backward, LayerNorm backward (the dependency chain).  Side lane: wgrad GEMMs,
+        bias column sums, LayerNorm partial reductions."""
         D, hid, H, hd = st.dim, st.hidden, st.heads, st.head_dim
         scale = hd ** -0.5
-        ws = pl.colsum_ws
-        dres16 = pl.dres16[:M * D].view(M, D)
-        d_hid = pl.d_hid[:M * hid].view(M, hid)
+        cws, wsm, wss = pl.colsum_ws, self.ws_main, self.ws_side
+        lanes = self.lanes
         d_d = pl.d_d[:M * D].view(M, D)
-        dqkv = pl.dqkv[:M * 3 * D].view(M, 3 * D)
         delta = pl.delta[:B * H * N]
         for i in reversed(range(st.depth)):
             pre = f"{st.prefix}.{i}"
             b, x_in = sb.blocks[i], sb.x[i]
-            dres = pl.dres[cur][:M * D].view(M, D)
+            hb = i & 1
+            d_hid = pl.d_hid[hb][:M * hid].view(M, hid)
+            dqkv = pl.dqkv[hb][:M * 3 * D].view(M, 3 * D)
+            dres16 = pl.dres16[cur][:M * D].view(M, D)
             # x_out = xmid + fc2(gelu(fc1(ln2))) + b2
-            ops.gemm(dres16, b.act, D, hid, M, a_mn_major=True, b_mn_major=True, out_f32=self._g(f"{pre}.mlp.fc2.weight"),
-                     accumulate=acc)
-            ops.colsum(dres, M, D, self._g(f"{pre}.mlp.fc2.bias"), ws, accumulate=acc)
-            ops.gemm(dres16, self._w(f"{pre}.mlp.fc2.weight"), M, hid, D, b_mn_major=True, dgelu_src=b.pre, out_bf16=d_hid)
-            ops.gemm(d_hid, b.ln2, hid, D, M, a_mn_major=True, b_mn_major=True, out_f32=self._g(f"{pre}.mlp.fc1.weight"),
-                     accumulate=acc)
-            ops.colsum(d_hid, M, hid, self._g(f"{pre}.mlp.fc1.bias"), ws, accumulate=acc)
-            ops.gemm(d_hid, self._w(f"{pre}.mlp.fc1.weight"), M, D, hid, b_mn_major=True, out_bf16=d_d)
+            self._side(lambda: ops.gemm(dres16, b.act, D, hid, M, a_mn_major=True, b_mn_major=True,
+                                        out_f32=self._g(f"{pre}.mlp.fc2.weight"), accumulate=acc, workspace=wss),
+                       reads=(("dres16", cur),))
+            lanes.before_write(("d_hid", hb))
+            ops.gemm(dres16, self._w(f"{pre}.mlp.fc2.weight"), M, hid, D, b_mn_major=True, dgelu_src=b.pre,
+                     out_bf16=d_hid, workspace=wsm)
+
+            def side_fc1(d_hid=d_hid, b=b, pre=pre):
+                ops.gemm(d_hid, b.ln2, hid, D, M, a_mn_major=True, b_mn_major=True,
+                         out_f32=self._g(f"{pre}.mlp.fc1.weight"), accumulate=acc, workspace=wss)
+                ops.colsum(d_hid, M, hid, self._g(f"{pre}.mlp.fc1.bias"), cws, accumulate=acc)
+            self._side(side_fc1, reads=(("d_hid", hb),))
+            ops.gemm(d_hid, self._w(f"{pre}.mlp.fc1.weight"), M, D, hid, b_mn_major=True, out_bf16=d_d, workspace=wsm)
             nxt = cur ^ 1
-            self._ln_bwd(pl, d_d, b.xmid, f"{pre}.norm2", b.mean2, b.rstd2, cur, nxt, M, D, acc)
+            self._ln_bwd(pl, d_d, b.xmid, f"{pre}.norm2", b.mean2, b.rstd2, cur, nxt, M, D, acc,
+                         f"{pre}.attn.proj.bias")
             cur = nxt
-            dres = pl.dres[cur][:M * D].view(M, D)
+            dres16 = pl.dres16[cur][:M * D].view(M, D)
             # xmid = x_in + proj(attn(qkv(ln1))) + bp
-            ops.gemm(dres16, b.o, D, D, M, a_mn_major=True, b_mn_major=True, out_f32=self._g(f"{pre}.attn.proj.weight"),
-                     accumulate=acc)
-            ops.colsum(dres, M, D, self._g(f"{pre}.attn.proj.bias"), ws, accumulate=acc)
-            ops.gemm(dres16, self._w(f"{pre}.attn.proj.weight"), M, D, D, b_mn_major=True, out_bf16=d_d)
+            self._side(lambda dres16=dres16, b=b, pre=pre: ops.gemm(
+                dres16, b.o, D, D, M, a_mn_major=True, b_mn_major=True, out_f32=self._g(f"{pre}.attn.proj.weight"),
+                accumulate=acc, workspace=wss), reads=(("dres16", cur),))
+            ops.gemm(dres16, self._w(f"{pre}.attn.proj.weight"), M, D, D, b_mn_major=True, out_bf16=d_d, workspace=wsm)
+            lanes.before_write(("dqkv", hb))
             ops.attention_bwd(b.qkv, b.o, d_d, b.lse, delta, dqkv, B, N, H, hd, scale)
-            ops.gemm(dqkv, b.ln1, 3 * D, D, M, a_mn_major=True, b_mn_major=True, out_f32=self._g(f"{pre}.attn.qkv.weight"),
-                     accumulate=acc)
-            ops.colsum(dqkv, M, 3 * D, self._g(f"{pre}.attn.qkv.bias"), ws, accumulate=acc)
-            ops.gemm(dqkv, self._w(f"{pre}.attn.qkv.weight"), M, D, 3 * D, b_mn_major=True, out_bf16=d_d)
+
+            def side_qkv(dqkv=dqkv, b=b, pre=pre):
+                ops.gemm(dqkv, b.ln1, 3 * D, D, M, a_mn_major=True, b_mn_major=True,
+                         out_f32=self._g(f"{pre}.attn.qkv.weight"), accumulate=acc, workspace=wss)
+                ops.colsum(dqkv, M, 3 * D, self._g(f"{pre}.attn.qkv.bias"), cws, accumulate=acc)
+            self._side(side_qkv, reads=(("dqkv", hb),))
+            ops.gemm(dqkv, self._w(f"{pre}.attn.qkv.weight"), M, D, 3 * D, b_mn_major=True, out_bf16=d_d, workspace=wsm)
             nxt = cur ^ 1
-            self._ln_bwd(pl, d_d, x_in, f"{pre}.norm1", b.mean1, b.rstd1, cur, nxt, M, D, acc)
+            below = f"{st.prefix}.{i - 1}.mlp.fc2.bias" if i > 0 else None
+            self._ln_bwd(pl, d_d, x_in, f"{pre}.norm1", b.mean1, b.rstd1, cur, nxt, M, D, acc, below)
             cur = nxt
         return cur
 
     # ------------------------------------------------------------------------------------------------ data parallel
-    @staticmethod
-    def _world() -> int:
-        import torch.distributed as dist
-        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-
     def broadcast_parameters(self) -> None:
-        """Ranks seed differently (k_fold_cross_valid_combined_brats.py:87) and the scripts never wrap DDP
-        (:154), so the module replicates rank 0's parameters itself: one broadcast of the flat buffer."""
-        if self._world() > 1:
-            import torch.distributed as dist
-            dist.broadcast(self.flat.p32, src=0)
-            dist.broadcast(self.pos, src=0)
-            dist.broadcast(self.dpos, src=0)
+        """One broadcast of the flat parameter buffer (+ the frozen position tables) from rank 0 (dp.py)."""
+        dp.broadcast_flat(self.flat.p32)
+        dp.broadcast_flat(self.pos)
+        dp.broadcast_flat(self.dpos)
 
     def allreduce_gradients(self) -> None:
         """Mean of the flat gradient buffer over ranks (one exchange step per optimizer step)."""
-        if self._world() > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat.g32, op=dist.ReduceOp.AVG)
+        if dp.world_size() > 1:
+            if self.grad_buckets is None:
+                offs = [(self.flat.offsets[n][0], self.flat.offsets[n][1]) for n in self.flat.order]
+                self.grad_buckets = dp.bucket_slices(offs, self.flat.total, self.bucket_elems)
+            dp.allreduce_mean_bucketed_(self.flat.g32, self.grad_buckets)
+
+    # ------------------------------------------------------------------------------------------------ optimizer
+    def fused_optimizer(self) -> "FusedAdamW":
+        if self.optim is None:
+            self.optim = FusedAdamW(self)
+        return self.optim
+
+
+class FusedAdamW:
+    """GradScaler.unscale_ + gradient norm + AdamW + GradScaler.update over the flat buffers in three launches
+    (include/vitae_b200.h: vitae_optim_prepare / vitae_adamw_flat), driven by the hyper-parameters of the caller's own
+    ``torch.optim.AdamW`` (k_fold_cross_valid_combined_brats.py:168-169).  The moments live in flat buffers; the
+    optimizer's ``state[p]['exp_avg' / 'exp_avg_sq']`` are views of them, so ``optimizer.state_dict()`` checkpoints and a
+    later plain ``optimizer.step()`` both keep working."""
+
+    def __init__(self, eng: MAEEngine):
+        flat, dev = eng.flat, eng.device
+        self.eng = eng
+        self.m = torch.zeros(flat.total, dtype=_F32, device=dev)
+        self.v = torch.zeros(flat.total, dtype=_F32, device=dev)
+        self.ctl = torch.zeros(8, dtype=_F32, device=dev)
+        self.ws = torch.empty(ops.optim_workspace_bytes(), dtype=torch.uint8, device=dev)
+        self.group_map = torch.full((flat.total // _ALIGN,), 255, dtype=torch.uint8, device=dev)
+        self.bound: Optional[int] = None       # id of the bound optimizer
+        self.bound_sig = None
+        self.host_steps = 0
+
+    @staticmethod
+    def supports(optimizer) -> bool:
+        if type(optimizer) is not torch.optim.AdamW:
+            return False
+        return all(not g.get("amsgrad", False) and not g.get("maximize", False) and not g.get("capturable", False)
+                   and not isinstance(g["lr"], torch.Tensor) for g in optimizer.param_groups)
+
+    def bind(self, optimizer) -> bool:
+        """Maps the optimizer's parameter groups onto 64-element chunks of the flat buffer and adopts / installs its
+        state.  Returns False when a parameter of the optimizer is not one of this engine's flat views."""
+        flat = self.eng.flat
+        by_ptr = {flat.v32[n].data_ptr(): n for n in flat.order}
+        sig = tuple(tuple(p.data_ptr() for p in g["params"]) for g in optimizer.param_groups)
+        if self.bound == id(optimizer) and self.bound_sig == sig:
+            return True
+        if len(optimizer.param_groups) > 8:
+            return False
+        gm = torch.full((flat.total // _ALIGN,), 255, dtype=torch.uint8)
+        steps = []
+        for gi, group in enumerate(optimizer.param_groups):
+            for p in group["params"]:
+                n = by_ptr.get(p.data_ptr())
+                if n is None:
+                    return False
+                o, k, shp = flat.offsets[n]
+                gm[o // _ALIGN:(o + k + _ALIGN - 1) // _ALIGN] = gi
+                st = optimizer.state.get(p)
+                mv, vv = self.m[o:o + k].view(shp), self.v[o:o + k].view(shp)
+                if st and "exp_avg" in st:
+                    if st["exp_avg"].data_ptr() != mv.data_ptr():
+                        mv.copy_(st["exp_avg"]); vv.copy_(st["exp_avg_sq"])
+                    steps.append(float(st["step"]))
+                optimizer.state[p] = {"step": torch.tensor(0.0), "exp_avg": mv, "exp_avg_sq": vv}
+        self.group_map.copy_(gm)
+        self.host_steps = int(max(steps)) if steps else 0
+        self.ctl[5] = float(self.host_steps)
+        for group in optimizer.param_groups:
+            for p in group["params"]:
+                optimizer.state[p]["step"].fill_(float(self.host_steps))
+        self.bound, self.bound_sig = id(optimizer), sig
+        return True
+
+    def step(self, optimizer, scaler=None) -> torch.Tensor:
+        """One optimizer step on the gradients currently in the flat gradient buffer; returns the (unscaled) global
+        gradient norm as a 0-dim device tensor.  ``scaler``: a torch.amp.GradScaler-like object whose scale lives in
+        ``ctl[0]`` (see utils/misc.py::NativeScalerWithGradNormCount) or None."""
+        eng, flat = self.eng, self.eng.flat
+        use_scaler = scaler is not None
+        gf, bf, gi = (scaler.get_growth_factor(), scaler.get_backoff_factor(), scaler.get_growth_interval()) \
+            if use_scaler else (2.0, 0.5, 2000)
+        ops.optim_prepare(flat.g32, flat.total, self.ctl, self.ws, gf, bf, gi, use_scaler)
+        rows = [(g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"]) for g in optimizer.param_groups]
+        ops.adamw_flat(flat.p32, flat.g32, self.m, self.v, flat.p16, flat.total, self.group_map, rows, self.ctl)
+        flat.stamp_shadow()
+        flat.overwrite_grads = True      # these gradients are consumed: the next backward starts from zero
+        self.host_steps += 1
+        return self.ctl[4].clone()
+
+    def sync_state(self, optimizer) -> None:
+        """Writes the device-side step count (skipped steps excluded) into the optimizer's per-parameter state (one
+        device read): call before ``optimizer.state_dict()`` / switching to ``optimizer.step()``."""
+        steps = float(self.ctl[5].item())
+        self.host_steps = int(steps)
+        for group in optimizer.param_groups:
+            for p in group["params"]:
+                st = optimizer.state.get(p)
+                if st is not None and "step" in st:
+                    st["step"].fill_(steps)

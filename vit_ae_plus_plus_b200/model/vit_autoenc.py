@@ -20,6 +20,7 @@ Differences a caller can observe (all documented in DESIGN.md):
 from __future__ import annotations
 
 import math
+import weakref
 from functools import partial
 from typing import Optional
 
@@ -186,6 +187,7 @@ class MaskedAutoencoderViT(nn.Module):
         self.pred_dtype = torch.float32      # dtype of the returned ``pred`` (set to torch.bfloat16 to skip the fp32 copy)
         self.report_edge_loss = False        # evaluate loss_list[1] even when edge_map_weight == 0
         self.require_backward_grad_sync = True   # data-parallel: all-reduce gradients in backward (see no_sync())
+        self.use_cuda_graph = True               # replay the forward / backward kernel sequences as CUDA graphs
         self._engine: Optional[MAEEngine] = None
         self.initialize_weights()
 
@@ -213,8 +215,17 @@ class MaskedAutoencoderViT(nn.Module):
             raise VitaeError("MaskedAutoencoderViT runs on a B200 only (module is on "
                              f"{self.cls_token.device}); there is no CPU / PyTorch fallback")
         self._engine = MAEEngine(self.cfg, self._trainable(), self.pos_embed, self.decoder_pos_embed, self.ln_eps)
+        self._engine.use_graphs = self.use_cuda_graph
+        ref = weakref.ref(self._engine)
+        for p in self._engine.flat.params.values():
+            p._vitae_engine = ref          # lets utils.misc.NativeScalerWithGradNormCount find the fused optimizer
         self._engine.broadcast_parameters()
         return self._engine
+
+    @property
+    def graph_replayed_launches(self) -> int:
+        """Kernels executed through CUDA-graph replays (the library's launch counter only sees direct enqueues)."""
+        return 0 if self._engine is None else self._engine.graph_replayed_launches
 
     def no_sync(self):
         """Context manager: skip the data-parallel gradient all-reduce (gradient-accumulation micro-steps)."""
@@ -233,10 +244,16 @@ class MaskedAutoencoderViT(nn.Module):
         eng = self._engine
         flat = eng.flat
         state = flat.grads_alias()
+        if state is None:
+            state = flat.grads_alias(thorough=True)
         saved = None
         if state is None:   # foreign / partially set .grad tensors: keep them and add ours afterwards
             saved = {n: flat.params[n].grad.clone() for n in flat.order if flat.params[n].grad is not None}
-        eng.backward(pl, drecon, dpred_extra=dpred, accumulate=state is True)
+        # accumulate into aliased .grad tensors unless the fused optimizer has consumed them since the last backward
+        acc = state is True and not flat.overwrite_grads
+        flat.overwrite_grads = False
+        eng.use_graphs = self.use_cuda_graph
+        eng.backward(pl, drecon, dpred_extra=dpred, accumulate=acc)
         if state is not True:
             for n in flat.order:
                 p = flat.params[n]
@@ -338,6 +355,7 @@ class MaskedAutoencoderViT(nn.Module):
     def forward(self, sample, mask_ratio=0.75, edge_map_weight=0, noise=None):
         """model/vit_autoenc.py:234-238 -> ([loss, raw_edge, recon, percep], pred [N, L, p^3*C], mask [N, L])."""
         eng = self.engine()
+        eng.use_graphs = self.use_cuda_graph
         x = self._check_volume(sample)
         noise = self._noise(x, noise)
         keep = self._len_keep(mask_ratio)

@@ -34,7 +34,8 @@ def _req(t: torch.Tensor, dtype, name: str) -> None:
 
 
 def gemm_config(M: int, N: int, K: int, n_sm: int = 148):
-    """Heuristic (tile_n, split_k): fill ~1 wave of 148 SMs; split K when the output grid is too small."""
+    """Heuristic (tile_n, split_k): fill ~1 wave of 148 SMs; split K only for long reductions on a small output grid
+    (patch-embed forward, decoder_pred dgrad: K = 16384), where the slab pass costs less than the idle SMs."""
     tiles_m = (M + 127) // 128
     num_kb = (K + 63) // 64
     tile_n = 128
@@ -42,9 +43,24 @@ def gemm_config(M: int, N: int, K: int, n_sm: int = 148):
         tile_n = 64
     tiles = tiles_m * ((N + tile_n - 1) // tile_n)
     split = 1
-    if tiles < n_sm // 2 and num_kb >= 8:
-        split = min(max(1, n_sm // tiles), max(1, num_kb // 4), 16)
+    if num_kb >= 32 and tiles <= n_sm:
+        split = min(max(1, (2 * n_sm) // tiles), max(1, num_kb // 8), 16)
     return tile_n, split
+
+
+class GrowBuf:
+    """A device byte buffer that grows on demand (never inside a CUDA-graph capture: the eager warm-up sizes it)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, nbytes: int) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes:
+            if torch.cuda.is_current_stream_capturing():
+                raise _lib.VitaeError("workspace would have to grow during CUDA-graph capture")
+            self.buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=self.device)
+        return self.buf
 
 
 _gemm_ws = {}
@@ -92,7 +108,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn_major
          ld_f32: Optional[int] = None, accumulate: bool = False, out_bf16: Optional[torch.Tensor] = None,
          out_gelu_bf16: Optional[torch.Tensor] = None, ld_bf16: Optional[int] = None,
          out_rows: Optional[torch.Tensor] = None, alpha: float = 1.0, alpha_ptr: Optional[torch.Tensor] = None,
-         tile_n: Optional[int] = None, split_k: Optional[int] = None) -> None:
+         tile_n: Optional[int] = None, split_k: Optional[int] = None, workspace: Optional[GrowBuf] = None) -> None:
     """acc[m,n] = sum_k A(m,k) B(n,k) on tcgen05 + fused epilogue; see include/vitae_b200.h."""
     lib = _lib.load()
     _req(a, _BF16, "gemm A"); _req(b, _BF16, "gemm B")
@@ -123,7 +139,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn_major
     ws_ptr, ws_bytes = None, 0
     if split_k > 1:
         ws_bytes = lib.vitae_gemm_workspace_bytes(M, N, split_k)
-        ws = _workspace(ws_bytes, a.device)
+        ws = workspace.get(ws_bytes) if workspace is not None else _workspace(ws_bytes, a.device)
         ws_ptr = ws.data_ptr()
     def launch():
         check(lib.vitae_gemm_bf16(a.data_ptr(), lda, int(a_mn_major), b.data_ptr(), ldb, int(b_mn_major), M, N, K,
@@ -145,8 +161,15 @@ def layernorm_bwd_blocks(rows: int) -> int:
     return _lib.load().vitae_layernorm_bwd_blocks(rows)
 
 
-def colsum_blocks(rows: int) -> int:
-    return _lib.load().vitae_colsum_blocks(rows)
+def colsum_workspace_bytes(rows: int, cols: int) -> int:
+    return _lib.load().vitae_colsum_workspace_bytes(rows, cols)
+
+
+def reduce_partials(partials, nblk: int, D: int, out0=None, out1=None, out2=None, accumulate: bool = False) -> None:
+    """Finishes layernorm_bwd's partials [3, nblk, D] -> (dgamma, dbeta, column sums of dx_out); None outputs skipped."""
+    lib = _lib.load()
+    check(lib.vitae_reduce_partials(partials.data_ptr(), nblk, D, _ptr(out0), _ptr(out1), _ptr(out2), int(accumulate),
+                                    _stream()), "vitae_reduce_partials")
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dx_out, dx_out_bf16, partials) -> None:
@@ -160,7 +183,10 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dx_out, dx_out_bf16, partials
 
 
 def colsum(inp, rows: int, cols: int, out, workspace, accumulate: bool = False, ld: Optional[int] = None) -> None:
+    """workspace: uint8 tensor of >= colsum_workspace_bytes(rows, cols) bytes, zero-filled at allocation (see header)."""
     lib = _lib.load()
+    if workspace.numel() * workspace.element_size() < lib.vitae_colsum_workspace_bytes(rows, cols):
+        raise _lib.VitaeError("colsum: workspace too small")
     in16 = inp.data_ptr() if inp.dtype == _BF16 else None
     in32 = inp.data_ptr() if inp.dtype == _F32 else None
     check(lib.vitae_colsum(in16, in32, rows, cols, ld if ld is not None else cols, out.data_ptr(), int(accumulate),
@@ -265,3 +291,28 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, param_bf16, n: int, lr: float, 
     check(lib.vitae_adamw_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                _ptr(param_bf16), n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, _ptr(inv_scale),
                                _ptr(found_inf), _stream()), "vitae_adamw_step")
+
+
+def optim_workspace_bytes() -> int:
+    return _lib.load().vitae_optim_workspace_bytes()
+
+
+def optim_prepare(grad, n: int, ctl, workspace, growth_factor: float, backoff_factor: float, growth_interval: int,
+                  use_scaler: bool) -> None:
+    lib = _lib.load()
+    _req(grad, _F32, "optim grad"); _req(ctl, _F32, "optim ctl")
+    check(lib.vitae_optim_prepare(grad.data_ptr(), n, ctl.data_ptr(), workspace.data_ptr(), growth_factor, backoff_factor,
+                                  growth_interval, int(use_scaler), _stream()), "vitae_optim_prepare")
+
+
+def adamw_flat(param, grad, exp_avg, exp_avg_sq, param_bf16, n: int, group_of_chunk, hyper_rows, ctl) -> None:
+    """hyper_rows: python list of (lr, beta1, beta2, eps, weight_decay) per parameter group (passed by value)."""
+    lib = _lib.load()
+    ng = len(hyper_rows)
+    host = (ctypes.c_float * (8 * ng))()
+    for i, row in enumerate(hyper_rows):
+        for j, val in enumerate(row):
+            host[8 * i + j] = float(val)
+    check(lib.vitae_adamw_flat(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                               _ptr(param_bf16), n, group_of_chunk.data_ptr(), ctypes.cast(host, ctypes.c_void_p), ng,
+                               ctl.data_ptr(), _stream()), "vitae_adamw_flat")

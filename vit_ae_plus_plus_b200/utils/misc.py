@@ -148,13 +148,55 @@ def get_grad_norm_(parameters, norm_type: float = 2.0) -> torch.Tensor:
 
 class NativeScalerWithGradNormCount:
     """Same call contract as the reference's wrapper (misc.py:251-277): scale -> backward -> (unscale, norm | clip,
-    step, update) when ``update_grad``; returns the gradient norm or None."""
+    step, update) when ``update_grad``; returns the gradient norm or None.
+
+    When ``optimizer`` is a plain ``torch.optim.AdamW`` over the parameters of one of this package's models (the
+    optimizer the k-fold scripts build, k_fold_cross_valid_combined_brats.py:168-169) and no clipping is requested,
+    unscale + norm + AdamW + scale update run as three kernels over the model's flat buffers
+    (engine.FusedAdamW) -- same arithmetic, same optimizer state layout; the loss scale then lives on the device.
+    Anything else takes the reference's torch path unchanged."""
     state_dict_key = "amp_scaler"
 
     def __init__(self):
         self._scaler = torch.amp.GradScaler("cuda")
+        self._fused = None
+        self.allow_fused = True
+
+    def _fused_for(self, optimizer, clip_grad, create_graph):
+        if not self.allow_fused or clip_grad is not None or create_graph:
+            return None
+        from ..engine import FusedAdamW
+        if not FusedAdamW.supports(optimizer):
+            return None
+        try:
+            p0 = optimizer.param_groups[0]["params"][0]
+        except (IndexError, KeyError):
+            return None
+        ref = getattr(p0, "_vitae_engine", None)
+        eng = ref() if ref is not None else None
+        if eng is None or not eng.flat.still_aliased():
+            return None
+        fo = eng.fused_optimizer()
+        if not fo.bind(optimizer):
+            return None
+        if self._fused is not fo:      # hand the loss-scale state to the device-side control block
+            sd = self._scaler.state_dict() if self._scaler.is_enabled() else {}
+            fo.ctl[0] = float(sd.get("scale", 1.0))
+            fo.ctl[1] = float(sd.get("_growth_tracker", 0))
+            self._fused = fo
+        return fo
 
     def __call__(self, loss, optimizer, clip_grad=None, parameters=None, create_graph=False, update_grad=True):
+        fo = self._fused_for(optimizer, clip_grad, create_graph)
+        if fo is not None:
+            (loss * fo.ctl[0]).backward()
+            if not update_grad:
+                return None
+            return fo.step(optimizer, self._scaler)
+        if self._fused is not None:    # leaving the fused path: give the scale state back to torch's scaler
+            self._scaler.load_state_dict(self.state_dict())
+            self._fused.sync_state(optimizer)
+            self._fused = None
         self._scaler.scale(loss).backward(create_graph=create_graph)
         if not update_grad:
             return None
@@ -169,10 +211,18 @@ class NativeScalerWithGradNormCount:
         return norm
 
     def state_dict(self):
-        return self._scaler.state_dict()
+        if self._fused is None:
+            return self._scaler.state_dict()
+        scale, tracker = self._fused.ctl[:2].tolist()
+        return {"scale": scale, "growth_factor": self._scaler.get_growth_factor(),
+                "backoff_factor": self._scaler.get_backoff_factor(),
+                "growth_interval": self._scaler.get_growth_interval(), "_growth_tracker": int(tracker)}
 
     def load_state_dict(self, state_dict):
         self._scaler.load_state_dict(state_dict)
+        if self._fused is not None and state_dict:
+            self._fused.ctl[0] = float(state_dict["scale"])
+            self._fused.ctl[1] = float(state_dict["_growth_tracker"])
 
 
 def all_reduce_mean(x):

@@ -28,6 +28,16 @@ def _rel(a, b):
     return (a.double() - b.double()).abs().max().item() / (b.double().abs().max().item() + 1e-30)
 
 
+def _signal(name, t):
+    """Drops the K third of a qkv bias: softmax is invariant to a shift of the scores along the key axis, so that
+    gradient is exactly zero in the reference's algebra (model/vit.py:117-119) and pure rounding noise in any
+    implementation -- Adam's normalisation turns that noise into +-lr steps that no two code paths reproduce."""
+    if name.endswith("attn.qkv.bias"):
+        d = t.shape[0] // 3
+        return torch.cat([t[:d], t[2 * d:]])
+    return t
+
+
 # ------------------------------------------------------------------------------------------------ optimizer kernels
 @pytest.mark.parametrize("use_scaler", [True, False])
 def test_optim_prepare_and_adamw_flat_match_torch(use_scaler):
@@ -193,14 +203,17 @@ def test_fused_optimizer_path_matches_torch_gradscaler_adamw_path():
     assert _rel(norm_f, norm_t) < 1e-4
     sd_t, sd_f = m_t.state_dict(), m_f.state_dict()
     for k in sd_t:
-        assert _rel(sd_f[k], sd_t[k]) < 2e-3, k      # Adam turns last-bit gradient differences into ~lr-sized steps
+        assert _rel(_signal(k, sd_f[k]), _signal(k, sd_t[k])) < 2e-3, k   # Adam amplifies last-bit gradient differences
     # optimizer / scaler state stays in torch's layout (checkpoints: utils/misc.py:295-312)
     m_f.engine().fused_optimizer().sync_state(opt_f)
     st_t, st_f = opt_t.state_dict()["state"], opt_f.state_dict()["state"]
     assert sorted(st_t) == sorted(st_f)
+    # tensors whose true gradient is (nearly) zero hold rounding noise only: compare them on the scale of the others
+    floor = 1e-3 * max(float(st_t[i]["exp_avg"].abs().max()) for i in st_t)
     for i in st_t:
         assert float(st_f[i]["step"]) == float(st_t[i]["step"]) == 6.0
-        assert _rel(st_f[i]["exp_avg"], st_t[i]["exp_avg"]) < 1e-3 + 1e-30
+        a, b = st_f[i]["exp_avg"].double(), st_t[i]["exp_avg"].double()
+        assert (a - b).abs().max().item() < 5e-3 * max(b.abs().max().item(), floor), i
     assert sc_f.state_dict()["scale"] == sc_t.state_dict()["scale"]
     assert sc_f.state_dict()["_growth_tracker"] == sc_t.state_dict()["_growth_tracker"] == 6
 
@@ -226,7 +239,7 @@ def test_switching_between_fused_and_torch_optimizer_paths():
         curve.append(losses[0].detach())
     assert _rel(torch.stack(curve).cpu(), curve_t) < 1e-4
     for k, v in m_t.state_dict().items():
-        assert _rel(m.state_dict()[k], v) < 2e-3, k
+        assert _rel(_signal(k, m.state_dict()[k]), _signal(k, v)) < 2e-3, k
 
 
 def test_loss_curve_100_steps_matches_oracle():

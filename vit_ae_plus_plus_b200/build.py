@@ -40,14 +40,17 @@ def _digest() -> str:
 def build(force: bool = False, verbose: bool = True) -> str:
     os.makedirs(BUILD_DIR, exist_ok=True)
     stamp = os.path.join(BUILD_DIR, "digest.txt")
-    digest = _digest()
+    flags = list(NVCC_FLAGS)
+    if os.environ.get("VITAE_TRACE") == "1":      # debug build: per-phase clock stamps in the GEMM (tools/gemm_trace.py)
+        flags.append("-DVITAE_GEMM_TRACE")
+    digest = _digest() + ("+trace" if "-DVITAE_GEMM_TRACE" in flags else "")
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB_PATH
     nvcc = _nvcc()
 
     def compile_one(src):
         obj = os.path.join(BUILD_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

@@ -1,5 +1,6 @@
 // Error reporting + device check for libvitae_b200.so.
 #include "common.h"
+#include <stdlib.h>
 
 namespace vitae {
 static thread_local char g_err[512] = "";
@@ -10,6 +11,13 @@ int set_error(int code, const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
+}
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("VITAE_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 }  // namespace vitae
 

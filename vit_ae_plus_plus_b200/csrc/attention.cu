@@ -101,6 +101,8 @@ template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N, int H,
                 float scale_log2) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int LD = HD + 8;
     __shared__ __align__(16) __nv_bfloat16 sQ[TILE * LD];
     __shared__ __align__(16) __nv_bfloat16 sK[2][TILE * LD];
@@ -195,6 +197,8 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
 __global__ void __launch_bounds__(256)
 attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout, float* __restrict__ delta,
                       int BN, int N, int H, int hd) {
+    pdl_trigger();
+    pdl_wait();
     const int tok = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (tok >= BN) return;
     const int lane = threadIdx.x & 31;
@@ -227,6 +231,8 @@ template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale, float scale_log2) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int LD = HD + 8;
     __shared__ __align__(16) __nv_bfloat16 sQ[TILE * LD];
     __shared__ __align__(16) __nv_bfloat16 sdO[TILE * LD];
@@ -301,6 +307,8 @@ template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
                     const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale, float scale_log2) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int LD = HD + 8;
     __shared__ __align__(16) __nv_bfloat16 sQ[TILE * LD];
     __shared__ __align__(16) __nv_bfloat16 sdO[TILE * LD];
@@ -393,11 +401,11 @@ extern "C" int vitae_attention_fwd(const void* qkv, void* out, float* lse, int B
     dim3 grid(ceil_div(N, TILE), H, B);
     const float sl2 = scale * LOG2E;
     if (hd == 64)
-        attn_fwd_kernel<64><<<grid, ATT_THREADS, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, N, H, sl2);
+        launch_kernel(attn_fwd_kernel<64>, dim3(grid), dim3(ATT_THREADS), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, N, H, sl2);
     else if (hd == 32)
-        attn_fwd_kernel<32><<<grid, ATT_THREADS, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, N, H, sl2);
+        launch_kernel(attn_fwd_kernel<32>, dim3(grid), dim3(ATT_THREADS), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, N, H, sl2);
     else
-        attn_fwd_kernel<16><<<grid, ATT_THREADS, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, N, H, sl2);
+        launch_kernel(attn_fwd_kernel<16>, dim3(grid), dim3(ATT_THREADS), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, N, H, sl2);
     VITAE_CHECK_LAUNCH("attention_fwd");
     return 0;
 }
@@ -411,22 +419,22 @@ extern "C" int vitae_attention_bwd(const void* qkv, const void* out, const void*
     const auto* o = static_cast<const __nv_bfloat16*>(out);
     const auto* g = static_cast<const __nv_bfloat16*>(dout);
     auto* dq = static_cast<__nv_bfloat16*>(dqkv);
-    attn_bwd_delta_kernel<<<ceil_div(B * N, 8), 256, 0, st>>>(o, g, delta, B * N, N, H, hd);
+    launch_kernel(attn_bwd_delta_kernel, dim3(ceil_div(B * N, 8)), dim3(256), 0, st, o, g, delta, B * N, N, H, hd);
     VITAE_CHECK_LAUNCH("attention_bwd_delta");
     dim3 grid(ceil_div(N, TILE), H, B);
     const float sl2 = scale * LOG2E;
     if (hd == 64) {
-        attn_bwd_dq_kernel<64><<<grid, ATT_THREADS, 0, st>>>(q, g, lse, delta, dq, N, H, scale, sl2);
+        launch_kernel(attn_bwd_dq_kernel<64>, dim3(grid), dim3(ATT_THREADS), 0, st, q, g, lse, delta, dq, N, H, scale, sl2);
         VITAE_CHECK_LAUNCH("attention_bwd_dq");
-        attn_bwd_dkv_kernel<64><<<grid, ATT_THREADS, 0, st>>>(q, g, lse, delta, dq, N, H, scale, sl2);
+        launch_kernel(attn_bwd_dkv_kernel<64>, dim3(grid), dim3(ATT_THREADS), 0, st, q, g, lse, delta, dq, N, H, scale, sl2);
     } else if (hd == 32) {
-        attn_bwd_dq_kernel<32><<<grid, ATT_THREADS, 0, st>>>(q, g, lse, delta, dq, N, H, scale, sl2);
+        launch_kernel(attn_bwd_dq_kernel<32>, dim3(grid), dim3(ATT_THREADS), 0, st, q, g, lse, delta, dq, N, H, scale, sl2);
         VITAE_CHECK_LAUNCH("attention_bwd_dq");
-        attn_bwd_dkv_kernel<32><<<grid, ATT_THREADS, 0, st>>>(q, g, lse, delta, dq, N, H, scale, sl2);
+        launch_kernel(attn_bwd_dkv_kernel<32>, dim3(grid), dim3(ATT_THREADS), 0, st, q, g, lse, delta, dq, N, H, scale, sl2);
     } else {
-        attn_bwd_dq_kernel<16><<<grid, ATT_THREADS, 0, st>>>(q, g, lse, delta, dq, N, H, scale, sl2);
+        launch_kernel(attn_bwd_dq_kernel<16>, dim3(grid), dim3(ATT_THREADS), 0, st, q, g, lse, delta, dq, N, H, scale, sl2);
         VITAE_CHECK_LAUNCH("attention_bwd_dq");
-        attn_bwd_dkv_kernel<16><<<grid, ATT_THREADS, 0, st>>>(q, g, lse, delta, dq, N, H, scale, sl2);
+        launch_kernel(attn_bwd_dkv_kernel<16>, dim3(grid), dim3(ATT_THREADS), 0, st, q, g, lse, delta, dq, N, H, scale, sl2);
     }
     VITAE_CHECK_LAUNCH("attention_bwd_dkv");
     return 0;

@@ -32,4 +32,28 @@ __host__ __device__ constexpr T ceil_div(T a, T b) {
     return (a + b - 1) / b;
 }
 
+// Programmatic dependent launch (PDL): every kernel of this library is enqueued with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so that its launch latency and prologue (barrier init, TMEM
+// allocation, descriptor prefetch) overlap the tail of its stream predecessor; inside a CUDA-graph capture the
+// attribute becomes a programmatic edge.  Contract for every kernel: call pdl_trigger() once its CTA holds all the
+// on-chip resources it will ever acquire, and pdl_wait() before its first global-memory access (ptx.cuh).
+// VITAE_PDL=0 in the environment launches with plain stream serialisation instead (A/B measurements).
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace vitae

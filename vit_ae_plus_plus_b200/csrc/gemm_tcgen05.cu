@@ -102,6 +102,23 @@ __device__ __forceinline__ void epilogue_group8(const EpiParams& ep, float alpha
     }
 }
 
+// Phase tracing (debug builds only: VITAE_TRACE=1 python -m vit_ae_plus_plus_b200.build): per CTA, SM-clock stamps of the
+// kernel phases are written to a device buffer registered with vitae_debug_set_gemm_trace (tools/gemm_trace.py).
+#ifdef VITAE_GEMM_TRACE
+__device__ unsigned long long* g_gemm_trace = nullptr;
+#define GEMM_TRACE(slot)                                                                                      \
+    do {                                                                                                      \
+        if (g_gemm_trace) {                                                                                   \
+            const int cta__ = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;                 \
+            unsigned long long t__;                                                                           \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                                           \
+            g_gemm_trace[cta__ * 16 + (slot)] = t__;                                                          \
+        }                                                                                                     \
+    } while (0)
+#else
+#define GEMM_TRACE(slot) do { } while (0)
+#endif
+
 template <int BN, int STAGES>
 struct GemmSmem {
     static constexpr int A_BYTES = BM * BK * 2;
@@ -133,6 +150,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int kb_begin = blockIdx.z * kb_per_split;
     const int kb_end = min(num_kb, kb_begin + kb_per_split);
     const int nkb = kb_end - kb_begin;
+    if (threadIdx.x == 0) GEMM_TRACE(0);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -155,6 +173,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // PDL: this CTA now holds everything it will ever acquire (smem, TMEM columns), so the next kernel in the stream may
+    // start its own prologue; our first global access (TMA loads, epilogue operands) waits for the predecessor grid.
+    if (threadIdx.x == 0) GEMM_TRACE(1);
+    pdl_trigger();
+    pdl_wait();
+    if (threadIdx.x == 0) GEMM_TRACE(2);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -179,7 +203,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 } else {
                     tma_load_2d(sb, &tmB, full_bar + s * 8, k0, n0);
                 }
+                if (i == 0) GEMM_TRACE(3);
             }
+            GEMM_TRACE(4);
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -191,6 +217,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 const uint32_t ph = (i / STAGES) & 1;
                 mbar_wait(full_bar + s * 8, ph);
                 tc_fence_after();
+                if (i == 0) GEMM_TRACE(5);
                 const uint32_t sa = base + s * S::STAGE_BYTES;
                 const uint32_t sb = sa + S::A_BYTES;
 #pragma unroll
@@ -205,12 +232,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 umma_commit(empty_bar + s * 8);  // frees the smem stage once these MMAs retire
             }
             umma_commit(tmem_full_bar);
+            GEMM_TRACE(6);
         }
         __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue warps (TMEM -> regs -> HBM)
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
+        if (threadIdx.x == 64) GEMM_TRACE(7);
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
         const int m = m0 + q * 32 + lane;
         const float alpha = ep.alpha * (ep.alpha_ptr ? *ep.alpha_ptr : 1.0f);
@@ -241,13 +270,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
         }
         tc_fence_before();
+        if (threadIdx.x == 64) GEMM_TRACE(8);
     }
     __syncthreads();
+    if (threadIdx.x == 0) GEMM_TRACE(9);
     if (warp == 2) tmem_dealloc(tmem_base, BN);
 }
 
 // Split-K finalize: sum the slabs in fixed order, then the fused epilogue.
 __global__ void gemm_splitk_finalize_kernel(const float* __restrict__ slabs, int splits, int M, int N, EpiParams ep) {
+    if (threadIdx.x == 0) GEMM_TRACE(1);
+    pdl_trigger();
+    pdl_wait();
+    if (threadIdx.x == 0) GEMM_TRACE(2);
     const int groups_per_row = N / 8;
     const long long total = static_cast<long long>(M) * groups_per_row;
     const float alpha = ep.alpha * (ep.alpha_ptr ? *ep.alpha_ptr : 1.0f);
@@ -348,12 +383,12 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int 
     const int kb_per_split = ceil_div(num_kb, splits);
     const int eff_splits = ceil_div(num_kb, kb_per_split);  // every z-slice gets >= 1 k-block
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), eff_splits);
-    kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ta, tb, M, N, num_kb, kb_per_split, ep, slabs);
+    launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS), S::TOTAL, stream, ta, tb, M, N, num_kb, kb_per_split, ep, slabs);
     VITAE_CHECK_LAUNCH("gemm_bf16_tcgen05");
     if (slabs) {
         const long long total = static_cast<long long>(M) * (N / 8);
         const int blocks = static_cast<int>(std::min<long long>(ceil_div<long long>(total, 256), 148 * 8));
-        gemm_splitk_finalize_kernel<<<blocks, 256, 0, stream>>>(slabs, eff_splits, M, N, ep);
+        launch_kernel(gemm_splitk_finalize_kernel, dim3(blocks), dim3(256), 0, stream, slabs, eff_splits, M, N, ep);
         VITAE_CHECK_LAUNCH("gemm_splitk_finalize");
     }
     return 0;
@@ -371,6 +406,13 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUt
 }  // namespace vitae
 
 using namespace vitae;
+
+#ifdef VITAE_GEMM_TRACE
+extern "C" int vitae_debug_set_gemm_trace(void* buf) {
+    cudaError_t e = cudaMemcpyToSymbol(g_gemm_trace, &buf, sizeof(buf));
+    return e == cudaSuccess ? 0 : set_error(-3, "set_gemm_trace: %s", cudaGetErrorString(e));
+}
+#endif
 
 extern "C" size_t vitae_gemm_workspace_bytes(int M, int N, int split_k) {
     if (split_k <= 1) return 0;

@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      __nv_bfloat16* __restrict__ y16, float* __restrict__ y32, float* __restrict__ mean,
                      float* __restrict__ rstd, int rows, int D, float eps) {
+    pdl_trigger();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nvec = D >> 2;  // float4 per row
     for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
@@ -82,6 +84,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ dx_in, float* __restrict__ dx_out, __nv_bfloat16* __restrict__ dx16,
                      float* __restrict__ partials, int rows, int D) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[LN_WARPS][32 * 4 + 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nvec = D >> 2;
@@ -172,25 +176,36 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
     }
 }
 
-// out[part][col] (+)= sum_blk partials[part][blk][col]: finishes LayerNorm-backward partials (up to 3 outputs, 1 launch)
+// out[part][col] (+)= sum_blk partials[part][blk][col]: finishes LayerNorm-backward partials (up to 3 outputs, 1 launch).
+// Block = 32 columns x 8 row lanes; lane ty adds blocks ty, ty+8, ...; the 8 lane sums are added in fixed order.
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ partials, int nblk, int D, float* __restrict__ out0,
                        float* __restrict__ out1, float* __restrict__ out2, int accumulate) {
-    const int col = blockIdx.x * 256 + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + tx;
     float* out = blockIdx.y == 0 ? out0 : (blockIdx.y == 1 ? out1 : out2);
-    if (col >= D || out == nullptr) return;
-    const float* p = partials + static_cast<size_t>(blockIdx.y) * nblk * D + col;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int b = 0;
-    for (; b + 4 <= nblk; b += 4) {
-        s0 += p[static_cast<size_t>(b) * D];
-        s1 += p[static_cast<size_t>(b + 1) * D];
-        s2 += p[static_cast<size_t>(b + 2) * D];
-        s3 += p[static_cast<size_t>(b + 3) * D];
+    if (out == nullptr) return;
+    float s0 = 0.f, s1 = 0.f;
+    if (col < D) {
+        const float* p = partials + static_cast<size_t>(blockIdx.y) * nblk * D + col;
+        int b = ty;
+        for (; b + 8 < nblk; b += 16) {
+            s0 += p[static_cast<size_t>(b) * D];
+            s1 += p[static_cast<size_t>(b + 8) * D];
+        }
+        if (b < nblk) s0 += p[static_cast<size_t>(b) * D];
     }
-    for (; b < nblk; ++b) s0 += p[static_cast<size_t>(b) * D];
-    const float s = (s0 + s1) + (s2 + s3);
-    out[col] = accumulate ? out[col] + s : s;
+    red[ty][tx] = s0 + s1;
+    __syncthreads();
+    if (ty == 0 && col < D) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][tx];
+        out[col] = accumulate ? out[col] + s : s;
+    }
 }
 
 // Column sums in ONE launch.  Block (bx, by): 256 columns starting at bx*256 (lane = 8 consecutive columns, a warp
@@ -223,6 +238,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ in, int rows, int cols, int ld, float* __restrict__ out, int accumulate,
               float* __restrict__ ws_partials, unsigned int* __restrict__ counters, int rows_per_slice) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[8][CS_COLS + 8];
     __shared__ unsigned int ticket_sh;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -290,7 +307,7 @@ extern "C" int vitae_layernorm_fwd(const float* x, const float* gamma, const flo
     const int blocks = std::min(ceil_div(rows, LN_WARPS), 148 * 4);
     auto* y16 = static_cast<__nv_bfloat16*>(y_bf16);
     cudaStream_t st = as_stream(stream);
-#define VITAE_LN_FWD(V) layernorm_fwd_kernel<V><<<blocks, LN_WARPS * 32, 0, st>>>(x, gamma, beta, y16, y_f32, mean, rstd, rows, D, eps)
+#define VITAE_LN_FWD(V) launch_kernel(layernorm_fwd_kernel<V>, dim3(blocks), dim3(LN_WARPS * 32), 0, st, x, gamma, beta, y16, y_f32, mean, rstd, rows, D, eps)
     switch (ln_vec_class(D)) {
         case 1: VITAE_LN_FWD(1); break;
         case 2: VITAE_LN_FWD(2); break;
@@ -315,7 +332,7 @@ extern "C" int vitae_layernorm_bwd(const void* dy_bf16, const float* dy_f32, con
     const auto* dy16 = static_cast<const __nv_bfloat16*>(dy_bf16);
     auto* dx16 = static_cast<__nv_bfloat16*>(dx_out_bf16);
     cudaStream_t st = as_stream(stream);
-#define VITAE_LN_BWD(V) layernorm_bwd_kernel<V><<<blocks, LN_WARPS * 32, 0, st>>>(dy16, dy_f32, x, gamma, mean, rstd, dx_in, dx_out, dx16, partials, rows, D)
+#define VITAE_LN_BWD(V) launch_kernel(layernorm_bwd_kernel<V>, dim3(blocks), dim3(LN_WARPS * 32), 0, st, dy16, dy_f32, x, gamma, mean, rstd, dx_in, dx_out, dx16, partials, rows, D)
     switch (ln_vec_class(D)) {
         case 1: VITAE_LN_BWD(1); break;
         case 2: VITAE_LN_BWD(2); break;
@@ -331,8 +348,8 @@ extern "C" int vitae_layernorm_bwd(const void* dy_bf16, const float* dy_f32, con
 extern "C" int vitae_reduce_partials(const float* partials, int nblk, int D, float* out0, float* out1, float* out2,
                                      int accumulate, void* stream) {
     VITAE_REQUIRE(partials && nblk > 0 && D > 0 && (out0 || out1 || out2), "reduce_partials: bad arguments");
-    dim3 grid(ceil_div(D, 256), 3);
-    reduce_partials_kernel<<<grid, 256, 0, as_stream(stream)>>>(partials, nblk, D, out0, out1, out2, accumulate);
+    dim3 grid(ceil_div(D, 32), 3);
+    launch_kernel(reduce_partials_kernel, dim3(grid), dim3(256), 0, as_stream(stream), partials, nblk, D, out0, out1, out2, accumulate);
     VITAE_CHECK_LAUNCH("reduce_partials");
     return 0;
 }
@@ -362,9 +379,9 @@ extern "C" int vitae_colsum(const void* in_bf16, const float* in_f32, int rows, 
     auto* parts = reinterpret_cast<float*>(static_cast<char*>(workspace) + ((static_cast<size_t>(strips) * sizeof(unsigned int) + 255) / 256) * 256);
     dim3 grid(strips, eff_slices);
     if (in_bf16)
-        colsum_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(in_bf16), rows, cols, ld, out, accumulate, parts, counters, rows_per_slice);
+        launch_kernel(colsum_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(in_bf16), rows, cols, ld, out, accumulate, parts, counters, rows_per_slice);
     else
-        colsum_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(in_f32, rows, cols, ld, out, accumulate, parts, counters, rows_per_slice);
+        launch_kernel(colsum_kernel<float>, dim3(grid), dim3(256), 0, as_stream(stream), in_f32, rows, cols, ld, out, accumulate, parts, counters, rows_per_slice);
     VITAE_CHECK_LAUNCH("colsum");
     return 0;
 }

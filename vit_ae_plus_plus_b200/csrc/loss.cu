@@ -49,6 +49,8 @@ template <typename T, int CT>
 __global__ void __launch_bounds__(256)
 masked_mse_fwd_kernel(const T* __restrict__ pred, const float* __restrict__ vol, const float* __restrict__ mask,
                       float* __restrict__ patch_sums, int Crt, int V, int p, int g) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sh[8];
     const int C = CT ? CT : Crt;
     const int L = g * g * g;
@@ -90,6 +92,8 @@ masked_mse_fwd_kernel(const T* __restrict__ pred, const float* __restrict__ vol,
 __global__ void __launch_bounds__(256)
 masked_mse_finalize_kernel(const float* __restrict__ patch_sums, const float* __restrict__ mask, int n, float P,
                            float* __restrict__ loss_out) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sh[8];
     float s = 0.f, m = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -110,6 +114,8 @@ __global__ void __launch_bounds__(256)
 masked_mse_bwd_kernel(const T* __restrict__ pred, const float* __restrict__ vol, const float* __restrict__ mask,
                       const float* __restrict__ mask_sum, const float* __restrict__ dloss,
                       __nv_bfloat16* __restrict__ dpred, int Crt, int V, int p, int g) {
+    pdl_trigger();
+    pdl_wait();
     const int C = CT ? CT : Crt;
     const int L = g * g * g;
     const int b = blockIdx.x / (L + 1), t = blockIdx.x % (L + 1);  // token row incl. cls
@@ -158,12 +164,12 @@ static int launch_fwd(const T* pred, const float* vol, const float* mask, float*
                       int V, int p, cudaStream_t st) {
     const int g = V / p, L = g * g * g;
     const int n = B * L;
-    if (C == 4) masked_mse_fwd_kernel<T, 4><<<n, 256, 0, st>>>(pred, vol, mask, patch_sums, C, V, p, g);
-    else if (C == 1) masked_mse_fwd_kernel<T, 1><<<n, 256, 0, st>>>(pred, vol, mask, patch_sums, C, V, p, g);
-    else if (C == 2) masked_mse_fwd_kernel<T, 2><<<n, 256, 0, st>>>(pred, vol, mask, patch_sums, C, V, p, g);
-    else masked_mse_fwd_kernel<T, 0><<<n, 256, 0, st>>>(pred, vol, mask, patch_sums, C, V, p, g);
+    if (C == 4) launch_kernel(masked_mse_fwd_kernel<T, 4>, dim3(n), dim3(256), 0, st, pred, vol, mask, patch_sums, C, V, p, g);
+    else if (C == 1) launch_kernel(masked_mse_fwd_kernel<T, 1>, dim3(n), dim3(256), 0, st, pred, vol, mask, patch_sums, C, V, p, g);
+    else if (C == 2) launch_kernel(masked_mse_fwd_kernel<T, 2>, dim3(n), dim3(256), 0, st, pred, vol, mask, patch_sums, C, V, p, g);
+    else launch_kernel(masked_mse_fwd_kernel<T, 0>, dim3(n), dim3(256), 0, st, pred, vol, mask, patch_sums, C, V, p, g);
     VITAE_CHECK_LAUNCH("masked_mse_fwd");
-    masked_mse_finalize_kernel<<<1, 256, 0, st>>>(patch_sums, mask, n, static_cast<float>(p) * p * p * C, loss_out);
+    launch_kernel(masked_mse_finalize_kernel, dim3(1), dim3(256), 0, st, patch_sums, mask, n, static_cast<float>(p) * p * p * C, loss_out);
     VITAE_CHECK_LAUNCH("masked_mse_finalize");
     return 0;
 }
@@ -173,8 +179,8 @@ static int launch_bwd(const T* pred, const float* vol, const float* mask, const 
                       __nv_bfloat16* dpred, int B, int C, int V, int p, cudaStream_t st) {
     const int g = V / p, L = g * g * g;
     const int n = B * (L + 1);
-    if (C == 4) masked_mse_bwd_kernel<T, 4><<<n, 256, 0, st>>>(pred, vol, mask, mask_sum, dloss, dpred, C, V, p, g);
-    else masked_mse_bwd_kernel<T, 0><<<n, 256, 0, st>>>(pred, vol, mask, mask_sum, dloss, dpred, C, V, p, g);
+    if (C == 4) launch_kernel(masked_mse_bwd_kernel<T, 4>, dim3(n), dim3(256), 0, st, pred, vol, mask, mask_sum, dloss, dpred, C, V, p, g);
+    else launch_kernel(masked_mse_bwd_kernel<T, 0>, dim3(n), dim3(256), 0, st, pred, vol, mask, mask_sum, dloss, dpred, C, V, p, g);
     VITAE_CHECK_LAUNCH("masked_mse_bwd");
     return 0;
 }

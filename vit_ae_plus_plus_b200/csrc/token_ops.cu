@@ -16,6 +16,8 @@ namespace vitae {
 __global__ void __launch_bounds__(1024)
 random_masking_kernel(const float* __restrict__ noise, int* __restrict__ ids_shuffle, int* __restrict__ ids_restore,
                       float* __restrict__ mask, int L, int Lpow2, int len_keep) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ unsigned long long keys[];
     const int b = blockIdx.x;
     for (int i = threadIdx.x; i < Lpow2; i += blockDim.x) {
@@ -59,6 +61,8 @@ random_masking_kernel(const float* __restrict__ noise, int* __restrict__ ids_shu
 __global__ void __launch_bounds__(256)
 im2col_patches_kernel(const float* __restrict__ vol, const int* __restrict__ ids_shuffle, __nv_bfloat16* __restrict__ cols,
                       int C, int V, int p, int g, int L, int keep) {
+    pdl_trigger();
+    pdl_wait();
     const int row = blockIdx.x;  // b*keep + j
     const int b = row / keep, j = row % keep;
     const int patch = ids_shuffle[static_cast<size_t>(b) * L + j];
@@ -90,6 +94,8 @@ build_row_maps_kernel(const int* __restrict__ ids_shuffle, int B, int L, int kee
                       int* __restrict__ enc_cls_rows, int* __restrict__ pe_pos_rows, int* __restrict__ dec_rows_of_enc,
                       int* __restrict__ dec_pos_rows_of_enc, int* __restrict__ masked_dec_rows,
                       int* __restrict__ masked_pos_rows) {
+    pdl_trigger();
+    pdl_wait();
     const int Ne = keep + 1, Nd = L + 1, nmask = L - keep;
     const int total = B * L;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -116,6 +122,8 @@ build_row_maps_kernel(const int* __restrict__ ids_shuffle, int B, int L, int kee
 __global__ void __launch_bounds__(128)
 fill_rows_kernel(float* __restrict__ dst, const int* __restrict__ row_idx, int D, const float* __restrict__ src0,
                  const int* __restrict__ src0_rows, const float* __restrict__ src1, const int* __restrict__ src1_rows) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x;
     const int r = row_idx ? row_idx[i] : i;
     const float* a = src0 + static_cast<size_t>(src0_rows ? src0_rows[i] : 0) * D;
@@ -133,6 +141,8 @@ fill_rows_kernel(float* __restrict__ dst, const int* __restrict__ row_idx, int D
 __global__ void __launch_bounds__(128)
 gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ row_idx, int D, __nv_bfloat16* __restrict__ dst16,
                    float* __restrict__ dst32) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x;
     const float* a = src + static_cast<size_t>(row_idx ? row_idx[i] : i) * D;
     for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {
@@ -147,15 +157,37 @@ gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ row_id
     }
 }
 
-// out[d] (+)= sum_i src[row_idx[i], d]; grid over column chunks, rows summed in fixed order (deterministic)
-__global__ void __launch_bounds__(128)
+// out[d] (+)= sum_i src[row_idx[i], d]; block = 32 columns x 32 row lanes: lane ty sums rows ty, ty+32, ... (4 loads in
+// flight), then the 32 lane sums are added in fixed order (deterministic)
+__global__ void __launch_bounds__(1024)
 sum_rows_kernel(const float* __restrict__ src, const int* __restrict__ row_idx, int nrows, int D, float* __restrict__ out,
                 int accumulate) {
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= D) return;
-    float s = 0.f;
-    for (int i = 0; i < nrows; ++i) s += src[static_cast<size_t>(row_idx ? row_idx[i] : i) * D + d];
-    out[d] = accumulate ? out[d] + s : s;
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float red[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int d = blockIdx.x * 32 + tx;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (d < D) {
+        int i = ty;
+        for (; i + 96 < nrows; i += 128) {
+            const int r0 = row_idx ? row_idx[i] : i, r1 = row_idx ? row_idx[i + 32] : i + 32;
+            const int r2 = row_idx ? row_idx[i + 64] : i + 64, r3 = row_idx ? row_idx[i + 96] : i + 96;
+            s0 += src[static_cast<size_t>(r0) * D + d];
+            s1 += src[static_cast<size_t>(r1) * D + d];
+            s2 += src[static_cast<size_t>(r2) * D + d];
+            s3 += src[static_cast<size_t>(r3) * D + d];
+        }
+        for (; i < nrows; i += 32) s0 += src[static_cast<size_t>(row_idx ? row_idx[i] : i) * D + d];
+    }
+    red[ty][tx] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (ty == 0 && d < D) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s += red[k][tx];
+        out[d] = accumulate ? out[d] + s : s;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -170,6 +202,8 @@ constexpr int CAST_CHUNK = 4096;  // elements per work item
 
 __global__ void __launch_bounds__(256)
 cast_params_kernel(const CastRecord* __restrict__ table, int ntensors, __nv_bfloat16* __restrict__ dst) {
+    pdl_trigger();
+    pdl_wait();
     // blockIdx.y = tensor, blockIdx.x strides over that tensor's chunks
     const CastRecord rec = table[blockIdx.y];
     const float* src = reinterpret_cast<const float*>(rec.src);
@@ -205,6 +239,8 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              __nv_bfloat16* __restrict__ p16, long long n, float lr, float b1, float b2, float eps, float wd, float bc1,
              float bc2, const float* __restrict__ inv_scale, const float* __restrict__ found_inf) {
+    pdl_trigger();
+    pdl_wait();
     if (found_inf && *found_inf != 0.f) return;
     const float is = inv_scale ? *inv_scale : 1.f;
     const float step_size = lr / bc1;
@@ -255,6 +291,8 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 grad_sqnorm_kernel(const float* __restrict__ g, long long n, float* __restrict__ partials) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sh[8];
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     const long long n4 = n >> 2;
@@ -281,6 +319,8 @@ grad_sqnorm_kernel(const float* __restrict__ g, long long n, float* __restrict__
 __global__ void __launch_bounds__(256)
 optim_finalize_kernel(const float* __restrict__ partials, int nblk, float* __restrict__ ctl, float growth_factor,
                       float backoff_factor, int growth_interval, int use_scaler) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ double sh[256];
     double s = 0.0;
     for (int i = threadIdx.x; i < nblk; i += 256) s += static_cast<double>(partials[i]);
@@ -326,6 +366,8 @@ __global__ void __launch_bounds__(256)
 adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                   __nv_bfloat16* __restrict__ p16, long long n, const unsigned char* __restrict__ group_of_chunk,
                   const AdamHyper hyper, int ngroups, const float* __restrict__ ctl) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float hs[8][8];   // per group: lr*wd factor, b1, b2, eps, step_size, inv_sqrt_bc2
     if (ctl[2] != 0.f) return;   // inf / nan gradients: GradScaler skips the step
     if (threadIdx.x < ngroups) {
@@ -385,7 +427,7 @@ extern "C" int vitae_random_masking(const float* noise, int32_t* ids_shuffle, in
     int lp = 2;
     while (lp < L) lp <<= 1;
     const int threads = std::min(1024, std::max(32, lp / 2));
-    random_masking_kernel<<<B, threads, lp * sizeof(unsigned long long), as_stream(stream)>>>(noise, ids_shuffle, ids_restore, mask, L, lp, len_keep);
+    launch_kernel(random_masking_kernel, dim3(B), dim3(threads), lp * sizeof(unsigned long long), as_stream(stream), noise, ids_shuffle, ids_restore, mask, L, lp, len_keep);
     VITAE_CHECK_LAUNCH("random_masking");
     return 0;
 }
@@ -398,7 +440,7 @@ extern "C" int vitae_build_row_maps(const int32_t* ids_shuffle, int B, int L, in
                       masked_dec_rows && masked_pos_rows, "build_row_maps: null pointer");
     VITAE_REQUIRE(B > 0 && L > 0 && keep > 0 && keep <= L, "build_row_maps: bad sizes B=%d L=%d keep=%d", B, L, keep);
     const int blocks = std::min(ceil_div(B * L, 256), 148);
-    build_row_maps_kernel<<<blocks, 256, 0, as_stream(stream)>>>(ids_shuffle, B, L, keep, enc_tok_rows, enc_cls_rows, pe_pos_rows,
+    launch_kernel(build_row_maps_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), ids_shuffle, B, L, keep, enc_tok_rows, enc_cls_rows, pe_pos_rows,
                                                                  dec_rows_of_enc, dec_pos_rows_of_enc, masked_dec_rows, masked_pos_rows);
     VITAE_CHECK_LAUNCH("build_row_maps");
     return 0;
@@ -410,7 +452,7 @@ extern "C" int vitae_im2col_patches(const float* vol, const int32_t* ids_shuffle
     VITAE_REQUIRE(p % 4 == 0 && V % p == 0 && keep > 0, "im2col: need p %% 4 == 0 and V %% p == 0 (V=%d p=%d)", V, p);
     const int g = V / p;
     VITAE_REQUIRE(g * g * g == L, "im2col: L=%d does not match (V/p)^3", L);
-    im2col_patches_kernel<<<B * keep, 256, 0, as_stream(stream)>>>(vol, ids_shuffle, static_cast<__nv_bfloat16*>(cols_bf16), C, V, p, g, L, keep);
+    launch_kernel(im2col_patches_kernel, dim3(B * keep), dim3(256), 0, as_stream(stream), vol, ids_shuffle, static_cast<__nv_bfloat16*>(cols_bf16), C, V, p, g, L, keep);
     VITAE_CHECK_LAUNCH("im2col_patches");
     return 0;
 }
@@ -419,7 +461,7 @@ extern "C" int vitae_fill_rows(float* dst, const int32_t* row_idx, int nrows, in
                                const int32_t* src0_rows, const float* src1, const int32_t* src1_rows, void* stream) {
     VITAE_REQUIRE(dst && src0 && nrows >= 0 && D % 4 == 0, "fill_rows: bad arguments");
     if (nrows == 0) return 0;
-    fill_rows_kernel<<<nrows, 128, 0, as_stream(stream)>>>(dst, row_idx, D, src0, src0_rows, src1, src1_rows);
+    launch_kernel(fill_rows_kernel, dim3(nrows), dim3(128), 0, as_stream(stream), dst, row_idx, D, src0, src0_rows, src1, src1_rows);
     VITAE_CHECK_LAUNCH("fill_rows");
     return 0;
 }
@@ -428,7 +470,7 @@ extern "C" int vitae_gather_rows(const float* src, const int32_t* row_idx, int n
                                  float* dst_f32, void* stream) {
     VITAE_REQUIRE(src && (dst_bf16 || dst_f32) && nrows >= 0 && D % 4 == 0, "gather_rows: bad arguments");
     if (nrows == 0) return 0;
-    gather_rows_kernel<<<nrows, 128, 0, as_stream(stream)>>>(src, row_idx, D, static_cast<__nv_bfloat16*>(dst_bf16), dst_f32);
+    launch_kernel(gather_rows_kernel, dim3(nrows), dim3(128), 0, as_stream(stream), src, row_idx, D, static_cast<__nv_bfloat16*>(dst_bf16), dst_f32);
     VITAE_CHECK_LAUNCH("gather_rows");
     return 0;
 }
@@ -436,7 +478,7 @@ extern "C" int vitae_gather_rows(const float* src, const int32_t* row_idx, int n
 extern "C" int vitae_sum_rows(const float* src, const int32_t* row_idx, int nrows, int D, float* out, int accumulate,
                               void* stream) {
     VITAE_REQUIRE(src && out && nrows >= 0 && D > 0, "sum_rows: bad arguments");
-    sum_rows_kernel<<<ceil_div(D, 128), 128, 0, as_stream(stream)>>>(src, row_idx, nrows, D, out, accumulate);
+    launch_kernel(sum_rows_kernel, dim3(ceil_div(D, 32)), dim3(1024), 0, as_stream(stream), src, row_idx, nrows, D, out, accumulate);
     VITAE_CHECK_LAUNCH("sum_rows");
     return 0;
 }
@@ -447,7 +489,7 @@ extern "C" int vitae_cast_params_bf16(const void* table, int ntensors, void* dst
     const long long avg = total_elems / ntensors + 1;
     int bx = static_cast<int>(std::min<long long>(64, std::max<long long>(1, (4 * avg) / CAST_CHUNK)));
     dim3 grid(bx, ntensors);
-    cast_params_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const CastRecord*>(table), ntensors, static_cast<__nv_bfloat16*>(dst_bf16));
+    launch_kernel(cast_params_kernel, dim3(grid), dim3(256), 0, as_stream(stream), static_cast<const CastRecord*>(table), ntensors, static_cast<__nv_bfloat16*>(dst_bf16));
     VITAE_CHECK_LAUNCH("cast_params");
     return 0;
 }
@@ -458,7 +500,7 @@ extern "C" int vitae_adamw_step(float* param, const float* grad, float* exp_avg,
                                 void* stream) {
     VITAE_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0, "adamw: bad arguments");
     const int blocks = static_cast<int>(std::min<long long>(ceil_div<long long>(n, 1024), 148 * 8));
-    adamw_kernel<<<blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, static_cast<__nv_bfloat16*>(param_bf16), n, lr,
+    launch_kernel(adamw_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), param, grad, exp_avg, exp_avg_sq, static_cast<__nv_bfloat16*>(param_bf16), n, lr,
                                                         beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, inv_scale, found_inf);
     VITAE_CHECK_LAUNCH("adamw");
     return 0;
@@ -473,9 +515,9 @@ extern "C" int vitae_optim_prepare(const float* grad, long long n, float* ctl, f
     VITAE_REQUIRE(grad && ctl && workspace && n > 0, "optim_prepare: bad arguments");
     VITAE_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0, "optim_prepare: grad must be 16-byte aligned");
     const int blocks = static_cast<int>(std::min<long long>(ceil_div<long long>(n, 1024), OPT_NORM_BLOCKS));
-    grad_sqnorm_kernel<<<blocks, 256, 0, as_stream(stream)>>>(grad, n, workspace);
+    launch_kernel(grad_sqnorm_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), grad, n, workspace);
     VITAE_CHECK_LAUNCH("grad_sqnorm");
-    optim_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(workspace, blocks, ctl, growth_factor, backoff_factor, growth_interval, use_scaler);
+    launch_kernel(optim_finalize_kernel, dim3(1), dim3(256), 0, as_stream(stream), workspace, blocks, ctl, growth_factor, backoff_factor, growth_interval, use_scaler);
     VITAE_CHECK_LAUNCH("optim_finalize");
     return 0;
 }
@@ -489,7 +531,7 @@ extern "C" int vitae_adamw_flat(float* param, const float* grad, float* exp_avg,
     AdamHyper hy;
     memset(&hy, 0, sizeof(hy));
     memcpy(hy.h, hyper, sizeof(float) * 8 * ngroups);   // host pointer, read during this call
-    adamw_flat_kernel<<<blocks, 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, static_cast<__nv_bfloat16*>(param_bf16), n,
+    launch_kernel(adamw_flat_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), param, grad, exp_avg, exp_avg_sq, static_cast<__nv_bfloat16*>(param_bf16), n,
                                                              group_of_chunk, hy, ngroups, ctl);
     VITAE_CHECK_LAUNCH("adamw_flat");
     return 0;

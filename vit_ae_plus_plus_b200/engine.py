@@ -28,6 +28,7 @@ loss / gradients of parameters (BASELINE.json north_star tolerance for this mode
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -149,7 +150,9 @@ class _Lanes:
     remembers which buffers it reads; ``before_write()`` makes main wait for the last side reader of a buffer."""
 
     def __init__(self, device):
-        self.stream = torch.cuda.Stream(device=device)
+        # higher priority than the main lane: with programmatic dependent launch the main chain keeps the next kernels'
+        # CTAs resident (waiting on their predecessor); side-lane CTAs must win the SM slots that free up
+        self.stream = torch.cuda.Stream(device=device, priority=int(os.environ.get("VITAE_SIDE_PRIORITY", "-1")))
         self.readers: Dict[object, torch.cuda.Event] = {}
         self.dirty = False
 

@@ -52,8 +52,11 @@ long long vitae_launch_count(void);
  *   if out_f32 : out_f32[r*ld_f32 + n]  = (accumulate ? old : 0) + v
  *   if out_bf16: out_bf16[r*ld_bf16 + n] = bf16(v)
  *   if out_gelu_bf16: out_gelu_bf16[r*ld_bf16 + n] = bf16(gelu(v))   (erf GELU, model/vit.py:81,92)
- * Requirements: N % 8 == 0, leading dims % 8 == 0, 16-byte aligned base pointers.
- * split_k > 1 needs workspace >= split_k*M*N*4 bytes (deterministic slab reduction, no atomics).
+ * Requirements: N % 8 == 0, leading dims % 8 == 0, 16-byte aligned base pointers (operands, outputs, bias, addend).
+ * The common epilogues of the training step (bf16 out; bf16 + GELU twin; fp32 out + same-row addend; bf16 + fp32 out;
+ * fp32 out / accumulate; bf16 out with GELU') run inside the GEMM kernel (TMA-store epilogue).  split_k > 1, row maps
+ * (out_rows / add_rows) and any other combination go through fp32 slabs and a finalize kernel (deterministic fixed-order
+ * reduction, no atomics) and need workspace >= vitae_gemm_workspace_bytes_for(...) bytes, 16-byte aligned.
  */
 typedef struct vitae_gemm_epilogue {
     float alpha;
@@ -77,6 +80,9 @@ int vitae_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int l
                     int K, const vitae_gemm_epilogue* ep, int tile_n, int split_k, void* workspace,
                     size_t workspace_bytes, void* stream);
 size_t vitae_gemm_workspace_bytes(int M, int N, int split_k);
+/* workspace bytes vitae_gemm_bf16 needs for this epilogue / operand layout / split (0 = none) */
+size_t vitae_gemm_workspace_bytes_for(const vitae_gemm_epilogue* ep, int a_mn_major, int b_mn_major, int M, int N,
+                                      int split_k);
 
 /* ------------------------------------------------------------------------------------------------------------
  * LayerNorm (biased variance, eps inside sqrt) -- nn.LayerNorm at model/vit.py:131,135,140-143 and

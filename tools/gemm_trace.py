@@ -16,7 +16,7 @@ from vit_ae_plus_plus_b200 import _lib, ops  # noqa: E402
 from tools.ncu_gemm import SHAPES  # noqa: E402
 
 NAMES = ["entry", "prologue", "pdl_wait", "tma_first", "tma_last", "stage0_landed", "mma_commit", "acc_ready", "epi_done",
-         "cta_done"]
+         "cta_done", "chunk0_staged", "chunk0_stored"]
 
 
 def main():
@@ -46,7 +46,7 @@ def main():
             t = t[live]
             t0 = int(t[:, 0].min())
             cols = []
-            for k in range(10):
+            for k in range(12):
                 v = [int(x) - t0 for x in t[:, k].tolist() if x > 0]
                 cols.append((statistics.median(v), max(v)) if v else (0, 0))
             print(f"{name:14s} {mode} tile_n={tn} split={sk} ctas={t.shape[0]:4d}  " +

@@ -46,6 +46,7 @@ SIGNATURES = {
     "vitae_gemm_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                 POINTER(GemmEpilogue), c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "vitae_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "vitae_gemm_workspace_bytes_for": (c_size_t, [POINTER(GemmEpilogue), c_int, c_int, c_int, c_int, c_int]),
     "vitae_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                     c_float, c_void_p]),
     "vitae_layernorm_bwd": (c_int, [c_void_p] * 10 + [c_int, c_int, c_void_p]),

@@ -1,14 +1,23 @@
 // bf16 x bf16 -> fp32 GEMM on the Blackwell 5th-gen tensor cores.
 //
-//   * operands staged by TMA (cp.async.bulk.tensor.2d) into 128B-swizzled shared-memory tiles, STAGES-deep
-//     mbarrier ring (full/empty), one producer thread;
+//   * operands staged by TMA (cp.async.bulk.tensor.2d) into 128B-swizzled shared-memory tiles; a pipeline stage
+//     holds SPB sub-blocks of 64 K-elements, so one mbarrier round trip (producer: wait / expect_tx, MMA issuer:
+//     wait / commit) is amortised over SPB * 4 tcgen05.mma -- the GEMMs of this path are short (K = 512 .. 3072)
+//     and the per-round-trip latency of the single producer / issuer threads, not bandwidth, bounded them
+//     (tools/tma_bench.cu: 330 cycles per 64-wide block with one block per stage, 220 = the ~110 B/clk/SM ingest
+//     ceiling with two);
 //   * tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16) issued by one elected thread, accumulator in TMEM;
-//   * four epilogue warps read the accumulator with tcgen05.ld (32x32b.x32) and apply the fused epilogue
-//     (alpha, bias, residual / positional addend with row gather, GELU', GELU, row-scattered fp32 / bf16 stores);
+//   * epilogue, compile-time specialised per output kind: each of the four epilogue warps reads its TMEM lane
+//     quadrant with tcgen05.ld (lane = accumulator row), applies alpha / bias / residual addend / GELU' / GELU in
+//     registers, writes 32-row x 128-byte boxes into 128B-swizzled staging buffers (the drained pipeline stages) and
+//     one elected lane hands them to the TMA store engine (cp.async.bulk.tensor store, or fp32 reduce-add when
+//     accumulating): ~150 instructions per warp instead of per-element address arithmetic, and ragged M / N edges
+//     are clipped by the tensor map;
 //   * both operand majors (K-major = nn.Linear layout, MN-major = transposed) so that forward, dgrad and wgrad of
 //     every Linear on the path (see include/vitae_b200.h) are the same kernel with different tensor maps;
-//   * optional split-K: each split writes its fp32 partial tile to a slab, a finalize kernel reduces the slabs in
-//     fixed order (deterministic) and applies the epilogue.
+//   * split-K and the rarely used epilogue features (row scatter / gather maps, unusual output combinations) go
+//     through fp32 slabs: every split stores its partial tile (same TMA-store epilogue), a finalize kernel reduces
+//     the slabs in fixed order (deterministic) and applies the generic epilogue.
 #include <mutex>
 #include <unordered_map>
 
@@ -18,9 +27,10 @@
 namespace vitae {
 
 constexpr int BM = 128;
-constexpr int BK = 64;
+constexpr int BK = 64;             // K elements per sub-block (= one 128-byte swizzled row)
 constexpr int GEMM_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
 
+// generic epilogue description (finalize kernel); mirrors vitae_gemm_epilogue
 struct EpiParams {
     float alpha;
     const float* alpha_ptr;
@@ -39,71 +49,42 @@ struct EpiParams {
     const int* out_rows;
 };
 
+// what the in-kernel epilogue needs besides the output tensor maps
+struct EpiLite {
+    float alpha;
+    const float* alpha_ptr;
+    const float* bias;
+    const float* addend;              // fp32 [M, ldadd], same rows as the output (EPI_ADD_F32)
+    int ldadd;
+    const __nv_bfloat16* dgelu_src;   // bf16 [M, ld_dgelu] (EPI_DGELU_BF16)
+    int ld_dgelu;
+    int accumulate;                   // EPI_F32: add into the destination (TMA reduce-add)
+};
+
+// in-kernel epilogue kinds (everything else is "generic": slabs + finalize kernel)
+enum EpiKind : int {
+    EPI_BF16 = 0,        // out_bf16 = bf16(v)                                   qkv / decoder_pred forward, dgrads
+    EPI_BF16_GELU = 1,   // out_bf16 = bf16(v), out1 = bf16(gelu(v))             fc1 forward (pre-activation kept for GELU')
+    EPI_ADD_F32 = 2,     // out_f32 = v + addend                                 proj / fc2 forward (+ residual stream)
+    EPI_BF16_F32 = 3,    // out_bf16 = bf16(v), out1(f32) = v                    decoder_pred forward with an fp32 copy
+    EPI_F32 = 4,         // out_f32 (+)= v                                       wgrads, split-K slabs
+    EPI_DGELU_BF16 = 5,  // out_bf16 = bf16(v * gelu'(src))                      fc2 dgrad
+};
+
+#ifdef VITAE_EPI_NOGELU
+__device__ __forceinline__ float gelu_erf(float x) { return x; }
+__device__ __forceinline__ float dgelu_erf(float x) { return x; }
+#else
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float dgelu_erf(float x) {
     const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
     const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
     return cdf + x * pdf;
 }
+#endif
 
-// Epilogue for 8 consecutive columns [n, n+8) of logical row m (all in range; N % 8 == 0).
-__device__ __forceinline__ void epilogue_group8(const EpiParams& ep, float alpha, int m, int n, float (&v)[8]) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] *= alpha;
-    if (ep.bias) {
-        const float4 b0 = *reinterpret_cast<const float4*>(ep.bias + n);
-        const float4 b1 = *reinterpret_cast<const float4*>(ep.bias + n + 4);
-        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-    }
-    if (ep.addend) {
-        const int ra = ep.add_rows ? ep.add_rows[m] : m;
-        const float* a = ep.addend + static_cast<size_t>(ra) * ep.ldadd + n;
-        const float4 a0 = *reinterpret_cast<const float4*>(a);
-        const float4 a1 = *reinterpret_cast<const float4*>(a + 4);
-        v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w;
-        v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
-    }
-    if (ep.dgelu_src) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(ep.dgelu_src + static_cast<size_t>(m) * ep.ld_dgelu + n);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 f = __bfloat1622float2(h[i]);
-            v[2 * i] *= dgelu_erf(f.x);
-            v[2 * i + 1] *= dgelu_erf(f.y);
-        }
-    }
-    const int r = ep.out_rows ? ep.out_rows[m] : m;
-    if (ep.out_f32) {
-        float* o = ep.out_f32 + static_cast<size_t>(r) * ep.ld_f32 + n;
-        float4 o0 = make_float4(v[0], v[1], v[2], v[3]);
-        float4 o1 = make_float4(v[4], v[5], v[6], v[7]);
-        if (ep.accumulate) {
-            const float4 p0 = *reinterpret_cast<const float4*>(o);
-            const float4 p1 = *reinterpret_cast<const float4*>(o + 4);
-            o0.x += p0.x; o0.y += p0.y; o0.z += p0.z; o0.w += p0.w;
-            o1.x += p1.x; o1.y += p1.y; o1.z += p1.z; o1.w += p1.w;
-        }
-        *reinterpret_cast<float4*>(o) = o0;
-        *reinterpret_cast<float4*>(o + 4) = o1;
-    }
-    if (ep.out_bf16) {
-        uint4 pk;
-        pk.x = pack_bf16(v[0], v[1]); pk.y = pack_bf16(v[2], v[3]);
-        pk.z = pack_bf16(v[4], v[5]); pk.w = pack_bf16(v[6], v[7]);
-        *reinterpret_cast<uint4*>(ep.out_bf16 + static_cast<size_t>(r) * ep.ld_bf16 + n) = pk;
-    }
-    if (ep.out_gelu_bf16) {
-        uint4 pk;
-        pk.x = pack_bf16(gelu_erf(v[0]), gelu_erf(v[1])); pk.y = pack_bf16(gelu_erf(v[2]), gelu_erf(v[3]));
-        pk.z = pack_bf16(gelu_erf(v[4]), gelu_erf(v[5])); pk.w = pack_bf16(gelu_erf(v[6]), gelu_erf(v[7]));
-        *reinterpret_cast<uint4*>(ep.out_gelu_bf16 + static_cast<size_t>(r) * ep.ld_bf16 + n) = pk;
-    }
-}
-
-// Phase tracing (debug builds only: VITAE_TRACE=1 python -m vit_ae_plus_plus_b200.build): per CTA, SM-clock stamps of the
-// kernel phases are written to a device buffer registered with vitae_debug_set_gemm_trace (tools/gemm_trace.py).
+// Phase tracing (debug builds only: VITAE_TRACE=1 python -m vit_ae_plus_plus_b200.build): per CTA, %globaltimer stamps of
+// the kernel phases are written to a device buffer registered with vitae_debug_set_gemm_trace (tools/gemm_trace.py).
 #ifdef VITAE_GEMM_TRACE
 __device__ unsigned long long* g_gemm_trace = nullptr;
 #define GEMM_TRACE(slot)                                                                                      \
@@ -119,20 +100,33 @@ __device__ unsigned long long* g_gemm_trace = nullptr;
 #define GEMM_TRACE(slot) do { } while (0)
 #endif
 
-template <int BN, int STAGES>
+template <int BN, int SPB, int STAGES>
 struct GemmSmem {
-    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int A_BYTES = BM * BK * 2;               // one sub-block of A
     static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+    static constexpr int SUB_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGE_BYTES = SPB * SUB_BYTES;
+    static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFFSET = PIPE_BYTES;             // full[STAGES], empty[STAGES], tmem_full, tmem slot
+    static constexpr int BIAS_OFFSET = BAR_OFFSET + (2 * STAGES + 2) * 8;
+    static constexpr int TOTAL = BIAS_OFFSET + BN * 4 + 1024; // + alignment slack
+    // epilogue staging (reuses the drained pipeline): 4 warps x 2 outputs x 2 buffers x 4 KB
+    static_assert(PIPE_BYTES >= 4 * 2 * 2 * 4096, "epilogue staging does not fit into the pipeline stages");
 };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+// 16-byte chunk j of row r inside a 32-row x 128-byte SWIZZLE_128B box
+__device__ __forceinline__ uint32_t swz128(int r, int j) { return static_cast<uint32_t>(r * 128 + ((j ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+template <int BN, int SPB, int STAGES, bool A_MN, bool B_MN, int KIND>
 __global__ void __launch_bounds__(GEMM_THREADS)
-gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-                         int num_kb, int kb_per_split, EpiParams ep, float* __restrict__ slabs) {
-    using S = GemmSmem<BN, STAGES>;
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, int M, int N,
+                         int num_sub, int sub_per_split, EpiLite ep) {
+    using S = GemmSmem<BN, SPB, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     const uint32_t base = (raw_u32 + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -142,19 +136,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const uint32_t empty_bar = full_bar + STAGES * 8;
     const uint32_t tmem_full_bar = empty_bar + STAGES * 8;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + 2 * STAGES + 1);
+    float* bias_s = reinterpret_cast<float*>(sm + S::BIAS_OFFSET);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM;
     const int n0 = blockIdx.x * BN;
-    const int kb_begin = blockIdx.z * kb_per_split;
-    const int kb_end = min(num_kb, kb_begin + kb_per_split);
-    const int nkb = kb_end - kb_begin;
+    const int sub_begin = blockIdx.z * sub_per_split;
+    const int nsub = min(num_sub, sub_begin + sub_per_split) - sub_begin;
+    const int niter = (nsub + SPB - 1) / SPB;
     if (threadIdx.x == 0) GEMM_TRACE(0);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmO0);
+        if (KIND == EPI_BF16_GELU || KIND == EPI_BF16_F32) tma_prefetch_desc(&tmO1);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -183,27 +180,35 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (i / STAGES) & 1;
+            for (int it = 0; it < niter; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const int cnt = min(SPB, nsub - it * SPB);
                 mbar_wait(empty_bar + s * 8, ph ^ 1);
-                mbar_arrive_expect_tx(full_bar + s * 8, S::STAGE_BYTES);
-                const uint32_t sa = base + s * S::STAGE_BYTES;
-                const uint32_t sb = sa + S::A_BYTES;
-                const int k0 = (kb_begin + i) * BK;
-                if (A_MN) {
+                mbar_arrive_expect_tx(full_bar + s * 8, cnt * S::SUB_BYTES);
 #pragma unroll
-                    for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmA, full_bar + s * 8, m0 + 64 * j, k0);
-                } else {
-                    tma_load_2d(sa, &tmA, full_bar + s * 8, k0, m0);
-                }
-                if (B_MN) {
+                for (int u = 0; u < SPB; ++u) {
+                    if (u < cnt) {
+                        const uint32_t sa = base + s * S::STAGE_BYTES + u * S::SUB_BYTES;
+                        const uint32_t sb = sa + S::A_BYTES;
+                        const int k0 = (sub_begin + it * SPB + u) * BK;
+                        if (A_MN) {
 #pragma unroll
-                    for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tmB, full_bar + s * 8, n0 + 64 * j, k0);
-                } else {
-                    tma_load_2d(sb, &tmB, full_bar + s * 8, k0, n0);
+                            for (int j = 0; j < BM / 64; ++j)
+                                tma_load_2d(sa + j * (BK * 128), &tmA, full_bar + s * 8, m0 + 64 * j, k0);
+                        } else {
+                            tma_load_2d(sa, &tmA, full_bar + s * 8, k0, m0);
+                        }
+                        if (B_MN) {
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j)
+                                tma_load_2d(sb + j * (BK * 128), &tmB, full_bar + s * 8, n0 + 64 * j, k0);
+                        } else {
+                            tma_load_2d(sb, &tmB, full_bar + s * 8, k0, n0);
+                        }
+                    }
                 }
-                if (i == 0) GEMM_TRACE(3);
+                if (it == 0) GEMM_TRACE(3);
             }
             GEMM_TRACE(4);
         }
@@ -212,22 +217,28 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // ------------------------------------------------------------------ MMA issuer (single thread)
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (i / STAGES) & 1;
+            for (int it = 0; it < niter; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const int cnt = min(SPB, nsub - it * SPB);
                 mbar_wait(full_bar + s * 8, ph);
                 tc_fence_after();
-                if (i == 0) GEMM_TRACE(5);
-                const uint32_t sa = base + s * S::STAGE_BYTES;
-                const uint32_t sb = sa + S::A_BYTES;
+                if (it == 0) GEMM_TRACE(5);
 #pragma unroll
-                for (int kk = 0; kk < BK / 16; ++kk) {
-                    // K-major: 16 bf16 = 32 B along the swizzled row; MN-major: 16 K-rows of 128 B
-                    const uint64_t da = A_MN ? umma_smem_desc_sw128(sa + kk * 2048, BK * 128, 1024)
-                                             : umma_smem_desc_sw128(sa + kk * 32, 16, 1024);
-                    const uint64_t db = B_MN ? umma_smem_desc_sw128(sb + kk * 2048, BK * 128, 1024)
-                                             : umma_smem_desc_sw128(sb + kk * 32, 16, 1024);
-                    umma_bf16(tmem_base, da, db, idesc, (i | kk) != 0 ? 1u : 0u);
+                for (int u = 0; u < SPB; ++u) {
+                    if (u < cnt) {
+                        const uint32_t sa = base + s * S::STAGE_BYTES + u * S::SUB_BYTES;
+                        const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+                        for (int kk = 0; kk < BK / 16; ++kk) {
+                            // K-major: 16 bf16 = 32 B along the swizzled row; MN-major: 16 K-rows of 128 B
+                            const uint64_t da = A_MN ? umma_smem_desc_sw128(sa + kk * 2048, BK * 128, 1024)
+                                                     : umma_smem_desc_sw128(sa + kk * 32, 16, 1024);
+                            const uint64_t db = B_MN ? umma_smem_desc_sw128(sb + kk * 2048, BK * 128, 1024)
+                                                     : umma_smem_desc_sw128(sb + kk * 32, 16, 1024);
+                            umma_bf16(tmem_base, da, db, idesc, (it | u | kk) != 0 ? 1u : 0u);
+                        }
+                    }
                 }
                 umma_commit(empty_bar + s * 8);  // frees the smem stage once these MMAs retire
             }
@@ -236,39 +247,126 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------------ epilogue warps (TMEM -> regs -> HBM)
+        // ------------------------------------------------------------------ epilogue warps
+        const int q = warp & 3;                    // TMEM lane quadrant this warp may access
+        const int et = threadIdx.x - 64;           // 0..127 among the epilogue threads
+        const int mrow = m0 + q * 32 + lane;       // this lane's accumulator row
+        // bias slice of this tile -> shared memory (read by every lane for every row)
+        for (int c = et; c < BN; c += 128) bias_s[c] = (ep.bias && n0 + c < N) ? ep.bias[n0 + c] : 0.f;
+        const float alpha = ep.alpha * (ep.alpha_ptr ? *ep.alpha_ptr : 1.0f);
+        named_bar_sync(1, 128);
+        // staging: per warp [output 0: buffers 0,1][output 1: buffers 0,1], 32 rows x 128 B each
+        const uint32_t stg = base + (warp - 2) * (4 * 4096);
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         if (threadIdx.x == 64) GEMM_TRACE(7);
-        const int q = warp & 3;  // TMEM lane quadrant this warp may access
-        const int m = m0 + q * 32 + lane;
-        const float alpha = ep.alpha * (ep.alpha_ptr ? *ep.alpha_ptr : 1.0f);
-        float* slab = slabs ? slabs + static_cast<size_t>(blockIdx.z) * M * N : nullptr;
+
+        constexpr bool OUT0_BF16 = KIND != EPI_ADD_F32 && KIND != EPI_F32;   // primary output element type
+        // one bulk commit group per bf16 box (incl. its GELU twin) or per fp32 box; EPI_BF16_F32 commits one per chunk
+        int nbox = 0;   // bf16 boxes committed so far
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             if (n0 + c >= N) break;
             uint32_t raw[32];
             tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, raw);
+            // staging buffers alternate: everything but the most recent bulk group must have been read by the engine
+            if (lane == 0) tma_store_wait_read<1>();
+            // operands of this chunk that come from global memory (lane = row: 128 / 64 contiguous bytes per lane)
+            float4 add4[KIND == EPI_ADD_F32 ? 8 : 1];
+            uint4 dg4[KIND == EPI_DGELU_BF16 ? 4 : 1];
+            if (KIND == EPI_ADD_F32) {
+                const float* arow = ep.addend + static_cast<size_t>(mrow) * ep.ldadd + n0 + c;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    add4[j] = (mrow < M && n0 + c + 4 * j < N) ? *reinterpret_cast<const float4*>(arow + 4 * j)
+                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (KIND == EPI_DGELU_BF16) {
+                const __nv_bfloat16* drow = ep.dgelu_src + static_cast<size_t>(mrow) * ep.ld_dgelu + n0 + c;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    dg4[j] = (mrow < M && n0 + c + 8 * j < N) ? *reinterpret_cast<const uint4*>(drow + 8 * j)
+                                                              : make_uint4(0u, 0u, 0u, 0u);
+            }
             tmem_ld_wait();
-            if (m < M) {
+            __syncwarp();   // lane 0's wait_group.read above now covers the whole warp
+            float v[32];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int n = n0 + c + g * 8;
-                    if (n < N) {
-                        float v[8];
+            for (int j = 0; j < 8; ++j) {
+                const float4 b = *reinterpret_cast<const float4*>(bias_s + c + 4 * j);
+                v[4 * j + 0] = __uint_as_float(raw[4 * j + 0]) * alpha + b.x;
+                v[4 * j + 1] = __uint_as_float(raw[4 * j + 1]) * alpha + b.y;
+                v[4 * j + 2] = __uint_as_float(raw[4 * j + 2]) * alpha + b.z;
+                v[4 * j + 3] = __uint_as_float(raw[4 * j + 3]) * alpha + b.w;
+            }
+            if (KIND == EPI_ADD_F32) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[g * 8 + i]);
-                        if (slab) {
-                            float* o = slab + static_cast<size_t>(m) * N + n;
-                            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                        } else {
-                            epilogue_group8(ep, alpha, m, n, v);
-                        }
+                for (int j = 0; j < 8; ++j) {
+                    v[4 * j + 0] += add4[j].x; v[4 * j + 1] += add4[j].y; v[4 * j + 2] += add4[j].z; v[4 * j + 3] += add4[j].w;
+                }
+            }
+            if (KIND == EPI_DGELU_BF16) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&dg4[j]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 f = __bfloat1622float2(h[i]);
+                        v[8 * j + 2 * i] *= dgelu_erf(f.x);
+                        v[8 * j + 2 * i + 1] *= dgelu_erf(f.y);
                     }
                 }
             }
+            const int half = (c >> 5) & 1;
+            if (OUT0_BF16) {
+                // a 32-row x 64-column bf16 box spans two 32-column chunks: even chunk -> 16B chunks 0..3, odd -> 4..7
+                const uint32_t buf = stg + ((nbox & 1) ? 4096 : 0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    sts128(buf + swz128(lane, 4 * half + j), pack_bf16(v[8 * j + 0], v[8 * j + 1]),
+                           pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]),
+                           pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                if (KIND == EPI_BF16_GELU) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        sts128(buf + 8192 + swz128(lane, 4 * half + j),
+                               pack_bf16(gelu_erf(v[8 * j + 0]), gelu_erf(v[8 * j + 1])),
+                               pack_bf16(gelu_erf(v[8 * j + 2]), gelu_erf(v[8 * j + 3])),
+                               pack_bf16(gelu_erf(v[8 * j + 4]), gelu_erf(v[8 * j + 5])),
+                               pack_bf16(gelu_erf(v[8 * j + 6]), gelu_erf(v[8 * j + 7])));
+                }
+            }
+            if (!OUT0_BF16 || KIND == EPI_BF16_F32) {
+                // fp32 box: 32 rows x 32 columns (128 B per row), one per chunk, two buffers alternating by chunk
+                const uint32_t buf = stg + (KIND == EPI_BF16_F32 ? 8192 : 0) + (half ? 4096 : 0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    sts128(buf + swz128(lane, j), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                           __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                bool issued = false;
+                if (!OUT0_BF16 || KIND == EPI_BF16_F32) {
+                    const uint32_t buf = stg + (KIND == EPI_BF16_F32 ? 8192 : 0) + (half ? 4096 : 0);
+                    const CUtensorMap* mp = KIND == EPI_BF16_F32 ? &tmO1 : &tmO0;
+                    if (KIND == EPI_F32 && ep.accumulate) tma_reduce_add_3d(mp, buf, n0 + c, m0 + q * 32, blockIdx.z);
+                    else tma_store_3d(mp, buf, n0 + c, m0 + q * 32, KIND == EPI_BF16_F32 ? 0 : blockIdx.z);
+                    issued = true;
+                }
+                if (OUT0_BF16 && (half == 1 || n0 + c + 32 >= N)) {
+                    const uint32_t buf = stg + ((nbox & 1) ? 4096 : 0);
+                    tma_store_3d(&tmO0, buf, n0 + (c & ~63), m0 + q * 32, 0);
+                    if (KIND == EPI_BF16_GELU) tma_store_3d(&tmO1, buf + 8192, n0 + (c & ~63), m0 + q * 32, 0);
+                    issued = true;
+                }
+                if (issued || KIND == EPI_BF16_F32) tma_store_commit();
+            }
+            if (OUT0_BF16 && (half == 1 || n0 + c + 32 >= N)) ++nbox;
         }
+        if (lane == 0) tma_store_wait_read<0>();   // the engine must have read our staging buffers before the CTA exits
+        __syncwarp();
         tc_fence_before();
         if (threadIdx.x == 64) GEMM_TRACE(8);
     }
@@ -277,28 +375,64 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (warp == 2) tmem_dealloc(tmem_base, BN);
 }
 
-// Split-K finalize: sum the slabs in fixed order, then the fused epilogue.
-__global__ void gemm_splitk_finalize_kernel(const float* __restrict__ slabs, int splits, int M, int N, EpiParams ep) {
-    if (threadIdx.x == 0) GEMM_TRACE(1);
+// ---------------------------------------------------------------------------------------------------- generic epilogue
+__device__ __forceinline__ void generic_epilogue4(const EpiParams& ep, float alpha, int m, int n, float4 acc) {
+    float v[4] = {acc.x * alpha, acc.y * alpha, acc.z * alpha, acc.w * alpha};
+    if (ep.bias) {
+        const float4 b = *reinterpret_cast<const float4*>(ep.bias + n);
+        v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+    }
+    if (ep.addend) {
+        const int ra = ep.add_rows ? ep.add_rows[m] : m;
+        const float4 a = *reinterpret_cast<const float4*>(ep.addend + static_cast<size_t>(ra) * ep.ldadd + n);
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+    }
+    if (ep.dgelu_src) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(ep.dgelu_src + static_cast<size_t>(m) * ep.ld_dgelu + n);
+        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+        v[0] *= dgelu_erf(lo.x); v[1] *= dgelu_erf(lo.y); v[2] *= dgelu_erf(hi.x); v[3] *= dgelu_erf(hi.y);
+    }
+    const int r = ep.out_rows ? ep.out_rows[m] : m;
+    if (ep.out_f32) {
+        float* o = ep.out_f32 + static_cast<size_t>(r) * ep.ld_f32 + n;
+        float4 o4 = make_float4(v[0], v[1], v[2], v[3]);
+        if (ep.accumulate) {
+            const float4 p = *reinterpret_cast<const float4*>(o);
+            o4.x += p.x; o4.y += p.y; o4.z += p.z; o4.w += p.w;
+        }
+        *reinterpret_cast<float4*>(o) = o4;
+    }
+    if (ep.out_bf16) {
+        uint2 pk;
+        pk.x = pack_bf16(v[0], v[1]); pk.y = pack_bf16(v[2], v[3]);
+        *reinterpret_cast<uint2*>(ep.out_bf16 + static_cast<size_t>(r) * ep.ld_bf16 + n) = pk;
+    }
+    if (ep.out_gelu_bf16) {
+        uint2 pk;
+        pk.x = pack_bf16(gelu_erf(v[0]), gelu_erf(v[1])); pk.y = pack_bf16(gelu_erf(v[2]), gelu_erf(v[3]));
+        *reinterpret_cast<uint2*>(ep.out_gelu_bf16 + static_cast<size_t>(r) * ep.ld_bf16 + n) = pk;
+    }
+}
+
+// Split-K / generic finalize: sum the slabs in fixed order, then the generic epilogue.  One thread per (row, 4 columns).
+__global__ void __launch_bounds__(256)
+gemm_splitk_finalize_kernel(const float* __restrict__ slabs, int splits, int M, int N, EpiParams ep) {
     pdl_trigger();
     pdl_wait();
-    if (threadIdx.x == 0) GEMM_TRACE(2);
-    const int groups_per_row = N / 8;
+    const int groups_per_row = N / 4;
     const long long total = static_cast<long long>(M) * groups_per_row;
     const float alpha = ep.alpha * (ep.alpha_ptr ? *ep.alpha_ptr : 1.0f);
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int m = static_cast<int>(idx / groups_per_row);
-        const int n = static_cast<int>(idx % groups_per_row) * 8;
-        float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int n = static_cast<int>(idx % groups_per_row) * 4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int s = 0; s < splits; ++s) {
-            const float* p = slabs + (static_cast<size_t>(s) * M + m) * N + n;
-            const float4 a = *reinterpret_cast<const float4*>(p);
-            const float4 b = *reinterpret_cast<const float4*>(p + 4);
-            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-            v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+            const float4 p = *reinterpret_cast<const float4*>(slabs + (static_cast<size_t>(s) * M + m) * N + n);
+            a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
         }
-        epilogue_group8(ep, alpha, m, n, v);
+        generic_epilogue4(ep, alpha, m, n, a);
     }
 }
 
@@ -322,27 +456,30 @@ static EncodeTiledFn get_encode_fn() {
 
 struct TmapKey {
     const void* ptr;
-    uint64_t d0, d1, ld;
-    uint32_t b0, b1;
+    uint64_t d0, d1, d2, ld;
+    uint32_t b0, b1, esize;
     bool operator==(const TmapKey& o) const {
-        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && ld == o.ld && b0 == o.b0 && b1 == o.b1;
+        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && ld == o.ld && b0 == o.b0 && b1 == o.b1 &&
+               esize == o.esize;
     }
 };
 struct TmapKeyHash {
     size_t operator()(const TmapKey& k) const {
         size_t h = reinterpret_cast<size_t>(k.ptr);
         auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-        mix(k.d0); mix(k.d1); mix(k.ld); mix(k.b0); mix(k.b1);
+        mix(k.d0); mix(k.d1); mix(k.d2); mix(k.ld); mix(k.b0); mix(k.b1); mix(k.esize);
         return h;
     }
 };
 
-// 2-D bf16 tensor map: inner dim d0 (contiguous), outer dim d1 with row pitch ld elements, box b0 x b1, 128B swizzle,
-// out-of-bounds elements read as zero (so ragged M/N/K need no special casing in the kernel).
-static int make_tmap(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0, uint32_t b1) {
+// Tensor map over a row-major matrix, or (d2 > 0) a stack of d2 matrices of d1 rows (pitch ld elements, matrix pitch
+// d1*ld): inner dim d0 (contiguous), box b0 x b1 (x 1), 128B swizzle, element size 2 (bf16) or 4 (fp32).
+// Out-of-bounds elements read as zero and are clipped on stores, so ragged M / N / K need no special casing.
+static int make_tmap(CUtensorMap* out, const void* ptr, uint32_t esize, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld,
+                     uint32_t b0, uint32_t b1) {
     static std::mutex mu;
     static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
-    const TmapKey key{ptr, d0, d1, ld, b0, b1};
+    const TmapKey key{ptr, d0, d1, d2, ld, b0, b1, esize};
     {
         std::lock_guard<std::mutex> g(mu);
         auto it = cache.find(key);
@@ -353,54 +490,102 @@ static int make_tmap(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1
     }
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return set_error(-4, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
-    const cuuint64_t dims[2] = {d0, d1};
-    const cuuint64_t strides[1] = {ld * 2};
-    const cuuint32_t box[2] = {b0, b1};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const cuuint32_t rank = d2 ? 3 : 2;
+    const cuuint64_t dims[3] = {d0, d1, d2 ? d2 : 1};
+    const cuuint64_t strides[2] = {ld * esize, d1 * ld * esize};
+    const cuuint32_t box[3] = {b0, b1, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(out, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank,
+                           const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
-        return set_error(-5, "cuTensorMapEncodeTiled failed (%d) ptr=%p dims=%llu,%llu ld=%llu box=%u,%u", (int)r, ptr,
-                         (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)ld, b0, b1);
+        return set_error(-5, "cuTensorMapEncodeTiled failed (%d) ptr=%p esize=%u dims=%llu,%llu,%llu ld=%llu box=%u,%u", (int)r,
+                         ptr, esize, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+                         (unsigned long long)ld, b0, b1);
     std::lock_guard<std::mutex> g(mu);
     if (cache.size() > 8192) cache.clear();
     cache.emplace(key, *out);
     return 0;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int num_kb, int splits, const EpiParams& ep,
-                       float* slabs, cudaStream_t stream) {
-    using S = GemmSmem<BN, STAGES>;
-    auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, A_MN, B_MN>;
+struct GemmLaunch {
+    CUtensorMap ta, tb, to0, to1;
+    int M, N, num_sub, splits;
+    EpiLite ep;
+    cudaStream_t stream;
+};
+
+template <int BN, int SPB, int STAGES, bool A_MN, bool B_MN, int KIND>
+static int launch_gemm(const GemmLaunch& g) {
+    using S = GemmSmem<BN, SPB, STAGES>;
+    auto kern = gemm_bf16_tcgen05_kernel<BN, SPB, STAGES, A_MN, B_MN, KIND>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return set_error(-3, "cudaFuncSetAttribute(smem=%d): %s", S::TOTAL, cudaGetErrorString(e));
         attr_set = true;
     }
-    const int kb_per_split = ceil_div(num_kb, splits);
-    const int eff_splits = ceil_div(num_kb, kb_per_split);  // every z-slice gets >= 1 k-block
-    dim3 grid(ceil_div(N, BN), ceil_div(M, BM), eff_splits);
-    launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS), S::TOTAL, stream, ta, tb, M, N, num_kb, kb_per_split, ep, slabs);
+    const int sub_per_split = ceil_div(g.num_sub, g.splits);
+    const int eff_splits = ceil_div(g.num_sub, sub_per_split);  // every z-slice gets >= 1 sub-block
+    dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), eff_splits);
+    launch_kernel(kern, grid, dim3(GEMM_THREADS), S::TOTAL, g.stream, g.ta, g.tb, g.to0, g.to1, g.M, g.N, g.num_sub,
+                  sub_per_split, g.ep);
     VITAE_CHECK_LAUNCH("gemm_bf16_tcgen05");
-    if (slabs) {
-        const long long total = static_cast<long long>(M) * (N / 8);
-        const int blocks = static_cast<int>(std::min<long long>(ceil_div<long long>(total, 256), 148 * 8));
-        launch_kernel(gemm_splitk_finalize_kernel, dim3(blocks), dim3(256), 0, stream, slabs, eff_splits, M, N, ep);
-        VITAE_CHECK_LAUNCH("gemm_splitk_finalize");
-    }
-    return 0;
+    return eff_splits;
 }
 
-template <int BN, int STAGES>
-static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int num_kb,
-                          int splits, const EpiParams& ep, float* slabs, cudaStream_t stream) {
-    if (!a_mn && !b_mn) return launch_gemm<BN, STAGES, false, false>(ta, tb, M, N, num_kb, splits, ep, slabs, stream);
-    if (!a_mn && b_mn) return launch_gemm<BN, STAGES, false, true>(ta, tb, M, N, num_kb, splits, ep, slabs, stream);
-    if (a_mn && b_mn) return launch_gemm<BN, STAGES, true, true>(ta, tb, M, N, num_kb, splits, ep, slabs, stream);
-    return launch_gemm<BN, STAGES, true, false>(ta, tb, M, N, num_kb, splits, ep, slabs, stream);
+// tile configurations <BN, SPB, STAGES>: "deep" = the whole shared memory for one CTA per SM, "shallow" = two CTAs per SM
+template <bool A_MN, bool B_MN, int KIND>
+static int dispatch_tile(int bn, bool deep, const GemmLaunch& g) {
+    if (bn == 64) return deep ? launch_gemm<64, 2, 4, A_MN, B_MN, KIND>(g) : launch_gemm<64, 2, 2, A_MN, B_MN, KIND>(g);
+    if (bn == 128) return deep ? launch_gemm<128, 2, 3, A_MN, B_MN, KIND>(g) : launch_gemm<128, 1, 3, A_MN, B_MN, KIND>(g);
+    return launch_gemm<256, 2, 2, A_MN, B_MN, KIND>(g);
+}
+
+// only the (operand major, epilogue kind) pairs the training step uses are instantiated; anything else runs as EPI_F32
+// slabs + the generic finalize kernel
+static int dispatch(bool amn, bool bmn, int kind, int bn, bool deep, const GemmLaunch& g) {
+    if (!amn && !bmn) {
+        switch (kind) {
+            case EPI_BF16: return dispatch_tile<false, false, EPI_BF16>(bn, deep, g);
+            case EPI_BF16_GELU: return dispatch_tile<false, false, EPI_BF16_GELU>(bn, deep, g);
+            case EPI_ADD_F32: return dispatch_tile<false, false, EPI_ADD_F32>(bn, deep, g);
+            case EPI_BF16_F32: return dispatch_tile<false, false, EPI_BF16_F32>(bn, deep, g);
+            default: return dispatch_tile<false, false, EPI_F32>(bn, deep, g);
+        }
+    }
+    if (!amn && bmn) {
+        switch (kind) {
+            case EPI_BF16: return dispatch_tile<false, true, EPI_BF16>(bn, deep, g);
+            case EPI_DGELU_BF16: return dispatch_tile<false, true, EPI_DGELU_BF16>(bn, deep, g);
+            default: return dispatch_tile<false, true, EPI_F32>(bn, deep, g);
+        }
+    }
+    if (amn && bmn) return dispatch_tile<true, true, EPI_F32>(bn, deep, g);
+    return dispatch_tile<true, false, EPI_F32>(bn, deep, g);
+}
+
+static bool kind_available(bool amn, bool bmn, int kind) {
+    if (kind == EPI_F32) return true;
+    if (!amn && !bmn) return kind == EPI_BF16 || kind == EPI_BF16_GELU || kind == EPI_ADD_F32 || kind == EPI_BF16_F32;
+    if (!amn && bmn) return kind == EPI_BF16 || kind == EPI_DGELU_BF16;
+    return false;
+}
+
+// in-kernel epilogue kind for this epilogue description, or -1 when it needs the generic (slab + finalize) path
+static int classify(const vitae_gemm_epilogue* e, bool amn, bool bmn) {
+    if (e->out_rows || e->add_rows) return -1;
+    const bool f32 = e->out_f32 != nullptr, b16 = e->out_bf16 != nullptr, gl = e->out_gelu_bf16 != nullptr;
+    const bool add = e->addend != nullptr, dg = e->dgelu_src != nullptr;
+    int kind = -1;
+    if (b16 && !f32 && !gl && !add && !dg) kind = EPI_BF16;
+    else if (b16 && gl && !f32 && !add && !dg) kind = EPI_BF16_GELU;
+    else if (f32 && !b16 && !gl && add && !dg && !e->accumulate) kind = EPI_ADD_F32;
+    else if (b16 && f32 && !gl && !add && !dg && !e->accumulate) kind = EPI_BF16_F32;
+    else if (f32 && !b16 && !gl && !add && !dg) kind = EPI_F32;
+    else if (b16 && dg && !f32 && !gl && !add) kind = EPI_DGELU_BF16;
+    if (kind >= 0 && !kind_available(amn, bmn, kind)) kind = -1;
+    return kind;
 }
 
 }  // namespace vitae
@@ -419,6 +604,13 @@ extern "C" size_t vitae_gemm_workspace_bytes(int M, int N, int split_k) {
     return static_cast<size_t>(split_k) * M * N * sizeof(float);
 }
 
+extern "C" size_t vitae_gemm_workspace_bytes_for(const vitae_gemm_epilogue* e, int a_mn_major, int b_mn_major, int M, int N,
+                                                 int split_k) {
+    const int splits = split_k > 1 ? split_k : 1;
+    if (splits == 1 && e && classify(e, a_mn_major != 0, b_mn_major != 0) >= 0) return 0;
+    return static_cast<size_t>(splits) * M * N * sizeof(float);
+}
+
 extern "C" int vitae_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M,
                                int N, int K, const vitae_gemm_epilogue* e, int tile_n, int split_k, void* workspace,
                                size_t workspace_bytes, void* stream) {
@@ -434,45 +626,88 @@ extern "C" int vitae_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
     VITAE_REQUIRE(!e->addend || e->ldadd % 4 == 0, "gemm: ldadd %% 4");
     VITAE_REQUIRE(!e->dgelu_src || e->ld_dgelu % 8 == 0, "gemm: ld_dgelu %% 8");
     VITAE_REQUIRE(lda >= (a_mn_major ? M : K) && ldb >= (b_mn_major ? N : K), "gemm: leading dim too small");
+    VITAE_REQUIRE((reinterpret_cast<uintptr_t>(e->out_f32) & 15) == 0 && (reinterpret_cast<uintptr_t>(e->out_bf16) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(e->out_gelu_bf16) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(e->bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(e->addend) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(e->dgelu_src) & 15) == 0,
+                  "gemm: epilogue pointers must be 16-byte aligned");
 
+    const bool amn = a_mn_major != 0, bmn = b_mn_major != 0;
     int bn = tile_n;
     if (bn == 0) {
         const long long tiles128 = static_cast<long long>(ceil_div(M, BM)) * ceil_div(N, 128) * (split_k > 1 ? split_k : 1);
         bn = (tiles128 < 120) ? 64 : 128;
     }
     VITAE_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: tile_n must be 0/64/128/256 (got %d)", tile_n);
-    const int num_kb = ceil_div(K, BK);
+    const int num_sub = ceil_div(K, BK);
     int splits = split_k > 1 ? split_k : 1;
-    if (splits > num_kb) splits = num_kb;
+    if (splits > num_sub) splits = num_sub;
+    int kind = classify(e, amn, bmn);
+    const bool use_slabs = splits > 1 || kind < 0;
     float* slabs = nullptr;
-    if (splits > 1) {
-        VITAE_REQUIRE(workspace && workspace_bytes >= vitae_gemm_workspace_bytes(M, N, splits),
-                      "gemm: split_k=%d needs %zu workspace bytes, got %zu", splits, vitae_gemm_workspace_bytes(M, N, splits),
-                      workspace_bytes);
+    if (use_slabs) {
+        const size_t need = static_cast<size_t>(splits) * M * N * sizeof(float);
+        VITAE_REQUIRE(workspace && workspace_bytes >= need,
+                      "gemm: split_k=%d / generic epilogue needs %zu workspace bytes, got %zu "
+                      "(vitae_gemm_workspace_bytes_for)", splits, need, workspace_bytes);
+        VITAE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "gemm: workspace must be 16-byte aligned");
         slabs = static_cast<float*>(workspace);
+        kind = EPI_F32;
     }
 
-    CUtensorMap ta, tb;
+    GemmLaunch g;
+    g.M = M; g.N = N; g.num_sub = num_sub; g.splits = splits; g.stream = as_stream(stream);
     int rc;
-    if (a_mn_major) rc = make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
-    else            rc = make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
+    if (amn) rc = make_tmap(&g.ta, A, 2, (uint64_t)M, (uint64_t)K, 0, (uint64_t)lda, 64, BK);
+    else     rc = make_tmap(&g.ta, A, 2, (uint64_t)K, (uint64_t)M, 0, (uint64_t)lda, BK, BM);
     if (rc) return rc;
-    if (b_mn_major) rc = make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
-    else            rc = make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)bn);
+    if (bmn) rc = make_tmap(&g.tb, B, 2, (uint64_t)N, (uint64_t)K, 0, (uint64_t)ldb, 64, BK);
+    else     rc = make_tmap(&g.tb, B, 2, (uint64_t)K, (uint64_t)N, 0, (uint64_t)ldb, BK, (uint32_t)bn);
     if (rc) return rc;
 
-    EpiParams ep;
-    ep.alpha = e->alpha; ep.alpha_ptr = e->alpha_ptr; ep.bias = e->bias; ep.addend = e->addend;
-    ep.add_rows = e->add_rows; ep.ldadd = e->ldadd;
-    ep.dgelu_src = static_cast<const __nv_bfloat16*>(e->dgelu_src); ep.ld_dgelu = e->ld_dgelu;
-    ep.out_f32 = e->out_f32; ep.ld_f32 = e->ld_f32; ep.accumulate = e->accumulate;
-    ep.out_bf16 = static_cast<__nv_bfloat16*>(e->out_bf16);
-    ep.out_gelu_bf16 = static_cast<__nv_bfloat16*>(e->out_gelu_bf16); ep.ld_bf16 = e->ld_bf16;
-    ep.out_rows = e->out_rows;
+    g.ep.alpha = e->alpha; g.ep.alpha_ptr = e->alpha_ptr; g.ep.bias = e->bias; g.ep.addend = e->addend; g.ep.ldadd = e->ldadd;
+    g.ep.dgelu_src = static_cast<const __nv_bfloat16*>(e->dgelu_src); g.ep.ld_dgelu = e->ld_dgelu;
+    g.ep.accumulate = e->accumulate;
+    if (use_slabs) {
+        // raw partial sums: alpha 1, no bias; the finalize kernel applies the real epilogue
+        g.ep.alpha = 1.0f; g.ep.alpha_ptr = nullptr; g.ep.bias = nullptr; g.ep.addend = nullptr; g.ep.dgelu_src = nullptr;
+        g.ep.accumulate = 0;
+        rc = make_tmap(&g.to0, slabs, 4, (uint64_t)N, (uint64_t)M, (uint64_t)splits, (uint64_t)N, 32, 32);
+        if (rc) return rc;
+        g.to1 = g.to0;
+    } else {
+        const bool out0_bf16 = kind != EPI_ADD_F32 && kind != EPI_F32;
+        if (out0_bf16) rc = make_tmap(&g.to0, e->out_bf16, 2, (uint64_t)N, (uint64_t)M, 1, (uint64_t)e->ld_bf16, 64, 32);
+        else           rc = make_tmap(&g.to0, e->out_f32, 4, (uint64_t)N, (uint64_t)M, 1, (uint64_t)e->ld_f32, 32, 32);
+        if (rc) return rc;
+        g.to1 = g.to0;
+        if (kind == EPI_BF16_GELU)
+            rc = make_tmap(&g.to1, e->out_gelu_bf16, 2, (uint64_t)N, (uint64_t)M, 1, (uint64_t)e->ld_bf16, 64, 32);
+        if (kind == EPI_BF16_F32)
+            rc = make_tmap(&g.to1, e->out_f32, 4, (uint64_t)N, (uint64_t)M, 1, (uint64_t)e->ld_f32, 32, 32);
+        if (rc) return rc;
+    }
 
-    cudaStream_t st = as_stream(stream);
-    const bool amn = a_mn_major != 0, bmn = b_mn_major != 0;
-    if (bn == 64) return dispatch_major<64, 4>(amn, bmn, ta, tb, M, N, num_kb, splits, ep, slabs, st);
-    if (bn == 128) return dispatch_major<128, 3>(amn, bmn, ta, tb, M, N, num_kb, splits, ep, slabs, st);
-    return dispatch_major<256, 4>(amn, bmn, ta, tb, M, N, num_kb, splits, ep, slabs, st);
+    // Pipeline depth: a grid that fits one CTA per SM gets the deep ring (all of shared memory for one CTA); larger
+    // grids get the shallow one so that two CTAs share an SM (one's epilogue overlaps the other's main loop).
+    const long long ctas = static_cast<long long>(ceil_div(M, BM)) * ceil_div(N, bn) * splits;
+    const bool deep = ctas <= 148;
+    const int eff_splits = dispatch(amn, bmn, kind, bn, deep, g);
+    if (eff_splits < 0) return eff_splits;
+    if (use_slabs) {
+        EpiParams ep;
+        ep.alpha = e->alpha; ep.alpha_ptr = e->alpha_ptr; ep.bias = e->bias; ep.addend = e->addend;
+        ep.add_rows = e->add_rows; ep.ldadd = e->ldadd;
+        ep.dgelu_src = static_cast<const __nv_bfloat16*>(e->dgelu_src); ep.ld_dgelu = e->ld_dgelu;
+        ep.out_f32 = e->out_f32; ep.ld_f32 = e->ld_f32; ep.accumulate = e->accumulate;
+        ep.out_bf16 = static_cast<__nv_bfloat16*>(e->out_bf16);
+        ep.out_gelu_bf16 = static_cast<__nv_bfloat16*>(e->out_gelu_bf16); ep.ld_bf16 = e->ld_bf16;
+        ep.out_rows = e->out_rows;
+        const long long total = static_cast<long long>(M) * (N / 4);
+        const int blocks = static_cast<int>(std::min<long long>(ceil_div<long long>(total, 256), 148 * 8));
+        launch_kernel(gemm_splitk_finalize_kernel, dim3(blocks), dim3(256), 0, g.stream, static_cast<const float*>(slabs),
+                      eff_splits, M, N, ep);
+        VITAE_CHECK_LAUNCH("gemm_splitk_finalize");
+    }
+    return 0;
 }

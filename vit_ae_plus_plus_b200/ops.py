@@ -136,9 +136,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn_major
         tn, sk = gemm_config(M, N, K)
         tile_n = tn if tile_n is None else tile_n
         split_k = sk if split_k is None else split_k
-    ws_ptr, ws_bytes = None, 0
-    if split_k > 1:
-        ws_bytes = lib.vitae_gemm_workspace_bytes(M, N, split_k)
+    ws_ptr = None
+    ws_bytes = lib.vitae_gemm_workspace_bytes_for(ctypes.byref(ep), int(a_mn_major), int(b_mn_major), M, N, split_k)
+    if ws_bytes:   # split-K slabs, or an epilogue that runs in the finalize kernel (row maps, unusual output sets)
         ws = workspace.get(ws_bytes) if workspace is not None else _workspace(ws_bytes, a.device)
         ws_ptr = ws.data_ptr()
     def launch():

@@ -84,6 +84,14 @@ size_t vitae_gemm_workspace_bytes(int M, int N, int split_k);
 size_t vitae_gemm_workspace_bytes_for(const vitae_gemm_epilogue* ep, int a_mn_major, int b_mn_major, int M, int N,
                                       int split_k);
 
+/* Times the (tile_n, split_k) candidates of this GEMM on the device and returns the fastest (CUDA events; the GEMMs of
+ * the step are short and latency bound, so the best tiling depends on the exact shape).  Re-runs the GEMM many times:
+ * outputs are overwritten with identical values; not allowed for accumulate epilogues or on a capturing stream.
+ * Candidates whose slabs exceed `workspace_bytes` are skipped.  Synchronises `stream`. */
+int vitae_gemm_autotune(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M, int N,
+                        int K, const vitae_gemm_epilogue* ep, void* workspace, size_t workspace_bytes, void* stream,
+                        int* best_tile_n, int* best_split_k);
+
 /* ------------------------------------------------------------------------------------------------------------
  * LayerNorm (biased variance, eps inside sqrt) -- nn.LayerNorm at model/vit.py:131,135,140-143 and
  * model/vit_autoenc.py:36,51,174,195.  x fp32 [rows, D]; y bf16 [rows, D] (GEMM operand) and/or y_f32; mean/rstd
@@ -92,13 +100,16 @@ size_t vitae_gemm_workspace_bytes_for(const vitae_gemm_epilogue* ep, int a_mn_ma
 int vitae_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
                         float* mean, float* rstd, int rows, int D, float eps, void* stream);
 /* dx_out = (dx_in ? dx_in : 0) + LN'(dy); dy is bf16 (dy_bf16) or fp32 (dy_f32); also emits a bf16 copy of dx_out
- * (operand of the next dgrad/wgrad GEMM) when dx_out_bf16 != NULL.  Per-block partial sums go to
- * partials [3, nblocks, D] (nblocks = vitae_layernorm_bwd_blocks(rows)): [0] dgamma, [1] dbeta, [2] column sums of
- * dx_out (= gradient of the bias that was added to this residual stream: proj.bias / fc2.bias, model/vit.py:142-143).
- * Finish them with ONE vitae_reduce_partials launch. */
+ * (operand of the next dgrad/wgrad GEMM) when dx_out_bf16 != NULL.  Row-wise only (it is on the dgrad critical path). */
 int vitae_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* gamma,
                         const float* mean, const float* rstd, const float* dx_in, float* dx_out, void* dx_out_bf16,
-                        float* partials, int rows, int D, void* stream);
+                        int rows, int D, void* stream);
+/* Column reductions of the same backward, off the critical path: per-slice partial sums go to
+ * partials [3, nblocks, D] (nblocks = vitae_layernorm_bwd_blocks(rows)): [0] dgamma = sum dy*xhat, [1] dbeta = sum dy,
+ * [2] column sums of dx_out (= gradient of the bias that was added to this residual stream: proj.bias / fc2.bias,
+ * model/vit.py:142-143; zeros when dx_out == NULL).  Finish them with ONE vitae_reduce_partials launch. */
+int vitae_layernorm_param_grads(const void* dy_bf16, const float* dy_f32, const float* x, const float* mean,
+                                const float* rstd, const float* dx_out, float* partials, int rows, int D, void* stream);
 int vitae_layernorm_bwd_blocks(int rows);
 /* out_k[c] = (accumulate ? out_k[c] : 0) + sum_blk partials[k][blk][c] for k = 0..2; NULL outputs are skipped. */
 int vitae_reduce_partials(const float* partials, int nblk, int D, float* out0, float* out1, float* out2,

@@ -7,8 +7,8 @@
 // Round-1 implementation: warp-level mma.sync (m16n8k16 bf16, fp32 accumulate), ldmatrix from padded shared
 // memory, cp.async staging, online softmax in the exp2 domain with quad-shuffle row reductions.  Attention is
 // 7-14 % of the path's FLOPs; the dense contractions run on tcgen05 (gemm_tcgen05.cu).
-// Backward = three kernels: delta = rowsum(dO*O); dQ (one CTA per query tile, loops over kv tiles);
-// dK/dV (one CTA per kv tile, loops over query tiles).  No atomics -> deterministic.
+// Backward = two kernels: dQ (one CTA per query tile, loops over kv tiles; also produces delta = rowsum(dO*O) for its
+// rows) and dK/dV (one CTA per kv tile, loops over query tiles).  No atomics -> deterministic.
 #include "common.h"
 #include "ptx.cuh"
 
@@ -193,44 +193,11 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------------ backward
-// delta[b,h,n] = sum_d dO[b,n,h,d] * O[b,n,h,d]; one warp per token, 8-element chunks, group shuffle per head
-__global__ void __launch_bounds__(256)
-attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout, float* __restrict__ delta,
-                      int BN, int N, int H, int hd) {
-    pdl_trigger();
-    pdl_wait();
-    const int tok = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (tok >= BN) return;
-    const int lane = threadIdx.x & 31;
-    const int D = H * hd;
-    const int lanes_per_head = hd / 8;
-    const int b = tok / N, n = tok % N;
-    for (int c0 = 0; c0 < D / 8; c0 += 32) {
-        const int c = c0 + lane;
-        float s = 0.f;
-        if (c < D / 8) {
-            const uint4 a = *reinterpret_cast<const uint4*>(out + static_cast<size_t>(tok) * D + c * 8);
-            const uint4 g = *reinterpret_cast<const uint4*>(dout + static_cast<size_t>(tok) * D + c * 8);
-            const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&a);
-            const __nv_bfloat162* gp = reinterpret_cast<const __nv_bfloat162*>(&g);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 x = __bfloat1622float2(ap[i]), y = __bfloat1622float2(gp[i]);
-                s += x.x * y.x + x.y * y.y;
-            }
-        }
-        for (int o = lanes_per_head >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (c < D / 8 && (lane % lanes_per_head) == 0) {
-            const int h = (c * 8) / hd;
-            delta[(static_cast<size_t>(b) * H + h) * N + n] = s;
-        }
-    }
-}
-
 template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS)
-attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
-                   const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale, float scale_log2) {
+attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                   const float* __restrict__ lse, float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int N, int H,
+                   float scale, float scale_log2) {
     pdl_trigger();
     pdl_wait();
     constexpr int LD = HD + 8;
@@ -238,6 +205,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     __shared__ __align__(16) __nv_bfloat16 sdO[TILE * LD];
     __shared__ __align__(16) __nv_bfloat16 sK[TILE * LD];
     __shared__ __align__(16) __nv_bfloat16 sV[TILE * LD];
+    __shared__ __align__(16) __nv_bfloat16 sO[TILE * LD];   // forward output rows of this query tile (for delta)
     const int h = blockIdx.y, b = blockIdx.z;
     const int q0 = blockIdx.x * TILE;
     const int D = H * HD;
@@ -247,18 +215,20 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     const __nv_bfloat16* gk = gq + D;
     const __nv_bfloat16* gv = gq + 2 * D;
     const __nv_bfloat16* gdo = dout + static_cast<size_t>(b) * N * D + h * HD;
+    const __nv_bfloat16* go = out + static_cast<size_t>(b) * N * D + h * HD;
 
     load_tile_async<HD>(sQ, gq, pitch, q0, N);
     load_tile_async<HD>(sdO, gdo, D, q0, N);
+    load_tile_async<HD>(sO, go, D, q0, N);
     load_tile_async<HD>(sK, gk, pitch, 0, N);
     load_tile_async<HD>(sV, gv, pitch, 0, N);
     cp_async_commit();
 
     const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
     const float* lrow = lse + (static_cast<size_t>(b) * H + h) * N;
-    const float* drow = delta + (static_cast<size_t>(b) * H + h) * N;
+    float* drow = delta + (static_cast<size_t>(b) * H + h) * N;
     const float lse0 = r0 < N ? lrow[r0] * LOG2E : 0.f, lse1 = r1 < N ? lrow[r1] * LOG2E : 0.f;
-    const float dl0 = r0 < N ? drow[r0] : 0.f, dl1 = r1 < N ? drow[r1] : 0.f;
+    float dl0 = 0.f, dl1 = 0.f;   // delta = rowsum(dO * O), computed below from the staged tiles
 
     float dq[HD / 8][4];
 #pragma unroll
@@ -273,6 +243,24 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
         if (t == 0) {
             load_a_frags<HD>(sQ, warp, lane, qf);
             load_a_frags<HD>(sdO, warp, lane, dof);
+            // delta for this thread's two rows: the quad shares a row, each lane covers 2 of every 8 columns
+            const int lr0 = warp * 16 + (lane >> 2), lr1 = lr0 + 8;
+#pragma unroll
+            for (int j = 0; j < HD / 8; ++j) {
+                const int d = 8 * j + 2 * (lane & 3);
+                const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sdO + lr0 * LD + d));
+                const float2 o0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sO + lr0 * LD + d));
+                const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sdO + lr1 * LD + d));
+                const float2 o1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sO + lr1 * LD + d));
+                dl0 += a0.x * o0.x + a0.y * o0.y;
+                dl1 += a1.x * o1.x + a1.y * o1.y;
+            }
+            dl0 = quad_sum(dl0);
+            dl1 = quad_sum(dl1);
+            if ((lane & 3) == 0) {   // the dK/dV kernel (launched next) reads delta from global memory
+                if (r0 < N) drow[r0] = dl0;
+                if (r1 < N) drow[r1] = dl1;
+            }
         }
         float s[8][4], dp[8][4];
         mma_a_tileT<HD>(s, qf, sK, lane);
@@ -419,20 +407,18 @@ extern "C" int vitae_attention_bwd(const void* qkv, const void* out, const void*
     const auto* o = static_cast<const __nv_bfloat16*>(out);
     const auto* g = static_cast<const __nv_bfloat16*>(dout);
     auto* dq = static_cast<__nv_bfloat16*>(dqkv);
-    launch_kernel(attn_bwd_delta_kernel, dim3(ceil_div(B * N, 8)), dim3(256), 0, st, o, g, delta, B * N, N, H, hd);
-    VITAE_CHECK_LAUNCH("attention_bwd_delta");
     dim3 grid(ceil_div(N, TILE), H, B);
     const float sl2 = scale * LOG2E;
     if (hd == 64) {
-        launch_kernel(attn_bwd_dq_kernel<64>, dim3(grid), dim3(ATT_THREADS), 0, st, q, g, lse, delta, dq, N, H, scale, sl2);
+        launch_kernel(attn_bwd_dq_kernel<64>, dim3(grid), dim3(ATT_THREADS), 0, st, q, o, g, lse, delta, dq, N, H, scale, sl2);
         VITAE_CHECK_LAUNCH("attention_bwd_dq");
         launch_kernel(attn_bwd_dkv_kernel<64>, dim3(grid), dim3(ATT_THREADS), 0, st, q, g, lse, delta, dq, N, H, scale, sl2);
     } else if (hd == 32) {
-        launch_kernel(attn_bwd_dq_kernel<32>, dim3(grid), dim3(ATT_THREADS), 0, st, q, g, lse, delta, dq, N, H, scale, sl2);
+        launch_kernel(attn_bwd_dq_kernel<32>, dim3(grid), dim3(ATT_THREADS), 0, st, q, o, g, lse, delta, dq, N, H, scale, sl2);
         VITAE_CHECK_LAUNCH("attention_bwd_dq");
         launch_kernel(attn_bwd_dkv_kernel<32>, dim3(grid), dim3(ATT_THREADS), 0, st, q, g, lse, delta, dq, N, H, scale, sl2);
     } else {
-        launch_kernel(attn_bwd_dq_kernel<16>, dim3(grid), dim3(ATT_THREADS), 0, st, q, g, lse, delta, dq, N, H, scale, sl2);
+        launch_kernel(attn_bwd_dq_kernel<16>, dim3(grid), dim3(ATT_THREADS), 0, st, q, o, g, lse, delta, dq, N, H, scale, sl2);
         VITAE_CHECK_LAUNCH("attention_bwd_dq");
         launch_kernel(attn_bwd_dkv_kernel<16>, dim3(grid), dim3(ATT_THREADS), 0, st, q, g, lse, delta, dq, N, H, scale, sl2);
     }

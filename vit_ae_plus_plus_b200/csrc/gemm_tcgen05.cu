@@ -711,3 +711,62 @@ extern "C" int vitae_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
     }
     return 0;
 }
+
+// Times every (tile_n, split_k) candidate for this GEMM on the device (back-to-back launches from this loop: the host
+// enqueue cost of ~2 us per launch stays below the kernel time, so the stream is device-bound; CUDA events; best of two
+// trials) and returns the fastest.  The GEMMs of the training step are short and latency / ingest bound, which makes the
+// best tiling a property of the exact shape.  Candidates whose slabs do not fit into `workspace` are skipped.  The
+// outputs are overwritten repeatedly with the same values (do not use with accumulate).  Synchronises `stream`.
+extern "C" int vitae_gemm_autotune(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M,
+                                   int N, int K, const vitae_gemm_epilogue* e, void* workspace, size_t workspace_bytes,
+                                   void* stream, int* best_tile_n, int* best_split_k) {
+    VITAE_REQUIRE(e && best_tile_n && best_split_k, "gemm_autotune: null argument");
+    VITAE_REQUIRE(!e->accumulate, "gemm_autotune: accumulate epilogues cannot be re-run");
+    cudaStream_t st = as_stream(stream);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    VITAE_REQUIRE(cap == cudaStreamCaptureStatusNone, "gemm_autotune: stream is capturing");
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)
+        return set_error(-3, "gemm_autotune: cudaEventCreate failed");
+    const int num_sub = ceil_div(K, BK), tiles_m = ceil_div(M, BM);
+    const int tiles_n_opts[3] = {64, 128, 256};
+    const int split_opts[6] = {1, 2, 3, 4, 6, 8};
+    float best = 1e30f;
+    int rc = 0;
+    *best_tile_n = 0;
+    *best_split_k = 1;
+    for (int ti = 0; ti < 3 && rc == 0; ++ti) {
+        const int tn = tiles_n_opts[ti];
+        if (tn > 64 && N < tn) continue;
+        const long long tiles = static_cast<long long>(tiles_m) * ceil_div(N, tn);
+        for (int si = 0; si < 6 && rc == 0; ++si) {
+            const int sk = split_opts[si];
+            if (sk > 1 && (num_sub < 4 * sk || tiles * sk > 3 * 148)) continue;
+            if (vitae_gemm_workspace_bytes_for(e, a_mn_major, b_mn_major, M, N, sk) > workspace_bytes) continue;
+            constexpr int REPS = 12;
+            for (int w = 0; w < 2 && rc == 0; ++w)
+                rc = vitae_gemm_bf16(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, e, tn, sk, workspace, workspace_bytes, stream);
+            float t = 1e30f;
+            for (int trial = 0; trial < 2 && rc == 0; ++trial) {
+                cudaEventRecord(e0, st);
+                for (int r = 0; r < REPS && rc == 0; ++r)
+                    rc = vitae_gemm_bf16(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, e, tn, sk, workspace, workspace_bytes, stream);
+                cudaEventRecord(e1, st);
+                if (cudaEventSynchronize(e1) != cudaSuccess) rc = set_error(-3, "gemm_autotune: %s", cudaGetErrorString(cudaGetLastError()));
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                t = ms < t ? ms : t;
+            }
+            if (rc == 0 && t < best) {
+                best = t;
+                *best_tile_n = tn;
+                *best_split_k = sk;
+            }
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc == 0 && *best_tile_n == 0) return set_error(-2, "gemm_autotune: no candidate fits the workspace");
+    return rc;
+}

@@ -6,7 +6,6 @@
 namespace vitae {
 
 constexpr int LN_WARPS = 8;        // rows per CTA iteration
-constexpr int LN_BWD_MAX_BLOCKS = 148;
 // kernels are templated on LN_MAX_VEC = float4 per lane (D <= 128 * LN_MAX_VEC): registers follow the actual width
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -75,31 +74,23 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     }
 }
 
-// dx_out = dx_in + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
-// partials[0][blk][:] = sum dy * xhat (dgamma), partials[1][blk][:] = sum dy (dbeta),
-// partials[2][blk][:] = sum dx_out (column sums of the residual gradient = gradient of the bias added to that stream)
+// dx_out = dx_in + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma.   Row-wise only: this kernel sits on
+// the backward critical path (dgrad chain), so the column reductions that give the affine / bias gradients are a
+// separate kernel (layernorm_param_grads_kernel) that runs off that path.
 template <int LN_MAX_VEC>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ dy32, const float* __restrict__ x,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ dx_in, float* __restrict__ dx_out, __nv_bfloat16* __restrict__ dx16,
-                     float* __restrict__ partials, int rows, int D) {
+                     int rows, int D) {
     pdl_trigger();
     pdl_wait();
-    __shared__ float red[LN_WARPS][32 * 4 + 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nvec = D >> 2;
-    float4 dg[LN_MAX_VEC], db[LN_MAX_VEC], ds[LN_MAX_VEC];
-#pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
-        dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        ds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
     for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
         const float mu = mean[row], rs = rstd[row];
         const size_t off = static_cast<size_t>(row) * D;
-        float4 xh[LN_MAX_VEC], g[LN_MAX_VEC];
+        float4 xh[LN_MAX_VEC], g[LN_MAX_VEC], din[LN_MAX_VEC];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < LN_MAX_VEC; ++i) {
@@ -115,13 +106,12 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
                 } else {
                     d = reinterpret_cast<const float4*>(dy32 + off)[c];
                 }
+                if (dx_in) din[i] = reinterpret_cast<const float4*>(dx_in + off)[c];
                 const float4 gm = reinterpret_cast<const float4*>(gamma)[c];
                 xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
                 g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
                 s1 += g[i].x + g[i].y + g[i].z + g[i].w;
                 s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
-                dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
-                db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
             }
         }
         const float m1 = warp_sum(s1) / D, m2 = warp_sum(s2) / D;
@@ -135,11 +125,9 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
                 o.z = rs * (g[i].z - m1 - xh[i].z * m2);
                 o.w = rs * (g[i].w - m1 - xh[i].w * m2);
                 if (dx_in) {
-                    const float4 p = reinterpret_cast<const float4*>(dx_in + off)[c];
-                    o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+                    o.x += din[i].x; o.y += din[i].y; o.z += din[i].z; o.w += din[i].w;
                 }
                 reinterpret_cast<float4*>(dx_out + off)[c] = o;
-                ds[i].x += o.x; ds[i].y += o.y; ds[i].z += o.z; ds[i].w += o.w;
                 if (dx16) {
                     uint2 pk;
                     pk.x = pack_bf16(o.x, o.y);
@@ -149,30 +137,41 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
             }
         }
     }
-    // cross-warp reduction of the affine-gradient partials, one 128-column slab at a time
-    float* pg = partials + static_cast<size_t>(blockIdx.x) * D;
-    float* pb = partials + static_cast<size_t>(gridDim.x + blockIdx.x) * D;
-    float* ps = partials + static_cast<size_t>(2 * gridDim.x + blockIdx.x) * D;
-#pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
-        if (32 * i >= nvec) break;
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-            const float4 val = pass == 0 ? dg[i] : (pass == 1 ? db[i] : ds[i]);
-            __syncthreads();
-            red[warp][lane * 4 + 0] = val.x;
-            red[warp][lane * 4 + 1] = val.y;
-            red[warp][lane * 4 + 2] = val.z;
-            red[warp][lane * 4 + 3] = val.w;
-            __syncthreads();
-            if (threadIdx.x < 128) {
-                float s = 0.f;
-#pragma unroll
-                for (int w = 0; w < LN_WARPS; ++w) s += red[w][threadIdx.x];
-                const int col = 128 * i + threadIdx.x;
-                if (col < D) (pass == 0 ? pg : (pass == 1 ? pb : ps))[col] = s;
-            }
+}
+
+// Column reductions of the LayerNorm backward, per block of rows (finished by reduce_partials_kernel):
+// partials[0][blk][:] = sum dy * xhat (dgamma), partials[1][blk][:] = sum dy (dbeta),
+// partials[2][blk][:] = sum dx_out (column sums of the residual gradient = gradient of the bias added to that stream).
+// Block = 32 columns x 8 row lanes (coalesced 128-byte row segments); grid = (D / 32 strips, row slices).
+__global__ void __launch_bounds__(256)
+layernorm_param_grads_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ dy32,
+                             const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                             const float* __restrict__ dx_out, float* __restrict__ partials, int rows, int D,
+                             int rows_per_slice) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float red[3][8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + tx;
+    const int r0 = blockIdx.y * rows_per_slice, r1 = min(rows, r0 + rows_per_slice);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (col < D) {
+        for (int r = r0 + ty; r < r1; r += 8) {
+            const size_t o = static_cast<size_t>(r) * D + col;
+            const float d = dy16 ? __bfloat162float(dy16[o]) : dy32[o];
+            const float xh = (x[o] - mean[r]) * rstd[r];
+            a0 += d * xh;
+            a1 += d;
+            if (dx_out) a2 += dx_out[o];
         }
+    }
+    red[0][ty][tx] = a0; red[1][ty][tx] = a1; red[2][ty][tx] = a2;
+    __syncthreads();
+    if (ty < 3 && col < D) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[ty][k][tx];
+        partials[(static_cast<size_t>(ty) * gridDim.y + blockIdx.y) * D + col] = s;
     }
 }
 
@@ -320,19 +319,19 @@ extern "C" int vitae_layernorm_fwd(const float* x, const float* gamma, const flo
     return 0;
 }
 
-extern "C" int vitae_layernorm_bwd_blocks(int rows) { return std::max(1, std::min(ceil_div(rows, LN_WARPS), LN_BWD_MAX_BLOCKS)); }
+extern "C" int vitae_layernorm_bwd_blocks(int rows) { return std::max(1, std::min(ceil_div(rows, 32), 64)); }
 
 extern "C" int vitae_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* gamma,
                                    const float* mean, const float* rstd, const float* dx_in, float* dx_out,
-                                   void* dx_out_bf16, float* partials, int rows, int D, void* stream) {
+                                   void* dx_out_bf16, int rows, int D, void* stream) {
     VITAE_REQUIRE((dy_bf16 != nullptr) != (dy_f32 != nullptr), "layernorm_bwd: exactly one of dy_bf16/dy_f32");
-    VITAE_REQUIRE(x && gamma && mean && rstd && dx_out && partials, "layernorm_bwd: null pointer");
+    VITAE_REQUIRE(x && gamma && mean && rstd && dx_out, "layernorm_bwd: null pointer");
     VITAE_REQUIRE(rows > 0 && D > 0 && D % 4 == 0 && D <= 1024, "layernorm_bwd: unsupported D=%d rows=%d", D, rows);
-    const int blocks = vitae_layernorm_bwd_blocks(rows);
+    const int blocks = std::min(ceil_div(rows, LN_WARPS), 148 * 4);
     const auto* dy16 = static_cast<const __nv_bfloat16*>(dy_bf16);
     auto* dx16 = static_cast<__nv_bfloat16*>(dx_out_bf16);
     cudaStream_t st = as_stream(stream);
-#define VITAE_LN_BWD(V) launch_kernel(layernorm_bwd_kernel<V>, dim3(blocks), dim3(LN_WARPS * 32), 0, st, dy16, dy_f32, x, gamma, mean, rstd, dx_in, dx_out, dx16, partials, rows, D)
+#define VITAE_LN_BWD(V) launch_kernel(layernorm_bwd_kernel<V>, dim3(blocks), dim3(LN_WARPS * 32), 0, st, dy16, dy_f32, x, gamma, mean, rstd, dx_in, dx_out, dx16, rows, D)
     switch (ln_vec_class(D)) {
         case 1: VITAE_LN_BWD(1); break;
         case 2: VITAE_LN_BWD(2); break;
@@ -342,6 +341,21 @@ extern "C" int vitae_layernorm_bwd(const void* dy_bf16, const float* dy_f32, con
     }
 #undef VITAE_LN_BWD
     VITAE_CHECK_LAUNCH("layernorm_bwd");
+    return 0;
+}
+
+extern "C" int vitae_layernorm_param_grads(const void* dy_bf16, const float* dy_f32, const float* x, const float* mean,
+                                           const float* rstd, const float* dx_out, float* partials, int rows, int D,
+                                           void* stream) {
+    VITAE_REQUIRE((dy_bf16 != nullptr) != (dy_f32 != nullptr), "layernorm_param_grads: exactly one of dy_bf16/dy_f32");
+    VITAE_REQUIRE(x && mean && rstd && partials && rows > 0 && D > 0, "layernorm_param_grads: bad arguments");
+    const int nblk = vitae_layernorm_bwd_blocks(rows);
+    const int rows_per_slice = ceil_div(rows, nblk);
+    VITAE_REQUIRE(ceil_div(rows, rows_per_slice) <= nblk, "layernorm_param_grads: slice arithmetic");
+    dim3 grid(ceil_div(D, 32), nblk);
+    launch_kernel(layernorm_param_grads_kernel, grid, dim3(256), 0, as_stream(stream),
+                  static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, mean, rstd, dx_out, partials, rows, D, rows_per_slice);
+    VITAE_CHECK_LAUNCH("layernorm_param_grads");
     return 0;
 }
 

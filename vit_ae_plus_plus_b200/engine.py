@@ -195,7 +195,7 @@ class _GraphSlot:
         self.calls = 0
 
 
-MAX_INPUT_ADDRESSES = 1   # input-volume addresses that get their own (zero-copy) graphs; others are copied (below)
+MAX_INPUT_ADDRESSES = 4   # input-volume addresses that get their own (zero-copy) graphs; others are copied (below)
 
 
 class _Arena:
@@ -259,6 +259,8 @@ class MAEPlan:
         # buffers read by the side lane are double-buffered so that the main lane never waits for recent side work
         self.dres16 = [a.new((Mmax * Dmax,), _BF16), a.new((Mmax * Dmax,), _BF16)]
         self.d_d = a.new((Mmax * Dmax,), _BF16)
+        # LayerNorm-backward inputs: read again by the side lane (affine-gradient reductions), so two alternate
+        self.d_ln = [a.new((Mmax * Dmax,), _BF16), a.new((Mmax * Dmax,), _BF16)]
         self.d_hid = [a.new((Mmax * Hmax,), _BF16), a.new((Mmax * Hmax,), _BF16)]
         self.dqkv = [a.new((Mmax * 3 * Dmax,), _BF16), a.new((Mmax * 3 * Dmax,), _BF16)]
         self.delta = a.new((B * max(eng.enc.heads * self.Ne, eng.dec.heads * self.Nd),), _F32)
@@ -515,7 +517,7 @@ class MAEEngine:
                      out_f32=self._g("decoder_pred.weight"), accumulate=acc, workspace=wss)
             ops.colsum(dpred, pl.Md, P, self._g("decoder_pred.bias"), cws, accumulate=acc)
         self._side(side_pred, reads=("dpred",))
-        d_d = pl.d_d[:pl.Md * Dd].view(pl.Md, Dd)
+        d_d = self._ln_in(pl, pl.Md, Dd)
         ops.gemm(dpred, self._w("decoder_pred.weight"), pl.Md, Dd, P, b_mn_major=True, out_bf16=d_d, workspace=wsm)
         last_dec = f"decoder_blocks.{self.dec.depth - 1}.mlp.fc2.bias" if self.dec.depth else None
         cur = self._ln_bwd(pl, d_d, pl.dec.x[-1], "decoder_norm", pl.mean_dn, pl.rstd_dn, None, 0, pl.Md, Dd, acc,
@@ -535,7 +537,7 @@ class MAEEngine:
                      out_f32=self._g("decoder_embed.weight"), accumulate=acc, workspace=wss)
             ops.colsum(pl.g_embed, pl.Me, Dd, self._g("decoder_embed.bias"), cws, accumulate=acc)
         self._side(side_embed, reads=("g_embed", ("dres", cur)))
-        d_e = pl.d_d[:pl.Me * D].view(pl.Me, D)
+        d_e = self._ln_in(pl, pl.Me, D)
         ops.gemm(pl.g_embed, self._w("decoder_embed.weight"), pl.Me, D, Dd, b_mn_major=True, out_bf16=d_e,
                  workspace=wsm)
         # ---- encoder norm + blocks (vit_autoenc.py:172-175)
@@ -555,11 +557,18 @@ class MAEEngine:
         self._side(side_pe, reads=("g_pe",))
         lanes.join()
 
+    def _ln_in(self, pl: MAEPlan, M: int, D: int) -> torch.Tensor:
+        """Buffer for the input gradient (dy) of the NEXT _ln_bwd call; the side lane reads it after the main lane has
+        moved on, so main waits here only for the side reader of two calls ago."""
+        k = pl.ln_calls & 1
+        self.lanes.before_write(("d_ln", k))
+        return pl.d_ln[k][:M * D].view(M, D)
+
     def _ln_bwd(self, pl: MAEPlan, dy: torch.Tensor, x: torch.Tensor, name: str, mean, rstd, dx_in_idx: Optional[int],
                 out_idx: int, M: int, D: int, acc: bool, bias_name: Optional[str]) -> int:
-        """LayerNorm backward on the main lane: dres[out_idx] = (dres[dx_in_idx] if given) + LN'(dy), plus its bf16 copy
-        dres16[out_idx]; the affine gradients and ``bias_name`` (the bias whose gradient is the column sum of the new
-        residual gradient) are finished on the side lane.  Returns out_idx."""
+        """LayerNorm backward.  Main lane (critical path): dres[out_idx] = (dres[dx_in_idx] if given) + LN'(dy), plus its
+        bf16 copy dres16[out_idx].  Side lane: the column reductions -- affine gradients and ``bias_name`` (the bias whose
+        gradient is the column sum of the new residual gradient).  ``dy`` must come from _ln_in().  Returns out_idx."""
         nb = ops.layernorm_bwd_blocks(M)
         k = pl.ln_calls & 1
         pl.ln_calls += 1
@@ -567,11 +576,14 @@ class MAEEngine:
         dx_in = None if dx_in_idx is None else pl.dres[dx_in_idx][:M * D].view(M, D)
         dx_out = pl.dres[out_idx][:M * D].view(M, D)
         dx16 = pl.dres16[out_idx][:M * D].view(M, D)
-        self.lanes.before_write(("dres", out_idx), ("dres16", out_idx), ("part", k))
-        ops.layernorm_bwd(dy, x, self._p(f"{name}.weight"), mean, rstd, dx_in, dx_out, dx16, partials)
+        self.lanes.before_write(("dres", out_idx), ("dres16", out_idx))
+        ops.layernorm_bwd(dy, x, self._p(f"{name}.weight"), mean, rstd, dx_in, dx_out, dx16)
         gb = self._g(bias_name) if bias_name is not None else None
-        self._side(lambda: ops.reduce_partials(partials, nb, D, self._g(f"{name}.weight"), self._g(f"{name}.bias"), gb,
-                                               accumulate=acc), reads=(("part", k),))
+
+        def side():
+            ops.layernorm_param_grads(dy, x, mean, rstd, dx_out if gb is not None else None, partials)
+            ops.reduce_partials(partials, nb, D, self._g(f"{name}.weight"), self._g(f"{name}.bias"), gb, accumulate=acc)
+        self._side(side, reads=(("d_ln", k), ("dres", out_idx)))
         return out_idx
 
     def _stack_bwd(self, st: StackSpec, sb, pl: MAEPlan, M: int, B: int, N: int, cur: int, acc: bool) -> int:
@@ -604,9 +616,10 @@ class MAEEngine:
                          out_f32=self._g(f"{pre}.mlp.fc1.weight"), accumulate=acc, workspace=wss)
                 ops.colsum(d_hid, M, hid, self._g(f"{pre}.mlp.fc1.bias"), cws, accumulate=acc)
             self._side(side_fc1, reads=(("d_hid", hb),))
-            ops.gemm(d_hid, self._w(f"{pre}.mlp.fc1.weight"), M, D, hid, b_mn_major=True, out_bf16=d_d, workspace=wsm)
+            d_ln = self._ln_in(pl, M, D)
+            ops.gemm(d_hid, self._w(f"{pre}.mlp.fc1.weight"), M, D, hid, b_mn_major=True, out_bf16=d_ln, workspace=wsm)
             nxt = cur ^ 1
-            self._ln_bwd(pl, d_d, b.xmid, f"{pre}.norm2", b.mean2, b.rstd2, cur, nxt, M, D, acc,
+            self._ln_bwd(pl, d_ln, b.xmid, f"{pre}.norm2", b.mean2, b.rstd2, cur, nxt, M, D, acc,
                          f"{pre}.attn.proj.bias")
             cur = nxt
             dres16 = pl.dres16[cur][:M * D].view(M, D)
@@ -623,10 +636,11 @@ class MAEEngine:
                          out_f32=self._g(f"{pre}.attn.qkv.weight"), accumulate=acc, workspace=wss)
                 ops.colsum(dqkv, M, 3 * D, self._g(f"{pre}.attn.qkv.bias"), cws, accumulate=acc)
             self._side(side_qkv, reads=(("dqkv", hb),))
-            ops.gemm(dqkv, self._w(f"{pre}.attn.qkv.weight"), M, D, 3 * D, b_mn_major=True, out_bf16=d_d, workspace=wsm)
+            d_ln = self._ln_in(pl, M, D)
+            ops.gemm(dqkv, self._w(f"{pre}.attn.qkv.weight"), M, D, 3 * D, b_mn_major=True, out_bf16=d_ln, workspace=wsm)
             nxt = cur ^ 1
             below = f"{st.prefix}.{i - 1}.mlp.fc2.bias" if i > 0 else None
-            self._ln_bwd(pl, d_d, x_in, f"{pre}.norm1", b.mean1, b.rstd1, cur, nxt, M, D, acc, below)
+            self._ln_bwd(pl, d_ln, x_in, f"{pre}.norm1", b.mean1, b.rstd1, cur, nxt, M, D, acc, below)
             cur = nxt
         return cur
 

@@ -4,6 +4,7 @@ CUDA stream.  No fallbacks: a non-CUDA tensor or a missing library raises."""
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -46,6 +47,14 @@ def gemm_config(M: int, N: int, K: int, n_sm: int = 148):
     if num_kb >= 32 and tiles <= n_sm:
         split = min(max(1, (2 * n_sm) // tiles), max(1, num_kb // 8), 16)
     return tile_n, split
+
+
+# Measured (tile_n, split_k) per GEMM signature.  The GEMMs of this path are short and latency / ingest bound
+# (DESIGN.md), so the best tiling is found by timing the candidates once per shape on the device (first eager call,
+# vitae_gemm_autotune, ~2 ms per shape) instead of a static rule.  VITAE_GEMM_AUTOTUNE=0 keeps the static rule (run-to-run reproducible bits:
+# split-K changes the summation order).
+_tuned = {}
+AUTOTUNE = os.environ.get("VITAE_GEMM_AUTOTUNE", "1") != "0"
 
 
 class GrowBuf:
@@ -132,18 +141,37 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn_major
     ep.out_gelu_bf16 = _ptr(out_gelu_bf16)
     ep.ld_bf16 = ld_bf16 if ld_bf16 is not None else N
     ep.out_rows = _ptr(out_rows)
-    if tile_n is None or split_k is None:
-        tn, sk = gemm_config(M, N, K)
-        tile_n = tn if tile_n is None else tile_n
-        split_k = sk if split_k is None else split_k
-    ws_ptr = None
-    ws_bytes = lib.vitae_gemm_workspace_bytes_for(ctypes.byref(ep), int(a_mn_major), int(b_mn_major), M, N, split_k)
-    if ws_bytes:   # split-K slabs, or an epilogue that runs in the finalize kernel (row maps, unusual output sets)
-        ws = workspace.get(ws_bytes) if workspace is not None else _workspace(ws_bytes, a.device)
-        ws_ptr = ws.data_ptr()
-    def launch():
+    def launch_with(tn: int, sk: int):
+        ws_ptr = None
+        ws_bytes = lib.vitae_gemm_workspace_bytes_for(ctypes.byref(ep), int(a_mn_major), int(b_mn_major), M, N, sk)
+        if ws_bytes:   # split-K slabs, or an epilogue that runs in the finalize kernel (row maps, unusual output sets)
+            ws = workspace.get(ws_bytes) if workspace is not None else _workspace(ws_bytes, a.device)
+            ws_ptr = ws.data_ptr()
         check(lib.vitae_gemm_bf16(a.data_ptr(), lda, int(a_mn_major), b.data_ptr(), ldb, int(b_mn_major), M, N, K,
-                                  ctypes.byref(ep), tile_n, split_k, ws_ptr, ws_bytes, _stream()), "vitae_gemm_bf16")
+                                  ctypes.byref(ep), tn, sk, ws_ptr, ws_bytes, _stream()), "vitae_gemm_bf16")
+
+    if tile_n is None or split_k is None:
+        key = (M, N, K, bool(a_mn_major), bool(b_mn_major), bias is not None, addend is not None, add_rows is not None,
+               dgelu_src is not None, out_f32 is not None, out_bf16 is not None, out_gelu_bf16 is not None,
+               out_rows is not None)
+        cfg = _tuned.get(key)
+        if cfg is None:
+            if AUTOTUNE and not accumulate and not torch.cuda.is_current_stream_capturing():
+                ws_bytes = max(lib.vitae_gemm_workspace_bytes_for(ctypes.byref(ep), int(a_mn_major), int(b_mn_major), M, N, sk)
+                               for sk in (1, 8))
+                ws = (workspace.get(ws_bytes) if workspace is not None else _workspace(ws_bytes, a.device)) if ws_bytes else None
+                tn, sk = ctypes.c_int(0), ctypes.c_int(1)
+                check(lib.vitae_gemm_autotune(a.data_ptr(), lda, int(a_mn_major), b.data_ptr(), ldb, int(b_mn_major), M, N, K,
+                                              ctypes.byref(ep), _ptr(ws), ws_bytes, _stream(), ctypes.byref(tn),
+                                              ctypes.byref(sk)), "vitae_gemm_autotune")
+                cfg = _tuned[key] = (tn.value, sk.value)
+            else:
+                cfg = gemm_config(M, N, K)
+        tile_n = cfg[0] if tile_n is None else tile_n
+        split_k = cfg[1] if split_k is None else split_k
+
+    def launch():
+        launch_with(tile_n, split_k)
     launch()
     if _gemm_log is not None:
         _gemm_log.append((2.0 * M * N * K, launch))
@@ -172,14 +200,24 @@ def reduce_partials(partials, nblk: int, D: int, out0=None, out1=None, out2=None
                                     _stream()), "vitae_reduce_partials")
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dx_out, dx_out_bf16, partials) -> None:
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dx_out, dx_out_bf16) -> None:
     lib = _lib.load()
     rows, D = x.numel() // x.shape[-1], x.shape[-1]
     dy16 = dy.data_ptr() if dy.dtype == _BF16 else None
     dy32 = dy.data_ptr() if dy.dtype == _F32 else None
     check(lib.vitae_layernorm_bwd(dy16, dy32, x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                  _ptr(dx_in), dx_out.data_ptr(), _ptr(dx_out_bf16), partials.data_ptr(), rows, D,
-                                  _stream()), "vitae_layernorm_bwd")
+                                  _ptr(dx_in), dx_out.data_ptr(), _ptr(dx_out_bf16), rows, D, _stream()),
+          "vitae_layernorm_bwd")
+
+
+def layernorm_param_grads(dy, x, mean, rstd, dx_out, partials) -> None:
+    """partials [3, layernorm_bwd_blocks(rows), D] <- per-slice sums of dy*xhat, dy, dx_out (finish: reduce_partials)."""
+    lib = _lib.load()
+    rows, D = x.numel() // x.shape[-1], x.shape[-1]
+    dy16 = dy.data_ptr() if dy.dtype == _BF16 else None
+    dy32 = dy.data_ptr() if dy.dtype == _F32 else None
+    check(lib.vitae_layernorm_param_grads(dy16, dy32, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr(dx_out),
+                                          partials.data_ptr(), rows, D, _stream()), "vitae_layernorm_param_grads")
 
 
 def colsum(inp, rows: int, cols: int, out, workspace, accumulate: bool = False, ld: Optional[int] = None) -> None:

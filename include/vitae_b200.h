@@ -207,13 +207,15 @@ int vitae_adamw_step(float* param, const float* grad, float* exp_avg, float* exp
  * vitae_adamw_flat: AdamW over [0, n) (n % 64 == 0); group_of_chunk[i >> 6] = parameter group of element i
  * (>= ngroups: frozen / padding, left untouched); hyper: HOST fp32 [ngroups][8] = {lr, beta1, beta2, eps,
  * weight_decay, 0, 0, 0}, copied into the launch parameters during the call (ngroups <= 8); bias corrections use ctl[5]; the step is skipped when ctl[2] != 0; also writes the bf16
- * shadow param_bf16 (GEMM operands) when non-NULL. */
+ * shadow param_bf16 (GEMM operands) when non-NULL.  All pointers may be offset to a 64-aligned sub-range of the flat
+ * buffers (group_of_chunk offset by start/64): the step can be issued layer group by layer group.  max_blocks > 0 caps the
+ * grid (a step that overlaps the next forward must leave SM slots to it); 0 = default. */
 int vitae_optim_prepare(const float* grad, long long n, float* ctl, float* workspace, float growth_factor,
                         float backoff_factor, int growth_interval, int use_scaler, void* stream);
 size_t vitae_optim_workspace_bytes(void);
 int vitae_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16,
                      long long n, const unsigned char* group_of_chunk, const float* hyper, int ngroups,
-                     const float* ctl, void* stream);
+                     const float* ctl, int max_blocks, void* stream);
 
 #ifdef __cplusplus
 }

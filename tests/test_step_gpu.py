@@ -174,13 +174,14 @@ def test_many_input_addresses_fall_back_to_a_static_copy():
 
 
 # ------------------------------------------------------------------------------------------------ training steps
-def _train(cfg, P, xs, noises, fused, graphs, steps, lr=1e-3):
+def _train(cfg, P, xs, noises, fused, graphs, steps, lr=1e-3, overlap=False):
     from vit_ae_plus_plus_b200.utils import misc
     m = build(cfg, P)
     m.use_cuda_graph = graphs
     opt = torch.optim.AdamW(misc.add_weight_decay(m, 0.05), lr=lr, betas=(0.9, 0.95))
     scaler = misc.NativeScalerWithGradNormCount()
     scaler.allow_fused = fused
+    scaler.overlap_optimizer = overlap
     curve, norms = [], []
     for i in range(steps):
         losses, _, _ = m(xs[i % len(xs)], mask_ratio=0.75, noise=noises[i])
@@ -290,3 +291,25 @@ def test_device_prefetcher_delivers_batches_in_order_through_rotating_buffers():
     got = torch.cat(sums).cpu().tolist()
     assert all(abs(x - y) < 1e-9 * (1 + abs(y)) for x, y in zip(got, ref))
     assert list(misc.DevicePrefetcher([], "cuda")) == []
+
+
+@pytest.mark.parametrize("graphs", [True, False])
+def test_overlapped_optimizer_step_is_bit_identical(graphs):
+    """overlap_optimizer: AdamW runs per layer group on its own stream and the next forward waits group by group
+    (external events inside the captured forward).  Same kernels, same order per element -> identical bits; a missing
+    wait shows up as a forward that read a half-updated layer."""
+    cfg = O.CONFIGS["small"] if "small" in O.CONFIGS else O.CONFIGS["tiny"]
+    P = O.init_params(cfg, 21)
+    g = torch.Generator().manual_seed(22)
+    V, C = cfg["volume_size"], cfg["in_chans"]
+    L = (V // cfg["patch_size"]) ** 3
+    xs = [torch.randn(2, C, V, V, V, generator=g).cuda() for _ in range(2)]
+    noises = [torch.rand(2, L, generator=g) for _ in range(8)]
+    m_a, _, _, curve_a, norm_a = _train(cfg, P, xs, noises, fused=True, graphs=graphs, steps=8, overlap=False)
+    m_b, _, _, curve_b, norm_b = _train(cfg, P, xs, noises, fused=True, graphs=graphs, steps=8, overlap=True)
+    assert torch.equal(curve_a, curve_b) and torch.equal(norm_a, norm_b)
+    sd_a, sd_b = m_a.state_dict(), m_b.state_dict()
+    for k in sd_a:
+        assert torch.equal(sd_a[k], sd_b[k]), k
+    eng = m_b.engine()
+    assert len(eng.group_ranges) >= 3 and not eng.params_in_flight     # state_dict() waited for the optimizer stream

@@ -44,8 +44,9 @@ def main():
         scaler(losses[0], opt, parameters=model.parameters(), update_grad=True)
         opt.zero_grad()
 
-    for side in (True, False):
+    for side, overlap in ((True, True), (True, False), (False, False)):
         eng.use_side_lane = side
+        scaler.overlap_optimizer = overlap
         for pl in eng.plans.values():
             pl.graphs.clear()
         for _ in range(4):
@@ -59,7 +60,8 @@ def main():
         t_bwd = timed(lambda: eng.backward(pl, one, accumulate=False))
         fo = eng.fused_optimizer()
         t_opt = timed(lambda: fo.step(opt, scaler._scaler))
-        print(f"side_lane={side}: step {t_step:.3f} ms | forward {t_fwd:.3f} | backward {t_bwd:.3f} | optimizer {t_opt:.3f} "
+        eng.wait_params()
+        print(f"side_lane={side} overlap_opt={overlap}: step {t_step:.3f} ms | forward {t_fwd:.3f} | backward {t_bwd:.3f} | optimizer {t_opt:.3f} "
               f"| sum {t_fwd + t_bwd + t_opt:.3f}", flush=True)
 
 

@@ -524,10 +524,11 @@ extern "C" int vitae_optim_prepare(const float* grad, long long n, float* ctl, f
 
 extern "C" int vitae_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16,
                                 long long n, const unsigned char* group_of_chunk, const float* hyper, int ngroups,
-                                const float* ctl, void* stream) {
+                                const float* ctl, int max_blocks, void* stream) {
     VITAE_REQUIRE(param && grad && exp_avg && exp_avg_sq && group_of_chunk && hyper && ctl, "adamw_flat: null pointer");
     VITAE_REQUIRE(n > 0 && n % 64 == 0 && ngroups > 0 && ngroups <= 8, "adamw_flat: n=%lld must be a multiple of 64, 1..8 groups", n);
-    const int blocks = static_cast<int>(std::min<long long>(ceil_div<long long>(n, 1024), 148 * 8));
+    const int cap = max_blocks > 0 ? max_blocks : 148 * 8;
+    const int blocks = static_cast<int>(std::min<long long>(ceil_div<long long>(n, 1024), cap));
     AdamHyper hy;
     memset(&hy, 0, sizeof(hy));
     memcpy(hy.h, hyper, sizeof(float) * 8 * ngroups);   // host pointer, read during this call

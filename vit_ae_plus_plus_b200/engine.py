@@ -340,10 +340,67 @@ class MAEEngine:
         self.use_side_lane = True
         self.graph_replayed_launches = 0   # kernels executed through graph replays (vitae_launch_count sees enqueues)
         self.optim: Optional["FusedAdamW"] = None
+        # Parameter groups in FORWARD order (contiguous slices of the flat buffers, which are laid out in backward order):
+        # the optimizer can update them one after the other on its own stream while the next forward, which waits for
+        # group g right before its first kernel that reads it, is already running (FusedAdamW.step(overlap=True)).
+        # The events are "external": inside a captured forward they become event-wait nodes on the latest record.
+        self.group_of_param, self.group_ranges = self._make_param_groups()
+        self.param_ready = [torch.cuda.Event(external=True) for _ in self.group_ranges]
+        self.opt_stream = torch.cuda.Stream(device=dev, priority=0)
+        self.params_in_flight = False      # an overlapped optimizer step may still be writing the parameters
+        self._waited = set()               # groups the pass being enqueued has already waited for
         self.grad_buckets = None
         self.bucket_elems = 32 << 20       # 128 MB of fp32 gradients per all-reduce bucket
 
     # ------------------------------------------------------------------------------------------------ helpers
+    def _make_param_groups(self):
+        """name -> group id, and per group the [start, end) element range of the flat buffers (64-aligned)."""
+        eb = max(1, math.ceil(self.enc.depth / 4))
+        db = max(1, math.ceil(self.dec.depth / 2))
+        n_enc = math.ceil(self.enc.depth / eb) if self.enc.depth else 0
+        n_dec = math.ceil(self.dec.depth / db) if self.dec.depth else 0
+
+        def gid(name: str) -> int:
+            if name.startswith("patch_embed.") or name == "cls_token":
+                return 0
+            if name.startswith("blocks."):
+                return 1 + int(name.split(".")[1]) // eb
+            if name in ("norm.weight", "norm.bias", "decoder_embed.weight", "decoder_embed.bias", "mask_token"):
+                return 1 + n_enc
+            if name.startswith("decoder_blocks."):
+                return 2 + n_enc + int(name.split(".")[1]) // db
+            return 2 + n_enc + n_dec          # decoder_norm, decoder_pred
+        group_of = {n: gid(n) for n in self.flat.order}
+        ngroups = 3 + n_enc + n_dec
+        ranges = [[None, None] for _ in range(ngroups)]
+        names = self.flat.order
+        for i, n in enumerate(names):
+            o, k, _ = self.flat.offsets[n]
+            end = self.flat.offsets[names[i + 1]][0] if i + 1 < len(names) else self.flat.total
+            r = ranges[group_of[n]]
+            r[0] = o if r[0] is None else min(r[0], o)
+            r[1] = end if r[1] is None else max(r[1], end)
+        spans = sorted((r[0], r[1]) for r in ranges)
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:])) and spans[0][0] == 0 and spans[-1][1] == self.flat.total, \
+            "parameter groups must tile the flat buffer"
+        return group_of, [tuple(r) for r in ranges]
+
+    def _need(self, name: str) -> None:
+        """Orders the current stream after the optimizer's update of the group that holds parameter ``name`` (once per
+        group and pass: an event-wait node in front of a kernel costs that kernel its programmatic launch edge)."""
+        g = self.group_of_param[name]
+        if g not in self._waited:
+            self._waited.add(g)
+            torch.cuda.current_stream().wait_event(self.param_ready[g])
+
+    def wait_params(self) -> None:
+        """Current stream waits for every parameter group (call before non-engine work touches parameters, gradients or
+        optimizer state after an overlapped optimizer step)."""
+        if self.params_in_flight:
+            for ev in self.param_ready:
+                torch.cuda.current_stream().wait_event(ev)
+            self.params_in_flight = False
+
     def plan(self, B: int, keep: int) -> MAEPlan:
         key = (B, keep)
         pl = self.plans.get(key)
@@ -419,7 +476,7 @@ class MAEEngine:
         pl.noise.copy_(noise)
         if pred_f32 and pl.pred32 is None:
             pl.pred32 = torch.empty((pl.B, pl.Nd, self.P), dtype=_F32, device=self.device)
-        self.flat.refresh_shadow()
+        self.refresh_shadow()
 
         def body():
             self.encode(pl, vol, pl.noise)
@@ -427,21 +484,31 @@ class MAEEngine:
             if want_loss:
                 ops.masked_mse_fwd(pl.pred, vol, pl.mask, pl.patch_sums, pl.loss_out, self.p)
         self._run(pl, ("fwd", vol.data_ptr(), pred_f32, want_loss), body)
+        self.params_in_flight = False      # the pass above waited for every parameter group
         return pl
+
+    def refresh_shadow(self) -> None:
+        """bf16 shadow of the parameters; a cast pass (parameters written through torch) reads all of them."""
+        if self.flat.shadow_version != self.flat._version():
+            self.wait_params()
+        self.flat.refresh_shadow()
 
     def encode(self, pl: MAEPlan, vol: torch.Tensor, noise: torch.Tensor) -> None:
         """model/vit_autoenc.py:157-177 (forward_encoder): patch embed of the kept patches only (the dropped ones are
         discarded by the gather at :147, so embedding them is dead work) + pos, cls row, blocks, final norm."""
         B, keep, D = pl.B, pl.keep, self.enc.dim
+        self._waited = set()
         ops.random_masking(noise, pl.ids_shuffle, pl.ids_restore, pl.mask, keep)
         ops.build_row_maps(pl.ids_shuffle, keep, pl.maps)
         ops.im2col_patches(vol, pl.ids_shuffle, pl.cols, self.p, keep)
         x0 = pl.enc.x[0]
+        self._need("patch_embed.proj.weight")
         ops.gemm(pl.cols, self._w("patch_embed.proj.weight"), B * keep, D, self.Kpe,
                  bias=self._p("patch_embed.proj.bias"), addend=self.pos, add_rows=pl.maps["pe_pos_rows"], ldadd=D,
                  out_f32=x0, out_rows=pl.maps["enc_tok_rows"], workspace=self.ws_main)
         ops.fill_rows(x0, pl.maps["enc_cls_rows"], B, D, self._p("cls_token"), None, self.pos, None)
         self._stack_fwd(self.enc, pl.enc, pl.Me, B, pl.Ne)
+        self._need("norm.weight")
         ops.layernorm_fwd(pl.enc.x[-1], self._p("norm.weight"), self._p("norm.bias"), pl.latent, pl.mean_n, pl.rstd_n,
                           self.eps)
 
@@ -451,6 +518,8 @@ class MAEEngine:
             pl.pred32 = torch.empty((pl.B, pl.Nd, self.P), dtype=_F32, device=self.device)
         B, D, Dd = pl.B, self.enc.dim, self.dec.dim
         xd0 = pl.dec.x[0]
+        self._waited.discard(self.group_of_param["decoder_embed.weight"])   # decode() may be called on its own
+        self._need("decoder_embed.weight")
         ops.gemm(pl.latent, self._w("decoder_embed.weight"), pl.Me, Dd, D, bias=self._p("decoder_embed.bias"),
                  addend=self.dpos, add_rows=pl.maps["dec_pos_rows_of_enc"], ldadd=Dd, out_f32=xd0,
                  out_rows=pl.maps["dec_rows_of_enc"], workspace=self.ws_main)
@@ -458,6 +527,7 @@ class MAEEngine:
             ops.fill_rows(xd0, pl.maps["masked_dec_rows"], B * pl.nmask, Dd, self._p("mask_token"), None, self.dpos,
                           pl.maps["masked_pos_rows"])
         self._stack_fwd(self.dec, pl.dec, pl.Md, B, pl.Nd)
+        self._need("decoder_norm.weight")
         ops.layernorm_fwd(pl.dec.x[-1], self._p("decoder_norm.weight"), self._p("decoder_norm.bias"), pl.hN,
                           pl.mean_dn, pl.rstd_dn, self.eps)
         ops.gemm(pl.hN, self._w("decoder_pred.weight"), pl.Md, self.P, Dd, bias=self._p("decoder_pred.bias"),
@@ -472,6 +542,7 @@ class MAEEngine:
         for i in range(st.depth):
             pre = f"{st.prefix}.{i}"
             b, x_in, x_out = sb.blocks[i], sb.x[i], sb.x[i + 1]
+            self._need(f"{pre}.norm1.weight")
             ops.layernorm_fwd(x_in, self._p(f"{pre}.norm1.weight"), self._p(f"{pre}.norm1.bias"), b.ln1, b.mean1,
                               b.rstd1, self.eps)
             ops.gemm(b.ln1, self._w(f"{pre}.attn.qkv.weight"), M, 3 * D, D, bias=self._p(f"{pre}.attn.qkv.bias"),
@@ -727,25 +798,45 @@ class FusedAdamW:
         self.bound, self.bound_sig = id(optimizer), sig
         return True
 
-    def step(self, optimizer, scaler=None) -> torch.Tensor:
+    def step(self, optimizer, scaler=None, overlap: bool = False) -> torch.Tensor:
         """One optimizer step on the gradients currently in the flat gradient buffer; returns the (unscaled) global
         gradient norm as a 0-dim device tensor.  ``scaler``: a torch.amp.GradScaler-like object whose scale lives in
-        ``ctl[0]`` (see utils/misc.py::NativeScalerWithGradNormCount) or None."""
+        ``ctl[0]`` (see utils/misc.py::NativeScalerWithGradNormCount) or None.
+
+        ``overlap``: the AdamW pass (HBM-bound: 30 bytes per parameter) is issued per parameter group, in forward order,
+        on the engine's optimizer stream; the next ``forward`` waits for each group right before its first use, so the
+        update of the later layers hides behind the forward of the earlier ones.  Until that forward (or
+        ``engine.wait_params()``) the caller's stream is NOT ordered after the update."""
         eng, flat = self.eng, self.eng.flat
         use_scaler = scaler is not None
         gf, bf, gi = (scaler.get_growth_factor(), scaler.get_backoff_factor(), scaler.get_growth_interval()) \
             if use_scaler else (2.0, 0.5, 2000)
+        eng.wait_params()
         ops.optim_prepare(flat.g32, flat.total, self.ctl, self.ws, gf, bf, gi, use_scaler)
         rows = [(g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"]) for g in optimizer.param_groups]
-        ops.adamw_flat(flat.p32, flat.g32, self.m, self.v, flat.p16, flat.total, self.group_map, rows, self.ctl)
+        norm = self.ctl[4].clone()
+        if overlap:
+            main = torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            eng.opt_stream.wait_event(ev)
+            with torch.cuda.stream(eng.opt_stream):
+                for g, (a, b) in enumerate(eng.group_ranges):          # forward order
+                    ops.adamw_flat(flat.p32, flat.g32, self.m, self.v, flat.p16, b - a, self.group_map, rows, self.ctl,
+                                   start=a, max_blocks=148 * 2)
+                    eng.param_ready[g].record(eng.opt_stream)
+            eng.params_in_flight = True
+        else:
+            ops.adamw_flat(flat.p32, flat.g32, self.m, self.v, flat.p16, flat.total, self.group_map, rows, self.ctl)
         flat.stamp_shadow()
         flat.overwrite_grads = True      # these gradients are consumed: the next backward starts from zero
         self.host_steps += 1
-        return self.ctl[4].clone()
+        return norm
 
     def sync_state(self, optimizer) -> None:
         """Writes the device-side step count (skipped steps excluded) into the optimizer's per-parameter state (one
         device read): call before ``optimizer.state_dict()`` / switching to ``optimizer.step()``."""
+        self.eng.wait_params()
         steps = float(self.ctl[5].item())
         self.host_steps = int(steps)
         for group in optimizer.param_groups:

@@ -264,6 +264,11 @@ class MaskedAutoencoderViT(nn.Module):
         if self.require_backward_grad_sync:
             eng.allreduce_gradients()
 
+    def state_dict(self, *args, **kwargs):
+        if self._engine is not None:
+            self._engine.wait_params()       # an overlapped optimizer step may still be writing the parameters
+        return super().state_dict(*args, **kwargs)
+
     # ------------------------------------------------------------------------------------------------ reference API
     def patchify(self, volume):
         """model/vit_autoenc.py:100-113: (N, C, V, V, V) -> (N, L, p^3*C), within-patch order (pz, py, px, c).
@@ -307,7 +312,7 @@ class MaskedAutoencoderViT(nn.Module):
         eng = self.engine()
         x = self._check_volume(x)
         pl = eng.plan(x.shape[0], self._len_keep(mask_ratio))
-        eng.flat.refresh_shadow()
+        eng.refresh_shadow()
         eng.encode(pl, x, self._noise(x, noise))
         latent = pl.latent.float().view(x.shape[0], pl.Ne, self.embed_dim)
         return latent, pl.mask.clone(), pl.ids_restore.long()
@@ -318,7 +323,7 @@ class MaskedAutoencoderViT(nn.Module):
         eng = self.engine()
         B, Ne = x.shape[0], x.shape[1]
         pl = eng.plan(B, Ne - 1)
-        eng.flat.refresh_shadow()
+        eng.refresh_shadow()
         pl.latent.copy_(x.reshape(B * Ne, -1))
         pl.ids_shuffle.copy_(torch.argsort(ids_restore, dim=1))
         ops.build_row_maps(pl.ids_shuffle, Ne - 1, pl.maps)

@@ -343,14 +343,19 @@ def optim_prepare(grad, n: int, ctl, workspace, growth_factor: float, backoff_fa
                                   growth_interval, int(use_scaler), _stream()), "vitae_optim_prepare")
 
 
-def adamw_flat(param, grad, exp_avg, exp_avg_sq, param_bf16, n: int, group_of_chunk, hyper_rows, ctl) -> None:
-    """hyper_rows: python list of (lr, beta1, beta2, eps, weight_decay) per parameter group (passed by value)."""
+def adamw_flat(param, grad, exp_avg, exp_avg_sq, param_bf16, n: int, group_of_chunk, hyper_rows, ctl, start: int = 0,
+               max_blocks: int = 0) -> None:
+    """AdamW over elements [start, start + n) of the flat buffers (start, n multiples of 64).  hyper_rows: python list of
+    (lr, beta1, beta2, eps, weight_decay) per parameter group (passed by value)."""
     lib = _lib.load()
     ng = len(hyper_rows)
     host = (ctypes.c_float * (8 * ng))()
     for i, row in enumerate(hyper_rows):
         for j, val in enumerate(row):
             host[8 * i + j] = float(val)
-    check(lib.vitae_adamw_flat(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
-                               _ptr(param_bf16), n, group_of_chunk.data_ptr(), ctypes.cast(host, ctypes.c_void_p), ng,
-                               ctl.data_ptr(), _stream()), "vitae_adamw_flat")
+    assert start % 64 == 0 and n % 64 == 0
+    p16 = None if param_bf16 is None else param_bf16.data_ptr() + 2 * start
+    check(lib.vitae_adamw_flat(param.data_ptr() + 4 * start, grad.data_ptr() + 4 * start, exp_avg.data_ptr() + 4 * start,
+                               exp_avg_sq.data_ptr() + 4 * start, p16, n, group_of_chunk.data_ptr() + start // 64,
+                               ctypes.cast(host, ctypes.c_void_p), ng, ctl.data_ptr(), max_blocks, _stream()),
+          "vitae_adamw_flat")

@@ -96,7 +96,6 @@ def train_one_stage_epoch(model: torch.nn.Module, data_loader: Iterable, optimiz
     optimizer.zero_grad()
     if log_writer is not None:
         print("log_dir: {}".format(log_writer.log_dir))
-
     batches = misc.DevicePrefetcher(data_loader, device) if torch.device(device).type == "cuda" else data_loader
     for step, (sample, original_volume, _) in enumerate(
             metric_logger.log_every(batches, PRINT_FREQ, header, before_print=deferred.flush)):
@@ -125,6 +124,9 @@ def train_one_stage_epoch(model: torch.nn.Module, data_loader: Iterable, optimiz
         if update:
             optimizer.zero_grad()
 
+    eng = getattr(model, "_engine", None)
+    if eng is not None:
+        eng.wait_params()
     deferred.flush()
     metric_logger.synchronize_between_processes()
     print("Averaged stats:", metric_logger)

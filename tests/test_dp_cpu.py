@@ -39,6 +39,13 @@ def _worker(rank, world, port, q):
         g[5] = 10.0 * (rank + 1)
         dp.allreduce_mean_bucketed_(g, slices)
         out["g0"], out["g5"] = g[0].item(), g[5].item()
+        # asynchronous per-stage reducer (engine.backward(sync_grads=True)): slices in flight together, then one wait
+        g2 = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+        red = dp.GradReducer()
+        for a, b in [(0, 128), (128, 640), (640, 1000)]:
+            red.launch(g2[a:b])
+        red.wait()
+        out["g2_ok"] = bool(torch.equal(g2, torch.arange(1000, dtype=torch.float32) * 1.5)) and red.pending == []
         out["all_reduce_mean"] = misc.all_reduce_mean(float(rank))
         sv = misc.SmoothedValue()
         sv.update(1.0 + rank, n=2)
@@ -82,6 +89,7 @@ def test_world_size_2_gloo():
     assert res[0]["slices"][-1][1] == 1000
     for r in (0, 1):
         assert res[r]["g0"] == 1.5 and res[r]["g5"] == 15.0         # mean over ranks
+        assert res[r]["g2_ok"]
         assert res[r]["all_reduce_mean"] == 0.5
         assert res[r]["sv"] == (4, 6.0)
         assert res[r]["local_loss"] == 1.0 + r                      # meters stay rank-local (reference misc.py:95)

@@ -55,3 +55,29 @@ def allreduce_mean_(t: torch.Tensor, async_op: bool = False):
 def allreduce_mean_bucketed_(flat: torch.Tensor, slices: Sequence[Tuple[int, int]]) -> None:
     for a, b in slices:
         allreduce_mean_(flat[a:b])
+
+
+class GradReducer:
+    """Mean all-reduce of gradient slices, issued asynchronously: with NCCL a slice's collective runs on the process
+    group's own stream (ordered after everything enqueued on the current stream so far) while the caller keeps enqueueing
+    the next backward stage; ``wait()`` orders the current stream after all of them (no host block with NCCL)."""
+
+    def __init__(self):
+        self.pending = []
+
+    def launch(self, t: torch.Tensor) -> None:
+        w = world_size()
+        if w == 1 or t.numel() == 0:
+            return
+        if dist.get_backend() == "nccl":
+            self.pending.append((dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=True), None))
+        else:   # gloo: no AVG
+            self.pending.append((dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True), t))
+
+    def wait(self) -> None:
+        w = world_size()
+        for work, t in self.pending:
+            work.wait()
+            if t is not None:
+                t.div_(w)
+        self.pending = []

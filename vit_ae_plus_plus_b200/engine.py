@@ -559,74 +559,125 @@ class MAEEngine:
 
     # ------------------------------------------------------------------------------------------------ backward
     def backward(self, pl: MAEPlan, dloss: Optional[torch.Tensor], dpred_extra: Optional[torch.Tensor] = None,
-                 accumulate: bool = False) -> None:
+                 accumulate: bool = False, sync_grads: bool = False) -> None:
         """Gradient of (dloss * recon_loss [+ <dpred_extra, pred>]) w.r.t. every trainable parameter, written to
-        (accumulate=False) or added into (True) the flat gradient buffer.  Hand-derived reverse of forward()."""
+        (accumulate=False) or added into (True) the flat gradient buffer.  Hand-derived reverse of forward().
+
+        ``sync_grads`` (data parallel, world size > 1): the backward runs as a few stages (one CUDA graph each) whose
+        gradients are contiguous slices of the flat buffer; the mean all-reduce of a stage's slice is issued as soon as
+        that stage has been enqueued and overlaps the later stages (NCCL runs on its own stream)."""
         if dloss is None:
             pl.dloss.zero_()
         else:
             pl.dloss.copy_(dloss.reshape(1))
-        if dpred_extra is not None:   # auxiliary torch-side terms that consume ``pred`` (edge-map loss): not graphed
-            self._backward_impl(pl, dpred_extra, accumulate)
-        else:
-            self._run(pl, ("bwd", pl.vol.data_ptr(), bool(accumulate)), lambda: self._backward_impl(pl, None, accumulate))
+        staged = sync_grads and dp.world_size() > 1
+        stages = self._backward_stages(pl, dpred_extra, accumulate, split=staged)
+        reducer = dp.GradReducer() if staged else None
+        for i, (fn, (a, b)) in enumerate(stages):
+            if dpred_extra is not None and i == 0:   # auxiliary torch-side terms that consume ``pred``: not graphed
+                fn()
+            else:
+                self._run(pl, ("bwd", i, len(stages), pl.vol.data_ptr(), bool(accumulate)), fn)
+            if reducer is not None:
+                reducer.launch(self.flat.g32[a:b])
+        if reducer is not None:
+            reducer.wait()
 
-    def _backward_impl(self, pl: MAEPlan, dpred_extra: Optional[torch.Tensor], acc: bool) -> None:
+    def _backward_stages(self, pl: MAEPlan, dpred_extra: Optional[torch.Tensor], acc: bool, split: bool):
+        """[(enqueue function, (start, end) slice of the flat gradient buffer it completes)], in execution order.
+        split=False: one stage.  The stages share ``state['cur']`` (which of the two residual-gradient buffers is live)."""
         B, D, Dd, P = pl.B, self.enc.dim, self.dec.dim, self.P
         cws, wsm, wss = pl.colsum_ws, self.ws_main, self.ws_side
         lanes = self.lanes
-        # ---- loss: d recon / d pred (model/vit_autoenc.py:226-227), zeros for kept patches and the cls row
-        lanes.before_write("dpred")
-        ops.masked_mse_bwd(pl.pred, pl.vol, pl.mask, pl.loss_out[1:], pl.dloss, pl.dpred, self.p)
-        if dpred_extra is not None:
-            pl.dpred[:, 1:, :].add_(dpred_extra.to(_BF16))
-        dpred = pl.dpred.view(pl.Md, P)
-        # ---- decoder_pred (vit_autoenc.py:198)
+        state = {"cur": 0}
+        enc_split = self.enc.depth // 2
+        enc_hi = list(reversed(range(enc_split, self.enc.depth)))
+        enc_lo = list(reversed(range(0, enc_split)))
+        dec_all = list(reversed(range(self.dec.depth)))
 
-        def side_pred():
-            ops.gemm(dpred, pl.hN, P, Dd, pl.Md, a_mn_major=True, b_mn_major=True,
-                     out_f32=self._g("decoder_pred.weight"), accumulate=acc, workspace=wss)
-            ops.colsum(dpred, pl.Md, P, self._g("decoder_pred.bias"), cws, accumulate=acc)
-        self._side(side_pred, reads=("dpred",))
-        d_d = self._ln_in(pl, pl.Md, Dd)
-        ops.gemm(dpred, self._w("decoder_pred.weight"), pl.Md, Dd, P, b_mn_major=True, out_bf16=d_d, workspace=wsm)
-        last_dec = f"decoder_blocks.{self.dec.depth - 1}.mlp.fc2.bias" if self.dec.depth else None
-        cur = self._ln_bwd(pl, d_d, pl.dec.x[-1], "decoder_norm", pl.mean_dn, pl.rstd_dn, None, 0, pl.Md, Dd, acc,
-                           last_dec)
-        cur = self._stack_bwd(self.dec, pl.dec, pl, pl.Md, B, pl.Nd, cur, acc)
-        dxd = pl.dres[cur][:pl.Md * Dd].view(pl.Md, Dd)
-        # ---- mask tokens, decoder_embed (vit_autoenc.py:181-190)
-        lanes.before_write("g_embed")
-        ops.gather_rows(dxd, pl.maps["dec_rows_of_enc"], pl.Me, Dd, pl.g_embed, None)
+        def stage_pred():
+            # ---- loss: d recon / d pred (model/vit_autoenc.py:226-227), zeros for kept patches and the cls row
+            lanes.before_write("dpred")
+            ops.masked_mse_bwd(pl.pred, pl.vol, pl.mask, pl.loss_out[1:], pl.dloss, pl.dpred, self.p)
+            if dpred_extra is not None:
+                pl.dpred[:, 1:, :].add_(dpred_extra.to(_BF16))
+            dpred = pl.dpred.view(pl.Md, P)
+            # ---- decoder_pred (vit_autoenc.py:198)
 
-        def side_embed():
-            if pl.nmask > 0:
-                ops.sum_rows(dxd, pl.maps["masked_dec_rows"], B * pl.nmask, Dd, self._g("mask_token").view(-1), acc)
-            elif not acc:
-                self._g("mask_token").zero_()
-            ops.gemm(pl.g_embed, pl.latent, Dd, D, pl.Me, a_mn_major=True, b_mn_major=True,
-                     out_f32=self._g("decoder_embed.weight"), accumulate=acc, workspace=wss)
-            ops.colsum(pl.g_embed, pl.Me, Dd, self._g("decoder_embed.bias"), cws, accumulate=acc)
-        self._side(side_embed, reads=("g_embed", ("dres", cur)))
-        d_e = self._ln_in(pl, pl.Me, D)
-        ops.gemm(pl.g_embed, self._w("decoder_embed.weight"), pl.Me, D, Dd, b_mn_major=True, out_bf16=d_e,
-                 workspace=wsm)
-        # ---- encoder norm + blocks (vit_autoenc.py:172-175)
-        last_enc = f"blocks.{self.enc.depth - 1}.mlp.fc2.bias" if self.enc.depth else None
-        cur = self._ln_bwd(pl, d_e, pl.enc.x[-1], "norm", pl.mean_n, pl.rstd_n, None, 0, pl.Me, D, acc, last_enc)
-        cur = self._stack_bwd(self.enc, pl.enc, pl, pl.Me, B, pl.Ne, cur, acc)
-        dx0 = pl.dres[cur][:pl.Me * D].view(pl.Me, D)
-        # ---- cls token, patch embed (vit_autoenc.py:160-170); no input gradient for the volume
-        lanes.before_write("g_pe")
-        ops.gather_rows(dx0, pl.maps["enc_tok_rows"], B * pl.keep, D, pl.g_pe, None)
-        ops.sum_rows(dx0, pl.maps["enc_cls_rows"], B, D, self._g("cls_token").view(-1), acc)
-        ops.gemm(pl.g_pe, pl.cols, D, self.Kpe, B * pl.keep, a_mn_major=True, b_mn_major=True,
-                 out_f32=self._g("patch_embed.proj.weight").view(D, self.Kpe), accumulate=acc, workspace=wsm)
+            def side_pred():
+                ops.gemm(dpred, pl.hN, P, Dd, pl.Md, a_mn_major=True, b_mn_major=True,
+                         out_f32=self._g("decoder_pred.weight"), accumulate=acc, workspace=wss)
+                ops.colsum(dpred, pl.Md, P, self._g("decoder_pred.bias"), cws, accumulate=acc)
+            self._side(side_pred, reads=("dpred",))
+            d_d = self._ln_in(pl, pl.Md, Dd)
+            ops.gemm(dpred, self._w("decoder_pred.weight"), pl.Md, Dd, P, b_mn_major=True, out_bf16=d_d, workspace=wsm)
+            last_dec = f"decoder_blocks.{self.dec.depth - 1}.mlp.fc2.bias" if self.dec.depth else None
+            state["cur"] = self._ln_bwd(pl, d_d, pl.dec.x[-1], "decoder_norm", pl.mean_dn, pl.rstd_dn, None, 0, pl.Md, Dd,
+                                        acc, last_dec)
 
-        def side_pe():
-            ops.colsum(pl.g_pe, B * pl.keep, D, self._g("patch_embed.proj.bias"), cws, accumulate=acc)
-        self._side(side_pe, reads=("g_pe",))
-        lanes.join()
+        def stage_dec():
+            state["cur"] = self._stack_bwd(self.dec, pl.dec, pl, pl.Md, B, pl.Nd, state["cur"], acc, dec_all)
+
+        def stage_mid():
+            cur = state["cur"]
+            dxd = pl.dres[cur][:pl.Md * Dd].view(pl.Md, Dd)
+            # ---- mask tokens, decoder_embed (vit_autoenc.py:181-190)
+            lanes.before_write("g_embed")
+            ops.gather_rows(dxd, pl.maps["dec_rows_of_enc"], pl.Me, Dd, pl.g_embed, None)
+
+            def side_embed():
+                if pl.nmask > 0:
+                    ops.sum_rows(dxd, pl.maps["masked_dec_rows"], B * pl.nmask, Dd, self._g("mask_token").view(-1), acc)
+                elif not acc:
+                    self._g("mask_token").zero_()
+                ops.gemm(pl.g_embed, pl.latent, Dd, D, pl.Me, a_mn_major=True, b_mn_major=True,
+                         out_f32=self._g("decoder_embed.weight"), accumulate=acc, workspace=wss)
+                ops.colsum(pl.g_embed, pl.Me, Dd, self._g("decoder_embed.bias"), cws, accumulate=acc)
+            self._side(side_embed, reads=("g_embed", ("dres", cur)))
+            d_e = self._ln_in(pl, pl.Me, D)
+            ops.gemm(pl.g_embed, self._w("decoder_embed.weight"), pl.Me, D, Dd, b_mn_major=True, out_bf16=d_e,
+                     workspace=wsm)
+            # ---- encoder norm + the upper half of the blocks (vit_autoenc.py:172-175)
+            last_enc = f"blocks.{self.enc.depth - 1}.mlp.fc2.bias" if self.enc.depth else None
+            cur = self._ln_bwd(pl, d_e, pl.enc.x[-1], "norm", pl.mean_n, pl.rstd_n, None, 0, pl.Me, D, acc, last_enc)
+            state["cur"] = self._stack_bwd(self.enc, pl.enc, pl, pl.Me, B, pl.Ne, cur, acc, enc_hi)
+
+        def stage_enc_lo():
+            state["cur"] = self._stack_bwd(self.enc, pl.enc, pl, pl.Me, B, pl.Ne, state["cur"], acc, enc_lo)
+
+        def stage_embed():
+            dx0 = pl.dres[state["cur"]][:pl.Me * D].view(pl.Me, D)
+            # ---- cls token, patch embed (vit_autoenc.py:160-170); no input gradient for the volume
+            lanes.before_write("g_pe")
+            ops.gather_rows(dx0, pl.maps["enc_tok_rows"], B * pl.keep, D, pl.g_pe, None)
+            ops.sum_rows(dx0, pl.maps["enc_cls_rows"], B, D, self._g("cls_token").view(-1), acc)
+            ops.gemm(pl.g_pe, pl.cols, D, self.Kpe, B * pl.keep, a_mn_major=True, b_mn_major=True,
+                     out_f32=self._g("patch_embed.proj.weight").view(D, self.Kpe), accumulate=acc, workspace=wsm)
+
+            def side_pe():
+                ops.colsum(pl.g_pe, B * pl.keep, D, self._g("patch_embed.proj.bias"), cws, accumulate=acc)
+            self._side(side_pe, reads=("g_pe",))
+
+        off = lambda n: self.flat.offsets[n][0]
+        parts = [(stage_pred, off("decoder_pred.weight"))]
+        if dec_all:
+            parts.append((stage_dec, off(f"decoder_blocks.{dec_all[0]}.mlp.fc2.weight")))
+        parts.append((stage_mid, off("mask_token")))
+        if enc_lo:
+            parts.append((stage_enc_lo, off(f"blocks.{enc_lo[0]}.mlp.fc2.weight")))
+        parts.append((stage_embed, off("cls_token")))
+
+        def joined(fns):
+            def run():
+                for f in fns:
+                    f()
+                lanes.join()      # a stage is self-contained: its side-lane work is part of it
+            return run
+        if not split:
+            return [(joined([f for f, _ in parts]), (0, self.flat.total))]
+        starts = [o for _, o in parts] + [self.flat.total]
+        assert starts[0] == 0 and all(a < b for a, b in zip(starts, starts[1:])), "stage slices must tile the gradient buffer"
+        return [(joined([f]), (starts[i], starts[i + 1])) for i, (f, _) in enumerate(parts)]
 
     def _ln_in(self, pl: MAEPlan, M: int, D: int) -> torch.Tensor:
         """Buffer for the input gradient (dy) of the NEXT _ln_bwd call; the side lane reads it after the main lane has
@@ -657,7 +708,7 @@ class MAEEngine:
         self._side(side, reads=(("d_ln", k), ("dres", out_idx)))
         return out_idx
 
-    def _stack_bwd(self, st: StackSpec, sb, pl: MAEPlan, M: int, B: int, N: int, cur: int, acc: bool) -> int:
+    def _stack_bwd(self, st: StackSpec, sb, pl: MAEPlan, M: int, B: int, N: int, cur: int, acc: bool, layers) -> int:
         """Reverse of _stack_fwd.  On entry dres[cur] / dres16[cur] hold the gradient w.r.t. the stack output.
         Main lane: dgrad GEMMs, attention backward, LayerNorm backward (the dependency chain).  Side lane: wgrad GEMMs,
         bias column sums, LayerNorm partial reductions."""
@@ -667,7 +718,7 @@ class MAEEngine:
         lanes = self.lanes
         d_d = pl.d_d[:M * D].view(M, D)
         delta = pl.delta[:B * H * N]
-        for i in reversed(range(st.depth)):
+        for i in layers:
             pre = f"{st.prefix}.{i}"
             b, x_in = sb.blocks[i], sb.x[i]
             hb = i & 1
@@ -723,7 +774,8 @@ class MAEEngine:
         dp.broadcast_flat(self.dpos)
 
     def allreduce_gradients(self) -> None:
-        """Mean of the flat gradient buffer over ranks (one exchange step per optimizer step)."""
+        """Mean of the whole flat gradient buffer over ranks in a few large slices (not overlapped; the training step uses
+        backward(sync_grads=True), which overlaps the exchange with the backward stages)."""
         if dp.world_size() > 1:
             if self.grad_buckets is None:
                 offs = [(self.flat.offsets[n][0], self.flat.offsets[n][1]) for n in self.flat.order]

@@ -253,7 +253,9 @@ class MaskedAutoencoderViT(nn.Module):
         acc = state is True and not flat.overwrite_grads
         flat.overwrite_grads = False
         eng.use_graphs = self.use_cuda_graph
-        eng.backward(pl, drecon, dpred_extra=dpred, accumulate=acc)
+        # the gradient exchange overlaps the backward stages, except when foreign gradients still have to be added first
+        sync = self.require_backward_grad_sync
+        eng.backward(pl, drecon, dpred_extra=dpred, accumulate=acc, sync_grads=sync and saved is None)
         if state is not True:
             for n in flat.order:
                 p = flat.params[n]
@@ -261,7 +263,7 @@ class MaskedAutoencoderViT(nn.Module):
                     flat.vg[n].add_(saved[n])
                 if p.requires_grad:
                     p.grad = flat.vg[n]
-        if self.require_backward_grad_sync:
+        if sync and saved is not None:
             eng.allreduce_gradients()
 
     def state_dict(self, *args, **kwargs):

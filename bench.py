@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not use CUDA graphs for the step")
     ap.add_argument("--cpu-sample-steps", type=int, default=4)
+    ap.add_argument("--profile-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -220,11 +222,15 @@ def run_ours(a):
         sampler.start()
     n0 = lib.vitae_launch_count() + getattr(model, "graph_replayed_launches", 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if a.profile_range:
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(a.steps):
         last = step(pool[i % n_pool])
     e1.record()
     barrier()
+    if a.profile_range:
+        torch.cuda.profiler.stop()
     launches = lib.vitae_launch_count() + getattr(model, "graph_replayed_launches", 0) - n0
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)

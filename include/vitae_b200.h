@@ -99,7 +99,8 @@ int vitae_gemm_autotune(const void* A, int lda, int a_mn_major, const void* B, i
  */
 int vitae_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
                         float* mean, float* rstd, int rows, int D, float eps, void* stream);
-/* dx_out = (dx_in ? dx_in : 0) + LN'(dy); dy is bf16 (dy_bf16) or fp32 (dy_f32); also emits a bf16 copy of dx_out
+/* dx_out = (dx_in ? dx_in : 0) + LN'(dy); dy is bf16 (dy_bf16) or fp32 (dy_f32) or, when both are given, their sum (two
+ * consumers of the normalised tensor: decoder + contrastive predictor, model/vit_autoenc.py:272-283); also emits a bf16 copy of dx_out
  * (operand of the next dgrad/wgrad GEMM) when dx_out_bf16 != NULL.  Row-wise only (it is on the dgrad critical path). */
 int vitae_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* gamma,
                         const float* mean, const float* rstd, const float* dx_in, float* dx_out, void* dx_out_bf16,

@@ -320,6 +320,70 @@ def forward_backward(x, P: Params, cfg, mask_ratio: float, noise: torch.Tensor, 
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# Contrastive wrapper -- model/vit_autoenc.py:241-285 (ContrastiveMAEViT, use_proj=False) and the loss of
+# utils/train_one_epoch.py:113-114
+# ----------------------------------------------------------------------------------------------------------------
+BN_EPS = 1e-5  # nn.BatchNorm1d default (vit_autoenc.py:265)
+
+
+def predictor_param_shapes(cfg) -> Dict[str, tuple]:
+    D = cfg["embed_dim"]
+    return {"predictor.0.weight": (D, D), "predictor.1.weight": (D,), "predictor.1.bias": (D,),
+            "predictor.3.weight": (D, D), "predictor.3.bias": (D,)}
+
+
+def init_predictor_params(cfg, seed: int = 0, dtype=torch.float32, perturb: float = 0.02) -> Params:
+    """The predictor is built after super().__init__() and keeps torch's default Linear / BatchNorm init
+    (vit_autoenc.py:263-268); here: the same kaiming-uniform(a=sqrt(5)) range for the weights, perturbed
+    affine / bias so that tests exercise them."""
+    gen = torch.Generator().manual_seed(seed + 7919)
+    out: Params = {}
+    for name, shape in predictor_param_shapes(cfg).items():
+        if len(shape) == 2:
+            bound = 1.0 / math.sqrt(shape[1])
+            t = (torch.rand(shape, generator=gen) * 2 - 1) * bound
+        elif name == "predictor.1.weight":
+            t = 1.0 + perturb * torch.randn(shape, generator=gen)
+        else:
+            t = perturb * torch.randn(shape, generator=gen)
+        out[name] = t.to(dtype)
+    return out
+
+
+def predictor(z, P: Params):
+    """Linear(no bias) -> BatchNorm1d in training mode (batch statistics over the B*Ne token rows, biased variance)
+    -> ReLU -> Linear   (vit_autoenc.py:263-268)."""
+    h = F.linear(z, P["predictor.0.weight"])
+    mu, var = h.mean(0), h.var(0, unbiased=False)
+    h = (h - mu) / torch.sqrt(var + BN_EPS) * P["predictor.1.weight"] + P["predictor.1.bias"]
+    h = F.relu(h)
+    return F.linear(h, P["predictor.3.weight"], P["predictor.3.bias"])
+
+
+def forward_contrastive(x1, x2, P: Params, cfg, mask_ratio: float, noise1: torch.Tensor, noise2: torch.Tensor,
+                        edge_map_weight: float = 0.0, with_edge: bool = False):
+    """vit_autoenc.py:270-285 -> (loss_list, pred, mask, p1, p2, z1.detach(), z2.detach()); the second view is masked
+    with its own noise draw (:277)."""
+    latent1, mask, ids_restore = forward_encoder(x1, P, cfg, mask_ratio, noise1)
+    pred = forward_decoder(latent1, P, cfg, ids_restore)
+    target = patchify(x1, cfg["patch_size"])
+    recon = masked_mse(pred, target, mask)
+    raw_edge = edge_map_mse(pred, target, cfg["patch_size"]) if with_edge else torch.zeros((), dtype=pred.dtype)
+    percep = torch.zeros((), dtype=pred.dtype)
+    latent2, _, _ = forward_encoder(x2, P, cfg, mask_ratio, noise2)
+    z1 = latent1.reshape(-1, latent1.shape[2])
+    z2 = latent2.reshape(-1, latent2.shape[2])
+    return ([edge_map_weight * raw_edge + recon + percep, raw_edge, recon, percep], pred, mask, predictor(z1, P),
+            predictor(z2, P), z1.detach(), z2.detach())
+
+
+def contrastive_loss(p1, p2, z1, z2, contr_weight: float):
+    # utils/train_one_epoch.py:113-114 with criterion = nn.CosineSimilarity(dim=1) (:32)
+    cos = lambda a, b: F.cosine_similarity(a, b, dim=1)
+    return contr_weight * (-(cos(p1, z2).mean() + cos(p2, z1).mean()) * 0.5)
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # Optimizer grouping + AdamW as built at the call site (k_fold_cross_valid_combined_brats.py:168-169)
 # ----------------------------------------------------------------------------------------------------------------
 def weight_decay_groups(named_params, weight_decay: float):

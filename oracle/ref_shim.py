@@ -105,14 +105,14 @@ def reference_args(**over):
     return ns
 
 
-def build_reference_model(cfg: dict):
+def build_reference_model(cfg: dict, contrastive: bool = False):
     """cfg: same keys as oracle.mae_oracle.CONFIGS entries."""
     from functools import partial
     mod = load_reference()
     real = torch.load
     torch.load = mod._vitae_patched_load
     try:
-        m = mod.MaskedAutoencoderViT(
+        m = (mod.ContrastiveMAEViT if contrastive else mod.MaskedAutoencoderViT)(
             volume_size=cfg["volume_size"], patch_size=cfg["patch_size"], in_chans=cfg["in_chans"],
             embed_dim=cfg["embed_dim"], depth=cfg["depth"], num_heads=cfg["num_heads"],
             decoder_embed_dim=cfg["decoder_embed_dim"], decoder_depth=cfg["decoder_depth"],

@@ -67,6 +67,47 @@ def test_adamw_loss_curve_matches_reference(name):
     np.testing.assert_allclose(curve, g["curve"], rtol=2e-4)
 
 
+def _contr_inputs(g):
+    cfg = O.CONFIGS[str(g["config_name"])]
+    pseed, iseed, nseed, batch, stride, _ = [int(v) for v in g["meta"]]
+    V, C = cfg["volume_size"], cfg["in_chans"]
+    gen = torch.Generator().manual_seed(iseed)
+    x1 = torch.randn(batch, C, V, V, V, generator=gen)
+    x2 = x1 + 0.1 * torch.randn(batch, C, V, V, V, generator=gen)
+    _, L, _ = O.geometry(cfg)
+    torch.manual_seed(nseed)
+    noise1, noise2 = torch.rand(batch, L), torch.rand(batch, L)      # view 1 first, then view 2 (vit_autoenc.py:272,277)
+    P = dict(O.init_params(cfg, pseed))
+    P.update(O.init_predictor_params(cfg, pseed))
+    return cfg, P, x1, x2, noise1, noise2, stride
+
+
+def test_contrastive_wrapper_matches_reference():
+    """ContrastiveMAEViT forward (7-tuple) + the loop's contrastive loss + backward of the sum, against the unmodified
+    reference (golden: oracle/make_golden.py::run_reference_contrastive)."""
+    g = np.load(os.path.join(GOLD, "contr_small.npz"))
+    cfg, P, x1, x2, n1, n2, stride = _contr_inputs(g)
+    leaves = {k: v.clone().requires_grad_(k not in O.FROZEN) for k, v in P.items()}
+    losses, pred, mask, p1, p2, z1, z2 = O.forward_contrastive(x1, x2, leaves, cfg, float(g["mask_ratio"]), n1, n2,
+                                                               0.0, with_edge=True)
+    contr = O.contrastive_loss(p1, p2, z1, z2, float(g["contr_weight"]))
+    (losses[0] + contr).backward()
+    np.testing.assert_allclose([float(l) for l in losses], g["losses"], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(float(contr), float(g["contr"]), rtol=1e-4)
+    np.testing.assert_array_equal(mask.numpy(), g["mask"])
+    np.testing.assert_allclose(p1.detach().reshape(-1)[::stride].numpy(), g["p1_sample"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(p2.detach().reshape(-1)[::stride].numpy(), g["p2_sample"], rtol=1e-3, atol=1e-4)
+    assert not z1.requires_grad and not z2.requires_grad
+    names = [str(n) for n in g["grad_names"]]
+    got = {k for k, v in leaves.items() if v.grad is not None}
+    assert sorted(names) == sorted(got)
+    for n in names:
+        gr = leaves[n].grad.double().reshape(-1)
+        ref_norm = float(g[f"gnorm/{n}"])
+        assert abs(gr.norm().item() - ref_norm) <= 5e-4 * ref_norm + 1e-9, n
+        np.testing.assert_allclose(gr[:16].numpy(), g[f"ghead/{n}"], rtol=5e-3, atol=5e-5 * max(ref_norm, 1e-6), err_msg=n)
+
+
 def test_pos_embed_matches_reference():
     g = np.load(os.path.join(GOLD, "pos_embed.npz"))
     for key in g.files:

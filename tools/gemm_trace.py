@@ -27,19 +27,18 @@ def main():
     lib.vitae_debug_set_gemm_trace.argtypes = [ctypes.c_void_p]
     assert lib.vitae_debug_set_gemm_trace(trace.data_ptr()) == 0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for name, M, N, K, amn, bmn, out in SHAPES:
+    for name, M, N, K, amn, bmn, out, (tn, sk) in SHAPES:
         A = torch.randn((K, M) if amn else (M, K), device=dev).bfloat16()
         B = torch.randn((K, N) if bmn else (N, K), device=dev).bfloat16()
         o = torch.empty(M, N, device=dev, dtype=torch.float32 if out == "f32" else torch.bfloat16)
         kw = {"out_f32": o} if out == "f32" else {"out_bf16": o}
-        tn, sk = ops.gemm_config(M, N, K)
         for mode in ("warm", "cold"):
             for rep in range(3):
                 if mode == "cold":
                     flush.zero_()
                 trace.zero_()
                 torch.cuda.synchronize()
-                ops.gemm(A, B, M, N, K, a_mn_major=bool(amn), b_mn_major=bool(bmn), workspace=ws, **kw)
+                ops.gemm(A, B, M, N, K, a_mn_major=bool(amn), b_mn_major=bool(bmn), workspace=ws, tile_n=tn, split_k=sk, **kw)
                 torch.cuda.synchronize()
             t = trace.cpu()
             live = t[:, 0] > 0

@@ -97,14 +97,16 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
             const int c = lane + 32 * i;
             if (c < nvec) {
                 const float4 xv = reinterpret_cast<const float4*>(x + off)[c];
-                float4 d;
+                float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (dy16) {
                     const uint2 raw = reinterpret_cast<const uint2*>(dy16 + off)[c];
                     const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
                     const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
                     d = make_float4(lo.x, lo.y, hi.x, hi.y);
-                } else {
-                    d = reinterpret_cast<const float4*>(dy32 + off)[c];
+                }
+                if (dy32) {   // both given: the two upstream gradients are summed
+                    const float4 e = reinterpret_cast<const float4*>(dy32 + off)[c];
+                    d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
                 }
                 if (dx_in) din[i] = reinterpret_cast<const float4*>(dx_in + off)[c];
                 const float4 gm = reinterpret_cast<const float4*>(gamma)[c];
@@ -158,7 +160,7 @@ layernorm_param_grads_kernel(const __nv_bfloat16* __restrict__ dy16, const float
     if (col < D) {
         for (int r = r0 + ty; r < r1; r += 8) {
             const size_t o = static_cast<size_t>(r) * D + col;
-            const float d = dy16 ? __bfloat162float(dy16[o]) : dy32[o];
+            const float d = (dy16 ? __bfloat162float(dy16[o]) : 0.f) + (dy32 ? dy32[o] : 0.f);
             const float xh = (x[o] - mean[r]) * rstd[r];
             a0 += d * xh;
             a1 += d;
@@ -324,7 +326,7 @@ extern "C" int vitae_layernorm_bwd_blocks(int rows) { return std::max(1, std::mi
 extern "C" int vitae_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* gamma,
                                    const float* mean, const float* rstd, const float* dx_in, float* dx_out,
                                    void* dx_out_bf16, int rows, int D, void* stream) {
-    VITAE_REQUIRE((dy_bf16 != nullptr) != (dy_f32 != nullptr), "layernorm_bwd: exactly one of dy_bf16/dy_f32");
+    VITAE_REQUIRE(dy_bf16 != nullptr || dy_f32 != nullptr, "layernorm_bwd: need dy_bf16 and/or dy_f32");
     VITAE_REQUIRE(x && gamma && mean && rstd && dx_out, "layernorm_bwd: null pointer");
     VITAE_REQUIRE(rows > 0 && D > 0 && D % 4 == 0 && D <= 1024, "layernorm_bwd: unsupported D=%d rows=%d", D, rows);
     const int blocks = std::min(ceil_div(rows, LN_WARPS), 148 * 4);
@@ -347,7 +349,7 @@ extern "C" int vitae_layernorm_bwd(const void* dy_bf16, const float* dy_f32, con
 extern "C" int vitae_layernorm_param_grads(const void* dy_bf16, const float* dy_f32, const float* x, const float* mean,
                                            const float* rstd, const float* dx_out, float* partials, int rows, int D,
                                            void* stream) {
-    VITAE_REQUIRE((dy_bf16 != nullptr) != (dy_f32 != nullptr), "layernorm_param_grads: exactly one of dy_bf16/dy_f32");
+    VITAE_REQUIRE(dy_bf16 != nullptr || dy_f32 != nullptr, "layernorm_param_grads: need dy_bf16 and/or dy_f32");
     VITAE_REQUIRE(x && mean && rstd && partials && rows > 0 && D > 0, "layernorm_param_grads: bad arguments");
     const int nblk = vitae_layernorm_bwd_blocks(rows);
     const int rows_per_slice = ceil_div(rows, nblk);

@@ -241,6 +241,10 @@ class MAEPlan:
         self.dec = self._stack(a, eng.dec, self.Md, B, self.Nd)
         D, Dd = eng.enc.dim, eng.dec.dim
         self.latent = a.new((self.Me, D), _BF16)
+        self.dlatent: Optional[torch.Tensor] = None   # fp32 upstream gradient of the latent (contrastive predictor)
+        # fp32 copy of the latent for consumers outside the kernels (contrastive predictor): the cosine loss is sensitive
+        # to bf16 rounding of its inputs (3 % gradient error from that rounding alone)
+        self.latent32 = a.new((self.Me, D), _F32) if eng.want_latent32 else None
         self.mean_n, self.rstd_n = a.new((self.Me,), _F32), a.new((self.Me,), _F32)
         self.hN = a.new((self.Md, Dd), _BF16)
         self.mean_dn, self.rstd_dn = a.new((self.Md,), _F32), a.new((self.Md,), _F32)
@@ -340,6 +344,7 @@ class MAEEngine:
         self.use_side_lane = True
         self.graph_replayed_launches = 0   # kernels executed through graph replays (vitae_launch_count sees enqueues)
         self.optim: Optional["FusedAdamW"] = None
+        self.want_latent32 = False         # set before the first plan is built (ContrastiveMAEViT)
         # Parameter groups in FORWARD order (contiguous slices of the flat buffers, which are laid out in backward order):
         # the optimizer can update them one after the other on its own stream while the next forward, which waits for
         # group g right before its first kernel that reads it, is already running (FusedAdamW.step(overlap=True)).
@@ -401,8 +406,10 @@ class MAEEngine:
                 torch.cuda.current_stream().wait_event(ev)
             self.params_in_flight = False
 
-    def plan(self, B: int, keep: int) -> MAEPlan:
-        key = (B, keep)
+    def plan(self, B: int, keep: int, slot: int = 0) -> MAEPlan:
+        """Activation arena for this shape; ``slot`` > 0 gives a second, independent arena (the contrastive model keeps the
+        encoder activations of both views alive until backward)."""
+        key = (B, keep) if slot == 0 else (B, keep, slot)
         pl = self.plans.get(key)
         if pl is None:
             pl = MAEPlan(self, B, keep)
@@ -456,7 +463,7 @@ class MAEEngine:
         if not self.use_graphs:
             return vol
         ptr = vol.data_ptr()
-        known = {k[1] for k in pl.graphs if k[0] == "fwd"}
+        known = {k[1] for k in pl.graphs if k[0] in ("fwd", "enc")}
         if ptr in known or len(known) < MAX_INPUT_ADDRESSES:
             return vol
         if pl.vol_static is None:
@@ -466,6 +473,16 @@ class MAEEngine:
         return pl.vol_static
 
     # ------------------------------------------------------------------------------------------------ forward
+    def forward_encoder_only(self, vol: torch.Tensor, noise: torch.Tensor, keep: int, slot: int = 1) -> MAEPlan:
+        """Encoder pass alone (second view of the contrastive model, model/vit_autoenc.py:277) into arena ``slot``."""
+        pl = self.plan(vol.shape[0], keep, slot)
+        vol = self._resident(pl, vol)
+        pl.vol = vol
+        pl.noise.copy_(noise)
+        self.refresh_shadow()
+        self._run(pl, ("enc", vol.data_ptr()), lambda: self.encode(pl, vol, pl.noise))
+        return pl
+
     def forward(self, vol: torch.Tensor, noise: torch.Tensor, keep: int, want_loss: bool = True,
                 pred_f32: bool = False) -> MAEPlan:
         """vol fp32 [B,C,V,V,V] (contiguous, CUDA); noise fp32 [B,L].  Fills plan.pred / mask / loss_out."""
@@ -510,7 +527,7 @@ class MAEEngine:
         self._stack_fwd(self.enc, pl.enc, pl.Me, B, pl.Ne)
         self._need("norm.weight")
         ops.layernorm_fwd(pl.enc.x[-1], self._p("norm.weight"), self._p("norm.bias"), pl.latent, pl.mean_n, pl.rstd_n,
-                          self.eps)
+                          self.eps, y_f32=pl.latent32)
 
     def decode(self, pl: MAEPlan, pred_f32: bool = False) -> None:
         """model/vit_autoenc.py:179-203 (forward_decoder); pl.pred keeps the cls row (row 0 of each sample)."""
@@ -559,31 +576,45 @@ class MAEEngine:
 
     # ------------------------------------------------------------------------------------------------ backward
     def backward(self, pl: MAEPlan, dloss: Optional[torch.Tensor], dpred_extra: Optional[torch.Tensor] = None,
-                 accumulate: bool = False, sync_grads: bool = False) -> None:
+                 accumulate: bool = False, sync_grads: bool = False, dlatent: Optional[torch.Tensor] = None,
+                 encoder_only: bool = False) -> None:
         """Gradient of (dloss * recon_loss [+ <dpred_extra, pred>]) w.r.t. every trainable parameter, written to
         (accumulate=False) or added into (True) the flat gradient buffer.  Hand-derived reverse of forward().
 
         ``sync_grads`` (data parallel, world size > 1): the backward runs as a few stages (one CUDA graph each) whose
         gradients are contiguous slices of the flat buffer; the mean all-reduce of a stage's slice is issued as soon as
-        that stage has been enqueued and overlaps the later stages (NCCL runs on its own stream)."""
+        that stage has been enqueued and overlaps the later stages (NCCL runs on its own stream).
+
+        ``dlatent`` fp32 [B*Ne, D]: an additional upstream gradient of the normalised encoder output (the contrastive
+        predictor consumes it, model/vit_autoenc.py:280-283).  ``encoder_only``: reverse of forward_encoder_only() -- the
+        only upstream gradient is ``dlatent``; decoder parameters are not touched."""
         if dloss is None:
             pl.dloss.zero_()
         else:
             pl.dloss.copy_(dloss.reshape(1))
+        if dlatent is not None:
+            if pl.dlatent is None:
+                pl.dlatent = torch.empty((pl.Me, self.enc.dim), dtype=_F32, device=self.device)
+            pl.dlatent.copy_(dlatent.reshape(pl.Me, self.enc.dim))
+        elif encoder_only:
+            raise ops._lib.VitaeError("encoder-only backward needs the latent gradient")
         staged = sync_grads and dp.world_size() > 1
-        stages = self._backward_stages(pl, dpred_extra, accumulate, split=staged)
+        stages = self._backward_stages(pl, dpred_extra, accumulate, split=staged, with_dlatent=dlatent is not None,
+                                       encoder_only=encoder_only)
         reducer = dp.GradReducer() if staged else None
         for i, (fn, (a, b)) in enumerate(stages):
             if dpred_extra is not None and i == 0:   # auxiliary torch-side terms that consume ``pred``: not graphed
                 fn()
             else:
-                self._run(pl, ("bwd", i, len(stages), pl.vol.data_ptr(), bool(accumulate)), fn)
+                self._run(pl, ("bwd", i, len(stages), pl.vol.data_ptr(), bool(accumulate), dlatent is not None,
+                               encoder_only), fn)
             if reducer is not None:
                 reducer.launch(self.flat.g32[a:b])
         if reducer is not None:
             reducer.wait()
 
-    def _backward_stages(self, pl: MAEPlan, dpred_extra: Optional[torch.Tensor], acc: bool, split: bool):
+    def _backward_stages(self, pl: MAEPlan, dpred_extra: Optional[torch.Tensor], acc: bool, split: bool,
+                         with_dlatent: bool = False, encoder_only: bool = False):
         """[(enqueue function, (start, end) slice of the flat gradient buffer it completes)], in execution order.
         split=False: one stage.  The stages share ``state['cur']`` (which of the two residual-gradient buffers is live)."""
         B, D, Dd, P = pl.B, self.enc.dim, self.dec.dim, self.P
@@ -639,7 +670,13 @@ class MAEEngine:
                      workspace=wsm)
             # ---- encoder norm + the upper half of the blocks (vit_autoenc.py:172-175)
             last_enc = f"blocks.{self.enc.depth - 1}.mlp.fc2.bias" if self.enc.depth else None
-            cur = self._ln_bwd(pl, d_e, pl.enc.x[-1], "norm", pl.mean_n, pl.rstd_n, None, 0, pl.Me, D, acc, last_enc)
+            cur = self._ln_bwd(pl, d_e, pl.enc.x[-1], "norm", pl.mean_n, pl.rstd_n, None, 0, pl.Me, D, acc, last_enc,
+                               dy2=pl.dlatent if with_dlatent else None)
+            state["cur"] = self._stack_bwd(self.enc, pl.enc, pl, pl.Me, B, pl.Ne, cur, acc, enc_hi)
+
+        def stage_enc_top():   # encoder-only pass: the latent gradient is the only upstream gradient of the final norm
+            last_enc = f"blocks.{self.enc.depth - 1}.mlp.fc2.bias" if self.enc.depth else None
+            cur = self._ln_bwd(pl, pl.dlatent, pl.enc.x[-1], "norm", pl.mean_n, pl.rstd_n, None, 0, pl.Me, D, acc, last_enc)
             state["cur"] = self._stack_bwd(self.enc, pl.enc, pl, pl.Me, B, pl.Ne, cur, acc, enc_hi)
 
         def stage_enc_lo():
@@ -659,10 +696,13 @@ class MAEEngine:
             self._side(side_pe, reads=("g_pe",))
 
         off = lambda n: self.flat.offsets[n][0]
-        parts = [(stage_pred, off("decoder_pred.weight"))]
-        if dec_all:
-            parts.append((stage_dec, off(f"decoder_blocks.{dec_all[0]}.mlp.fc2.weight")))
-        parts.append((stage_mid, off("mask_token")))
+        if encoder_only:
+            parts = [(stage_enc_top, 0)]       # slices only matter for the gradient exchange; see backward()
+        else:
+            parts = [(stage_pred, off("decoder_pred.weight"))]
+            if dec_all:
+                parts.append((stage_dec, off(f"decoder_blocks.{dec_all[0]}.mlp.fc2.weight")))
+            parts.append((stage_mid, off("mask_token")))
         if enc_lo:
             parts.append((stage_enc_lo, off(f"blocks.{enc_lo[0]}.mlp.fc2.weight")))
         parts.append((stage_embed, off("cls_token")))
@@ -687,7 +727,7 @@ class MAEEngine:
         return pl.d_ln[k][:M * D].view(M, D)
 
     def _ln_bwd(self, pl: MAEPlan, dy: torch.Tensor, x: torch.Tensor, name: str, mean, rstd, dx_in_idx: Optional[int],
-                out_idx: int, M: int, D: int, acc: bool, bias_name: Optional[str]) -> int:
+                out_idx: int, M: int, D: int, acc: bool, bias_name: Optional[str], dy2: Optional[torch.Tensor] = None) -> int:
         """LayerNorm backward.  Main lane (critical path): dres[out_idx] = (dres[dx_in_idx] if given) + LN'(dy), plus its
         bf16 copy dres16[out_idx].  Side lane: the column reductions -- affine gradients and ``bias_name`` (the bias whose
         gradient is the column sum of the new residual gradient).  ``dy`` must come from _ln_in().  Returns out_idx."""
@@ -699,11 +739,11 @@ class MAEEngine:
         dx_out = pl.dres[out_idx][:M * D].view(M, D)
         dx16 = pl.dres16[out_idx][:M * D].view(M, D)
         self.lanes.before_write(("dres", out_idx), ("dres16", out_idx))
-        ops.layernorm_bwd(dy, x, self._p(f"{name}.weight"), mean, rstd, dx_in, dx_out, dx16)
+        ops.layernorm_bwd(dy, x, self._p(f"{name}.weight"), mean, rstd, dx_in, dx_out, dx16, dy2=dy2)
         gb = self._g(bias_name) if bias_name is not None else None
 
         def side():
-            ops.layernorm_param_grads(dy, x, mean, rstd, dx_out if gb is not None else None, partials)
+            ops.layernorm_param_grads(dy, x, mean, rstd, dx_out if gb is not None else None, partials, dy2=dy2)
             ops.reduce_partials(partials, nb, D, self._g(f"{name}.weight"), self._g(f"{name}.bias"), gb, accumulate=acc)
         self._side(side, reads=(("d_ln", k), ("dres", out_idx)))
         return out_idx

@@ -204,7 +204,10 @@ class MaskedAutoencoderViT(nn.Module):
 
     # ------------------------------------------------------------------------------------------------ engine plumbing
     def _trainable(self):
-        return {n: p for n, p in self.named_parameters() if n not in ("pos_embed", "decoder_pos_embed")}
+        """Parameters that live in the engine's flat buffers (everything of the MAE; the contrastive predictor /
+        projection head are ordinary torch modules with their own storage)."""
+        return {n: p for n, p in self.named_parameters()
+                if n not in ("pos_embed", "decoder_pos_embed") and not n.startswith(("predictor.", "projection_head."))}
 
     def engine(self) -> MAEEngine:
         """Builds (once per device placement) the flat parameter buffers; the nn.Parameters become views of them."""
@@ -220,7 +223,11 @@ class MaskedAutoencoderViT(nn.Module):
         for p in self._engine.flat.params.values():
             p._vitae_engine = ref          # lets utils.misc.NativeScalerWithGradNormCount find the fused optimizer
         self._engine.broadcast_parameters()
+        self._broadcast_extra_parameters()
         return self._engine
+
+    def _broadcast_extra_parameters(self):
+        """Data parallel: parameters outside the flat buffers (none in the plain MAE) follow rank 0 as well."""
 
     @property
     def graph_replayed_launches(self) -> int:
@@ -240,7 +247,7 @@ class MaskedAutoencoderViT(nn.Module):
                 module.require_backward_grad_sync = self.prev
         return _NoSync()
 
-    def _backward(self, pl, drecon, dpred):
+    def _backward(self, pl, drecon, dpred, dlatent=None, second=None):
         eng = self._engine
         flat = eng.flat
         state = flat.grads_alias()
@@ -253,9 +260,13 @@ class MaskedAutoencoderViT(nn.Module):
         acc = state is True and not flat.overwrite_grads
         flat.overwrite_grads = False
         eng.use_graphs = self.use_cuda_graph
-        # the gradient exchange overlaps the backward stages, except when foreign gradients still have to be added first
+        # the gradient exchange overlaps the backward stages, except when foreign gradients or a second (encoder-only,
+        # contrastive view 2) backward still have to be added first
         sync = self.require_backward_grad_sync
-        eng.backward(pl, drecon, dpred_extra=dpred, accumulate=acc, sync_grads=sync and saved is None)
+        overlap_sync = sync and saved is None and second is None
+        eng.backward(pl, drecon, dpred_extra=dpred, accumulate=acc, sync_grads=overlap_sync, dlatent=dlatent)
+        if second is not None and second[1] is not None:
+            eng.backward(second[0], None, accumulate=True, dlatent=second[1], encoder_only=True)
         if state is not True:
             for n in flat.order:
                 p = flat.params[n]
@@ -263,8 +274,13 @@ class MaskedAutoencoderViT(nn.Module):
                     flat.vg[n].add_(saved[n])
                 if p.requires_grad:
                     p.grad = flat.vg[n]
-        if sync and saved is not None:
+        if sync and not overlap_sync:
             eng.allreduce_gradients()
+        if sync:
+            self._sync_extra_grads()
+
+    def _sync_extra_grads(self):
+        """Data parallel: gradients of parameters outside the flat buffers (none in the plain MAE)."""
 
     def state_dict(self, *args, **kwargs):
         if self._engine is not None:
@@ -377,6 +393,104 @@ class MaskedAutoencoderViT(nn.Module):
         return self._loss_list(recon, pred, x, edge_map_weight), pred, mask
 
 
+class _ContrastiveStep(torch.autograd.Function):
+    """One autograd node for both views of the contrastive model: forward = full MAE pass on view 1 + encoder pass on
+    view 2; backward = full backward (with the latent gradient of view 1 added at the encoder norm) followed by the
+    encoder-only backward of view 2 accumulating into the same gradient buffers.  A single node fixes that order."""
+
+    @staticmethod
+    def forward(ctx, anchor, module, vol1, vol2, noise1, noise2, keep):
+        eng = module._engine
+        pl1 = eng.forward(vol1, noise1, keep, want_loss=True, pred_f32=module.pred_dtype == torch.float32)
+        pl2 = eng.forward_encoder_only(vol2, noise2, keep, slot=1)
+        pl1.step_id += 1
+        pl2.step_id += 1
+        ctx.module, ctx.pl1, ctx.pl2, ctx.ids = module, pl1, pl2, (pl1.step_id, pl2.step_id)
+        ctx.set_materialize_grads(False)
+        recon, mask = pl1.loss_out[0].clone(), pl1.mask.clone()
+        pred = pl1.pred_view(module.pred_dtype)
+        latent1, latent2 = pl1.latent32.clone(), pl2.latent32.clone()  # [B*Ne, D], model/vit_autoenc.py:280-281
+        ctx.mark_non_differentiable(mask)
+        return recon, pred, mask, latent1, latent2
+
+    @staticmethod
+    def backward(ctx, drecon, dpred, _dmask, dlat1, dlat2):
+        module, pl1, pl2 = ctx.module, ctx.pl1, ctx.pl2
+        if (pl1.step_id, pl2.step_id) != ctx.ids:
+            raise VitaeError("backward() after a later forward() of the same shape: the activation workspace was reused")
+        module._backward(pl1, drecon, dpred, dlatent=dlat1, second=(pl2, dlat2))
+        return None, None, None, None, None, None, None
+
+
+class ContrastiveMAEViT(MaskedAutoencoderViT):
+    """MAE + contrastive predictor on the encoder tokens of two views -- model/vit_autoenc.py:241-285, the k-fold scripts'
+    default ``--model contr_mae_vit_base_patch16`` (k_fold_cross_valid_combined_brats.py:37).  Both encoder passes, the
+    decoder, the loss and all their gradients run in the B200 kernels; the predictor (two small Linear layers around a
+    BatchNorm1d) is ordinary torch modules for now: its parameters are outside the flat buffers, so
+    an optimizer over ``model.parameters()`` takes the reference's torch AdamW/GradScaler path."""
+
+    def __init__(self, volume_size=224, patch_size=16, in_chans=3, embed_dim=1024, depth=24, num_heads=16,
+                 decoder_embed_dim=512, decoder_depth=8, decoder_num_heads=16, mlp_ratio=4., norm_layer=nn.LayerNorm,
+                 norm_pix_loss=False, args=None, use_proj=False):
+        super().__init__(volume_size=volume_size, patch_size=patch_size, in_chans=in_chans, embed_dim=embed_dim,
+                         depth=depth, num_heads=num_heads, decoder_embed_dim=decoder_embed_dim,
+                         decoder_depth=decoder_depth, decoder_num_heads=decoder_num_heads, mlp_ratio=mlp_ratio,
+                         norm_layer=norm_layer, norm_pix_loss=norm_pix_loss, args=args)
+        self.use_proj = use_proj
+        D = self.embed_dim
+        if use_proj:   # built by the reference, never called in its forward (vit_autoenc.py:254-262,270-285)
+            self.projection_head = nn.Sequential(nn.Linear(D, D, bias=False), nn.BatchNorm1d(D), nn.ReLU(inplace=True),
+                                                 nn.Linear(D, D, bias=False), nn.BatchNorm1d(D), nn.ReLU(inplace=True),
+                                                 nn.Linear(D, D, bias=False), nn.BatchNorm1d(D, affine=False))
+        # built after the base class' init: keeps torch's default Linear / BatchNorm initialisation (vit_autoenc.py:263-268)
+        self.predictor = nn.Sequential(nn.Linear(D, D, bias=False), nn.BatchNorm1d(D), nn.ReLU(inplace=True), nn.Linear(D, D))
+
+    def _extra_modules(self):
+        return [self.predictor] + ([self.projection_head] if self.use_proj else [])
+
+    def _broadcast_extra_parameters(self):
+        from .. import dp
+        for m in self._extra_modules():
+            for t in list(m.parameters()) + list(m.buffers()):
+                dp.broadcast_flat(t.data)
+
+    def _sync_extra_grads(self):
+        # the predictor's backward has already run when the engine node's backward is called (it is downstream of the latents)
+        from .. import dp
+        for m in self._extra_modules():
+            for p in m.parameters():
+                if p.grad is not None:
+                    dp.allreduce_mean_(p.grad)
+
+    def engine(self):
+        eng = super().engine()
+        eng.want_latent32 = True       # plans built from now on keep an fp32 copy of the normalised encoder output
+        return eng
+
+    def forward(self, view1, view2, mask_ratio=0.75, edge_map_weight=0, noise=None, noise2=None):
+        """-> ([loss, raw_edge, recon, percep], pred, mask, p1, p2, z1, z2) with p / z of shape [B*(keep+1), D]
+        (model/vit_autoenc.py:270-285).  ``noise`` / ``noise2``: optional mask noise of view 1 / view 2 (tests)."""
+        eng = self.engine()
+        eng.use_graphs = self.use_cuda_graph
+        x1, x2 = self._check_volume(view1), self._check_volume(view2)
+        n1 = self._noise(x1, noise)                 # drawn in the reference's order: view 1 first (:272), then view 2 (:277)
+        n2 = self._noise(x2, noise2)
+        keep = self._len_keep(mask_ratio)
+        if keep < 1:
+            raise VitaeError(f"mask_ratio={mask_ratio} keeps no patch")
+        if torch.is_grad_enabled() and self.cls_token.requires_grad:
+            recon, pred, mask, lat1, lat2 = _ContrastiveStep.apply(self.cls_token, self, x1, x2, n1, n2, keep)
+        else:
+            pl1 = eng.forward(x1, n1, keep, want_loss=True, pred_f32=self.pred_dtype == torch.float32)
+            pl2 = eng.forward_encoder_only(x2, n2, keep, slot=1)
+            pl1.step_id += 1
+            pl2.step_id += 1
+            recon, pred, mask = pl1.loss_out[0].clone(), pl1.pred_view(self.pred_dtype), pl1.mask.clone()
+            lat1, lat2 = pl1.latent32.clone(), pl2.latent32.clone()
+        p1, p2 = self.predictor(lat1), self.predictor(lat2)
+        return self._loss_list(recon, pred, x1, edge_map_weight), pred, mask, p1, p2, lat1.detach(), lat2.detach()
+
+
 def mae_vit_large_patch16_dec512d8b(**kwargs):
     return MaskedAutoencoderViT(embed_dim=1024, depth=24, num_heads=16, decoder_embed_dim=512, decoder_depth=8,
                                 decoder_num_heads=16, mlp_ratio=4, norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
@@ -387,5 +501,11 @@ def mae_vit_base_patch16_dec512d8b(**kwargs):
                                 decoder_num_heads=16, mlp_ratio=4, norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
 
 
+def contr_mae_vit_base_patch16_dec512d8b(**kwargs):
+    return ContrastiveMAEViT(embed_dim=768, depth=12, num_heads=12, decoder_embed_dim=512, decoder_depth=8,
+                             decoder_num_heads=16, mlp_ratio=4, norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
+
+
 mae_vit_base_patch16 = mae_vit_base_patch16_dec512d8b
 mae_vit_large_patch16 = mae_vit_large_patch16_dec512d8b
+contr_mae_vit_base_patch16 = contr_mae_vit_base_patch16_dec512d8b

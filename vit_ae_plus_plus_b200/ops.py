@@ -200,22 +200,31 @@ def reduce_partials(partials, nblk: int, D: int, out0=None, out1=None, out2=None
                                     _stream()), "vitae_reduce_partials")
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dx_out, dx_out_bf16) -> None:
+def _dy_pair(dy, dy2):
+    """(bf16 pointer, fp32 pointer) for one or two upstream gradients of different dtype (summed by the kernels)."""
+    ptr = {_BF16: None, _F32: None}
+    for t in (dy, dy2):
+        if t is not None:
+            if ptr[t.dtype] is not None:
+                raise _lib.VitaeError("layernorm backward: two upstream gradients need different dtypes (bf16 + fp32)")
+            ptr[t.dtype] = t.data_ptr()
+    return ptr[_BF16], ptr[_F32]
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dx_out, dx_out_bf16, dy2=None) -> None:
     lib = _lib.load()
     rows, D = x.numel() // x.shape[-1], x.shape[-1]
-    dy16 = dy.data_ptr() if dy.dtype == _BF16 else None
-    dy32 = dy.data_ptr() if dy.dtype == _F32 else None
+    dy16, dy32 = _dy_pair(dy, dy2)
     check(lib.vitae_layernorm_bwd(dy16, dy32, x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                   _ptr(dx_in), dx_out.data_ptr(), _ptr(dx_out_bf16), rows, D, _stream()),
           "vitae_layernorm_bwd")
 
 
-def layernorm_param_grads(dy, x, mean, rstd, dx_out, partials) -> None:
+def layernorm_param_grads(dy, x, mean, rstd, dx_out, partials, dy2=None) -> None:
     """partials [3, layernorm_bwd_blocks(rows), D] <- per-slice sums of dy*xhat, dy, dx_out (finish: reduce_partials)."""
     lib = _lib.load()
     rows, D = x.numel() // x.shape[-1], x.shape[-1]
-    dy16 = dy.data_ptr() if dy.dtype == _BF16 else None
-    dy32 = dy.data_ptr() if dy.dtype == _F32 else None
+    dy16, dy32 = _dy_pair(dy, dy2)
     check(lib.vitae_layernorm_param_grads(dy16, dy32, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr(dx_out),
                                           partials.data_ptr(), rows, D, _stream()), "vitae_layernorm_param_grads")
 

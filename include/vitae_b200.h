@@ -105,12 +105,15 @@ int vitae_layernorm_fwd(const float* x, const float* gamma, const float* beta, v
 int vitae_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* gamma,
                         const float* mean, const float* rstd, const float* dx_in, float* dx_out, void* dx_out_bf16,
                         int rows, int D, void* stream);
-/* Column reductions of the same backward, off the critical path: per-slice partial sums go to
- * partials [3, nblocks, D] (nblocks = vitae_layernorm_bwd_blocks(rows)): [0] dgamma = sum dy*xhat, [1] dbeta = sum dy,
- * [2] column sums of dx_out (= gradient of the bias that was added to this residual stream: proj.bias / fc2.bias,
- * model/vit.py:142-143; zeros when dx_out == NULL).  Finish them with ONE vitae_reduce_partials launch. */
+/* Column reductions of the same backward, off the critical path, in one launch: dgamma = sum dy*xhat, dbeta = sum dy,
+ * dbias = column sums of dx_out (= gradient of the bias that was added to this residual stream: proj.bias / fc2.bias,
+ * model/vit.py:142-143); NULL outputs are skipped; accumulate adds into them.  workspace:
+ * vitae_layernorm_param_grads_workspace_bytes(rows, D) bytes, ZERO-FILLED before its first use (ticket counters; every call
+ * leaves them zero) and not shared by calls that may run concurrently.  Deterministic (fixed-order slice reduction). */
 int vitae_layernorm_param_grads(const void* dy_bf16, const float* dy_f32, const float* x, const float* mean,
-                                const float* rstd, const float* dx_out, float* partials, int rows, int D, void* stream);
+                                const float* rstd, const float* dx_out, void* workspace, float* dgamma, float* dbeta,
+                                float* dbias, int accumulate, int rows, int D, void* stream);
+size_t vitae_layernorm_param_grads_workspace_bytes(int rows, int D);
 int vitae_layernorm_bwd_blocks(int rows);
 /* out_k[c] = (accumulate ? out_k[c] : 0) + sum_blk partials[k][blk][c] for k = 0..2; NULL outputs are skipped. */
 int vitae_reduce_partials(const float* partials, int nblk, int D, float* out0, float* out1, float* out2,
@@ -185,6 +188,12 @@ int vitae_masked_mse_fwd(const void* pred, int pred_is_bf16, const float* vol, c
 int vitae_masked_mse_bwd(const void* pred, int pred_is_bf16, const float* vol, const float* mask,
                          const float* mask_sum, const float* dloss, void* dpred_bf16, int B, int C, int V, int p,
                          void* stream);
+
+/* Pulls up to 12 device regions into L2 (cp.async.bulk.prefetch.L2): the next transformer block's weights and saved
+ * activations while the current block computes (every kernel of the path is a few microseconds long and would otherwise
+ * start with a cold HBM load).  ptrs / bytes: HOST arrays read during the call.  No reference counterpart (performance
+ * plumbing of the B200 path). */
+int vitae_prefetch_l2(const void* const* ptrs, const size_t* bytes, int n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Parameter plumbing: fp32 master weights -> flat bf16 shadow (one launch for all tensors).

@@ -43,18 +43,17 @@ def test_layernorm_fwd_bwd(rows, D):
     assert _rel(y32.cpu(), y_ref.detach()) < 1e-5
     assert _rel(y16.float().cpu(), y_ref.detach()) < 1e-2
 
-    nb = ops.layernorm_bwd_blocks(rows)
-    partials = torch.empty(3, nb, D, device=DEV)
+    ws = torch.zeros(ops.layernorm_param_grads_workspace_bytes(rows, D), dtype=torch.uint8, device=DEV)
     dx = torch.empty(rows, D, device=DEV)
     dx16 = torch.empty(rows, D, device=DEV, dtype=torch.bfloat16)
     for dyt, tol in ((dy.to(DEV), 2e-5), (dy.to(DEV).bfloat16(), 1e-2)):
         ops.layernorm_bwd(dyt, xd, gd, mean, rstd, dres.to(DEV), dx, dx16)
-        ops.layernorm_param_grads(dyt, xd, mean, rstd, dx, partials)
         dgamma = torch.empty(D, device=DEV)
         dbeta = torch.full((D,), 3.0, device=DEV)
         dbias = torch.empty(D, device=DEV)
-        ops.reduce_partials(partials, nb, D, dgamma, None, dbias)                 # NULL outputs are skipped
-        ops.reduce_partials(partials, nb, D, None, dbeta, None, accumulate=True)  # accumulate onto 3.0
+        ops.layernorm_param_grads(dyt, xd, mean, rstd, dx, ws, dgamma=dgamma, dbias=dbias)     # NULL outputs are skipped
+        ops.layernorm_param_grads(dyt, xd, mean, rstd, None, ws, dbeta=dbeta, accumulate=True)  # accumulate onto 3.0
+        assert int(ws[:1024].view(torch.int32).abs().sum()) == 0                               # tickets reset themselves
         assert _rel(dx.cpu(), xr.grad + dres) < tol
         assert _rel(dx16.float().cpu(), xr.grad + dres) < 1e-2
         assert _rel(dgamma.cpu(), gr.grad) < max(tol, 1e-4)

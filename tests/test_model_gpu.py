@@ -103,6 +103,31 @@ def test_vit_base_one_volume_matches_oracle():
     print("worst grad rel err", worst)
 
 
+def test_vit_large_96_one_volume_matches_oracle():
+    """configs[3] geometry (ViT-L/16, 96^3 x 4: D = 1024, 24 blocks, L = 216, keep = 54) at batch 1."""
+    worst = check_against_oracle(O.CONFIGS["vit_large_96"], 4, 1, 0.75, grad_tol=3e-2)
+    print("worst grad rel err", worst)
+
+
+@pytest.mark.parametrize("ratio", [0.25, 0.50])
+def test_vit_base_mask_ratio_sweep_forward_matches_oracle(ratio):
+    """configs[4]: mask-ratio sweep on ViT-B 128^3 (keep = 384 / 256 kept patches, ragged encoder lengths 385 / 257):
+    loss, pred and mask of one volume against the oracle's forward (backward at these ratios is covered on the small
+    configurations by test_small_configs_match_oracle)."""
+    cfg = O.CONFIGS["vit_base_128"]
+    P = O.init_params(cfg, 6)
+    x = torch.randn(1, 4, 128, 128, 128, generator=torch.Generator().manual_seed(7))
+    torch.manual_seed(8)
+    noise = torch.rand(1, 512)
+    with torch.no_grad():
+        l_ref, pred_ref, mask_ref, _ = O.forward(x, P, cfg, ratio, noise, 0.0, with_edge=False)
+        m = build(cfg, P)
+        losses, pred, mask = m(x.cuda(), mask_ratio=ratio, noise=noise)
+    assert torch.equal(mask.cpu(), mask_ref) and int(mask.sum()) == 512 - int(512 * (1 - ratio))
+    assert abs(losses[2].item() - l_ref[2].item()) <= TOL * abs(l_ref[2].item())
+    assert relmax(pred.float(), pred_ref) < TOL
+
+
 def test_gradient_accumulation_and_zero_grad():
     cfg = O.CONFIGS["tiny"]
     P = O.init_params(cfg, 2)

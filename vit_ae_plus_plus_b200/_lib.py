@@ -52,7 +52,8 @@ SIGNATURES = {
     "vitae_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                     c_float, c_void_p]),
     "vitae_layernorm_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_void_p]),
-    "vitae_layernorm_param_grads": (c_int, [c_void_p] * 7 + [c_int, c_int, c_void_p]),
+    "vitae_layernorm_param_grads": (c_int, [c_void_p] * 10 + [c_int, c_int, c_int, c_void_p]),
+    "vitae_layernorm_param_grads_workspace_bytes": (c_size_t, [c_int, c_int]),
     "vitae_layernorm_bwd_blocks": (c_int, [c_int]),
     "vitae_reduce_partials": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "vitae_colsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
@@ -69,6 +70,7 @@ SIGNATURES = {
                                      c_void_p]),
     "vitae_masked_mse_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                      c_int, c_int, c_void_p]),
+    "vitae_prefetch_l2": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "vitae_cast_params_bf16": (c_int, [c_void_p, c_int, c_void_p, c_longlong, c_void_p]),
     "vitae_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float,
                                  c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),

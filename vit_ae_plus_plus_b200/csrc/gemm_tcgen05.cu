@@ -18,6 +18,8 @@
 //   * split-K and the rarely used epilogue features (row scatter / gather maps, unusual output combinations) go
 //     through fp32 slabs: every split stores its partial tile (same TMA-store epilogue), a finalize kernel reduces
 //     the slabs in fixed order (deterministic) and applies the generic epilogue.
+#include <stdlib.h>
+
 #include <mutex>
 #include <unordered_map>
 
@@ -28,7 +30,8 @@ namespace vitae {
 
 constexpr int BM = 128;
 constexpr int BK = 64;             // K elements per sub-block (= one 128-byte swizzled row)
-constexpr int GEMM_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int GEMM_THREADS = 320;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
+constexpr int EPI_THREADS = 256;   // two warps per TMEM lane quadrant, each takes half of the tile's columns (BN >= 128)
 
 // generic epilogue description (finalize kernel); mirrors vitae_gemm_epilogue
 struct EpiParams {
@@ -110,8 +113,9 @@ struct GemmSmem {
     static constexpr int BAR_OFFSET = PIPE_BYTES;             // full[STAGES], empty[STAGES], tmem_full, tmem slot
     static constexpr int BIAS_OFFSET = BAR_OFFSET + (2 * STAGES + 2) * 8;
     static constexpr int TOTAL = BIAS_OFFSET + BN * 4 + 1024; // + alignment slack
-    // epilogue staging (reuses the drained pipeline): 4 warps x 2 outputs x 2 buffers x 4 KB
-    static_assert(PIPE_BYTES >= 4 * 2 * 2 * 4096, "epilogue staging does not fit into the pipeline stages");
+    // epilogue staging (reuses the drained pipeline): 8 warps x 2 x 4 KB (one output: two alternating buffers; two
+    // outputs: one buffer each)
+    static_assert(PIPE_BYTES >= 8 * 2 * 4096, "epilogue staging does not fit into the pipeline stages");
 };
 
 // 16-byte chunk j of row r inside a 32-row x 128-byte SWIZZLE_128B box
@@ -249,28 +253,35 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     } else {
         // ------------------------------------------------------------------ epilogue warps
         const int q = warp & 3;                    // TMEM lane quadrant this warp may access
-        const int et = threadIdx.x - 64;           // 0..127 among the epilogue threads
+        const int half = (warp - 2) >> 2;          // which half of the tile's columns (BN >= 128); BN = 64: half 1 idles
+        const int et = threadIdx.x - 64;           // 0..255 among the epilogue threads
         const int mrow = m0 + q * 32 + lane;       // this lane's accumulator row
         // bias slice of this tile -> shared memory (read by every lane for every row)
-        for (int c = et; c < BN; c += 128) bias_s[c] = (ep.bias && n0 + c < N) ? ep.bias[n0 + c] : 0.f;
+        for (int c = et; c < BN; c += EPI_THREADS) bias_s[c] = (ep.bias && n0 + c < N) ? ep.bias[n0 + c] : 0.f;
         const float alpha = ep.alpha * (ep.alpha_ptr ? *ep.alpha_ptr : 1.0f);
-        named_bar_sync(1, 128);
-        // staging: per warp [output 0: buffers 0,1][output 1: buffers 0,1], 32 rows x 128 B each
-        const uint32_t stg = base + (warp - 2) * (4 * 4096);
+        named_bar_sync(1, EPI_THREADS);
+        constexpr int CW = BN >= 128 ? BN / 2 : BN;      // columns per epilogue warp
+        constexpr bool TWO_OUT = KIND == EPI_BF16_GELU || KIND == EPI_BF16_F32;
+        // staging per warp: 8 KB = two 32-row x 128-byte boxes; one output: they alternate, two outputs: one each
+        const uint32_t stg = base + (warp - 2) * 8192;
+        const bool active = BN >= 128 || half == 0;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         if (threadIdx.x == 64) GEMM_TRACE(7);
 
         constexpr bool OUT0_BF16 = KIND != EPI_ADD_F32 && KIND != EPI_F32;   // primary output element type
-        // one bulk commit group per bf16 box (incl. its GELU twin) or per fp32 box; EPI_BF16_F32 commits one per chunk
         int nbox = 0;   // bf16 boxes committed so far
+        const int c_begin = half * CW;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = c_begin; active && c < c_begin + CW; c += 32) {
             if (n0 + c >= N) break;
             uint32_t raw[32];
             tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, raw);
-            // staging buffers alternate: everything but the most recent bulk group must have been read by the engine
-            if (lane == 0) tma_store_wait_read<1>();
+            // the staging buffer about to be rewritten must have been read by the TMA engine
+            if (lane == 0) {
+                if (TWO_OUT) tma_store_wait_read<0>();
+                else tma_store_wait_read<1>();
+            }
             // operands of this chunk that come from global memory (lane = row: 128 / 64 contiguous bytes per lane)
             float4 add4[KIND == EPI_ADD_F32 ? 8 : 1];
             uint4 dg4[KIND == EPI_DGELU_BF16 ? 4 : 1];
@@ -317,19 +328,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     }
                 }
             }
-            const int half = (c >> 5) & 1;
+            const int hc = (c >> 5) & 1;   // even / odd 32-column chunk
+            // buffer assignment: one output -> boxes alternate between the two buffers; two outputs -> buffer 0 = primary
+            // (bf16), buffer 1 = secondary
+            const uint32_t buf0 = stg + ((!TWO_OUT && ((OUT0_BF16 ? nbox : hc) & 1)) ? 4096 : 0);
+            const uint32_t buf1 = stg + 4096;
             if (OUT0_BF16) {
                 // a 32-row x 64-column bf16 box spans two 32-column chunks: even chunk -> 16B chunks 0..3, odd -> 4..7
-                const uint32_t buf = stg + ((nbox & 1) ? 4096 : 0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    sts128(buf + swz128(lane, 4 * half + j), pack_bf16(v[8 * j + 0], v[8 * j + 1]),
+                    sts128(buf0 + swz128(lane, 4 * hc + j), pack_bf16(v[8 * j + 0], v[8 * j + 1]),
                            pack_bf16(v[8 * j + 2], v[8 * j + 3]), pack_bf16(v[8 * j + 4], v[8 * j + 5]),
                            pack_bf16(v[8 * j + 6], v[8 * j + 7]));
                 if (KIND == EPI_BF16_GELU) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        sts128(buf + 8192 + swz128(lane, 4 * half + j),
+                        sts128(buf1 + swz128(lane, 4 * hc + j),
                                pack_bf16(gelu_erf(v[8 * j + 0]), gelu_erf(v[8 * j + 1])),
                                pack_bf16(gelu_erf(v[8 * j + 2]), gelu_erf(v[8 * j + 3])),
                                pack_bf16(gelu_erf(v[8 * j + 4]), gelu_erf(v[8 * j + 5])),
@@ -337,8 +351,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 }
             }
             if (!OUT0_BF16 || KIND == EPI_BF16_F32) {
-                // fp32 box: 32 rows x 32 columns (128 B per row), one per chunk, two buffers alternating by chunk
-                const uint32_t buf = stg + (KIND == EPI_BF16_F32 ? 8192 : 0) + (half ? 4096 : 0);
+                // fp32 box: 32 rows x 32 columns (128 B per row), one per chunk
+                const uint32_t buf = KIND == EPI_BF16_F32 ? buf1 : buf0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     sts128(buf + swz128(lane, j), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
@@ -346,24 +360,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             fence_proxy_async();
             __syncwarp();
+            const bool box_done = OUT0_BF16 && (hc == 1 || n0 + c + 32 >= N);
             if (lane == 0) {
-                bool issued = false;
-                if (!OUT0_BF16 || KIND == EPI_BF16_F32) {
-                    const uint32_t buf = stg + (KIND == EPI_BF16_F32 ? 8192 : 0) + (half ? 4096 : 0);
-                    const CUtensorMap* mp = KIND == EPI_BF16_F32 ? &tmO1 : &tmO0;
-                    if (KIND == EPI_F32 && ep.accumulate) tma_reduce_add_3d(mp, buf, n0 + c, m0 + q * 32, blockIdx.z);
-                    else tma_store_3d(mp, buf, n0 + c, m0 + q * 32, KIND == EPI_BF16_F32 ? 0 : blockIdx.z);
-                    issued = true;
+                if (!OUT0_BF16) {
+                    if (KIND == EPI_F32 && ep.accumulate) tma_reduce_add_3d(&tmO0, buf0, n0 + c, m0 + q * 32, blockIdx.z);
+                    else tma_store_3d(&tmO0, buf0, n0 + c, m0 + q * 32, blockIdx.z);
                 }
-                if (OUT0_BF16 && (half == 1 || n0 + c + 32 >= N)) {
-                    const uint32_t buf = stg + ((nbox & 1) ? 4096 : 0);
-                    tma_store_3d(&tmO0, buf, n0 + (c & ~63), m0 + q * 32, 0);
-                    if (KIND == EPI_BF16_GELU) tma_store_3d(&tmO1, buf + 8192, n0 + (c & ~63), m0 + q * 32, 0);
-                    issued = true;
+                if (KIND == EPI_BF16_F32) tma_store_3d(&tmO1, buf1, n0 + c, m0 + q * 32, 0);
+                if (box_done) {
+                    tma_store_3d(&tmO0, buf0, n0 + (c & ~63), m0 + q * 32, 0);
+                    if (KIND == EPI_BF16_GELU) tma_store_3d(&tmO1, buf1, n0 + (c & ~63), m0 + q * 32, 0);
                 }
-                if (issued || KIND == EPI_BF16_F32) tma_store_commit();
+                if (!OUT0_BF16 || KIND == EPI_BF16_F32 || box_done) tma_store_commit();
             }
-            if (OUT0_BF16 && (half == 1 || n0 + c + 32 >= N)) ++nbox;
+            if (box_done) ++nbox;
         }
         if (lane == 0) tma_store_wait_read<0>();   // the engine must have read our staging buffers before the CTA exits
         __syncwarp();
@@ -539,7 +549,7 @@ template <bool A_MN, bool B_MN, int KIND>
 static int dispatch_tile(int bn, bool deep, const GemmLaunch& g) {
     if (bn == 64) return deep ? launch_gemm<64, 2, 4, A_MN, B_MN, KIND>(g) : launch_gemm<64, 2, 2, A_MN, B_MN, KIND>(g);
     if (bn == 128) return deep ? launch_gemm<128, 2, 3, A_MN, B_MN, KIND>(g) : launch_gemm<128, 1, 3, A_MN, B_MN, KIND>(g);
-    return launch_gemm<256, 2, 2, A_MN, B_MN, KIND>(g);
+    return deep ? launch_gemm<256, 2, 2, A_MN, B_MN, KIND>(g) : launch_gemm<256, 1, 2, A_MN, B_MN, KIND>(g);
 }
 
 // only the (operand major, epilogue kind) pairs the training step uses are instantiated; anything else runs as EPI_F32
@@ -691,7 +701,9 @@ extern "C" int vitae_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
     // Pipeline depth: a grid that fits one CTA per SM gets the deep ring (all of shared memory for one CTA); larger
     // grids get the shallow one so that two CTAs share an SM (one's epilogue overlaps the other's main loop).
     const long long ctas = static_cast<long long>(ceil_div(M, BM)) * ceil_div(N, bn) * splits;
-    const bool deep = ctas <= 148;
+    // VITAE_GEMM_SHALLOW=1 (experiment): always the two-CTAs-per-SM rings, so that GEMMs of the two backward lanes can share SMs
+    static const bool force_shallow = [] { const char* e = getenv("VITAE_GEMM_SHALLOW"); return e && e[0] == '1'; }();
+    const bool deep = ctas <= 148 && !force_shallow;
     const int eff_splits = dispatch(amn, bmn, kind, bn, deep, g);
     if (eff_splits < 0) return eff_splits;
     if (use_slabs) {

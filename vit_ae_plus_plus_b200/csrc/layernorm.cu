@@ -141,18 +141,21 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
     }
 }
 
-// Column reductions of the LayerNorm backward, per block of rows (finished by reduce_partials_kernel):
-// partials[0][blk][:] = sum dy * xhat (dgamma), partials[1][blk][:] = sum dy (dbeta),
-// partials[2][blk][:] = sum dx_out (column sums of the residual gradient = gradient of the bias added to that stream).
-// Block = 32 columns x 8 row lanes (coalesced 128-byte row segments); grid = (D / 32 strips, row slices).
+// Column reductions of the LayerNorm backward in ONE launch: out0 = dgamma = sum dy * xhat, out1 = dbeta = sum dy,
+// out2 = column sums of dx_out (= gradient of the bias that was added to this residual stream).
+// Block = 32 columns x 8 row lanes (coalesced 128-byte row segments); grid = (D / 32 strips, row slices).  Every block
+// writes its slice's partial sums to partials[3][slices][D]; the last block of a strip to arrive (ticket counter, reset
+// for the next call) adds the slices in fixed order -> deterministic.
 __global__ void __launch_bounds__(256)
 layernorm_param_grads_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ dy32,
                              const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
-                             const float* __restrict__ dx_out, float* __restrict__ partials, int rows, int D,
-                             int rows_per_slice) {
+                             const float* __restrict__ dx_out, float* __restrict__ partials,
+                             unsigned int* __restrict__ counters, float* __restrict__ out0, float* __restrict__ out1,
+                             float* __restrict__ out2, int accumulate, int rows, int D, int rows_per_slice) {
     pdl_trigger();
     pdl_wait();
     __shared__ float red[3][8][33];
+    __shared__ unsigned int ticket_sh;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int col = blockIdx.x * 32 + tx;
     const int r0 = blockIdx.y * rows_per_slice, r1 = min(rows, r0 + rows_per_slice);
@@ -169,12 +172,28 @@ layernorm_param_grads_kernel(const __nv_bfloat16* __restrict__ dy16, const float
     }
     red[0][ty][tx] = a0; red[1][ty][tx] = a1; red[2][ty][tx] = a2;
     __syncthreads();
+    const int nsl = gridDim.y;
     if (ty < 3 && col < D) {
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) s += red[ty][k][tx];
-        partials[(static_cast<size_t>(ty) * gridDim.y + blockIdx.y) * D + col] = s;
+        partials[(static_cast<size_t>(ty) * nsl + blockIdx.y) * D + col] = s;
     }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) ticket_sh = atomicAdd(&counters[blockIdx.x], 1u);
+    __syncthreads();
+    if (ticket_sh != static_cast<unsigned int>(nsl - 1)) return;
+    __threadfence();
+    if (ty < 3 && col < D) {
+        float* out = ty == 0 ? out0 : (ty == 1 ? out1 : out2);
+        if (out) {
+            float t = 0.f;
+            for (int y = 0; y < nsl; ++y) t += __ldcg(partials + (static_cast<size_t>(ty) * nsl + y) * D + col);
+            out[col] = accumulate ? out[col] + t : t;
+        }
+    }
+    if (threadIdx.x == 0) counters[blockIdx.x] = 0u;
 }
 
 // out[part][col] (+)= sum_blk partials[part][blk][col]: finishes LayerNorm-backward partials (up to 3 outputs, 1 launch).
@@ -346,17 +365,24 @@ extern "C" int vitae_layernorm_bwd(const void* dy_bf16, const float* dy_f32, con
     return 0;
 }
 
+extern "C" size_t vitae_layernorm_param_grads_workspace_bytes(int rows, int D) {
+    return 1024 + static_cast<size_t>(3) * vitae_layernorm_bwd_blocks(rows) * D * sizeof(float);
+}
+
 extern "C" int vitae_layernorm_param_grads(const void* dy_bf16, const float* dy_f32, const float* x, const float* mean,
-                                           const float* rstd, const float* dx_out, float* partials, int rows, int D,
-                                           void* stream) {
+                                           const float* rstd, const float* dx_out, void* workspace, float* dgamma,
+                                           float* dbeta, float* dbias, int accumulate, int rows, int D, void* stream) {
     VITAE_REQUIRE(dy_bf16 != nullptr || dy_f32 != nullptr, "layernorm_param_grads: need dy_bf16 and/or dy_f32");
-    VITAE_REQUIRE(x && mean && rstd && partials && rows > 0 && D > 0, "layernorm_param_grads: bad arguments");
+    VITAE_REQUIRE(x && mean && rstd && workspace && rows > 0 && D > 0 && D <= 32 * 256, "layernorm_param_grads: bad arguments");
+    VITAE_REQUIRE(!dbias || dx_out, "layernorm_param_grads: dbias needs dx_out");
     const int nblk = vitae_layernorm_bwd_blocks(rows);
     const int rows_per_slice = ceil_div(rows, nblk);
-    VITAE_REQUIRE(ceil_div(rows, rows_per_slice) <= nblk, "layernorm_param_grads: slice arithmetic");
+    auto* counters = static_cast<unsigned int*>(workspace);                       // [<= 256] zero at first use, self-resetting
+    auto* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 1024);
     dim3 grid(ceil_div(D, 32), nblk);
     launch_kernel(layernorm_param_grads_kernel, grid, dim3(256), 0, as_stream(stream),
-                  static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, mean, rstd, dx_out, partials, rows, D, rows_per_slice);
+                  static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, mean, rstd, dx_out, partials, counters, dgamma, dbeta,
+                  dbias, accumulate, rows, D, rows_per_slice);
     VITAE_CHECK_LAUNCH("layernorm_param_grads");
     return 0;
 }

@@ -268,8 +268,9 @@ class MAEPlan:
         self.d_hid = [a.new((Mmax * Hmax,), _BF16), a.new((Mmax * Hmax,), _BF16)]
         self.dqkv = [a.new((Mmax * 3 * Dmax,), _BF16), a.new((Mmax * 3 * Dmax,), _BF16)]
         self.delta = a.new((B * max(eng.enc.heads * self.Ne, eng.dec.heads * self.Nd),), _F32)
-        nb = ops.layernorm_bwd_blocks(Mmax)
-        self.ln_partials = [a.new((3 * nb * Dmax,), _F32), a.new((3 * nb * Dmax,), _F32)]
+        ln_ws = ops.layernorm_param_grads_workspace_bytes(Mmax, Dmax)
+        self.ln_ws = torch.zeros(ln_ws, dtype=torch.uint8, device=dev)   # zero-filled: ticket counters (side lane only)
+        a.nbytes += ln_ws
         self.ln_calls = 0
         cs_bytes = max(ops.colsum_workspace_bytes(r, c) for r in (self.Me, self.Md, B * keep)
                        for c in (P, 3 * D, 3 * Dd, eng.enc.hidden, eng.dec.hidden, D, Dd))
@@ -342,6 +343,9 @@ class MAEEngine:
         self.ws_main, self.ws_side = ops.GrowBuf(dev), ops.GrowBuf(dev)
         self.use_graphs = True
         self.use_side_lane = True
+        # pull the next block's weights (and, in backward, its saved activations) into the 126 MB L2 while the current
+        # block computes: every kernel is a few microseconds long and would otherwise start with a cold HBM load
+        self.use_l2_prefetch = os.environ.get("VITAE_L2_PREFETCH", "1") != "0"
         self.graph_replayed_launches = 0   # kernels executed through graph replays (vitae_launch_count sees enqueues)
         self.optim: Optional["FusedAdamW"] = None
         self.want_latent32 = False         # set before the first plan is built (ContrastiveMAEViT)
@@ -389,6 +393,25 @@ class MAEEngine:
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:])) and spans[0][0] == 0 and spans[-1][1] == self.flat.total, \
             "parameter groups must tile the flat buffer"
         return group_of, [tuple(r) for r in ranges]
+
+    def _block_p16(self, prefix: str, i: int) -> torch.Tensor:
+        """bf16 shadow of block i's parameters: one contiguous slice of the flat buffer (fc2.weight ... norm1.bias)."""
+        a = self.flat.offsets[f"{prefix}.{i}.mlp.fc2.weight"][0]
+        o, k, _ = self.flat.offsets[f"{prefix}.{i}.norm1.bias"]
+        return self.flat.p16[a:o + k]
+
+    def _prefetch(self, tensors) -> None:
+        if self.use_l2_prefetch and self.use_side_lane:
+            ts = [t for t in tensors if t is not None]
+            self._side(lambda: ops.prefetch_l2(ts))
+
+    def _prefetch_block(self, st: StackSpec, sb, i: int, with_acts: bool) -> None:
+        if 0 <= i < st.depth:
+            ts = [self._block_p16(st.prefix, i)]
+            if with_acts:
+                b = sb.blocks[i]
+                ts += [b.pre, b.act, b.ln2, b.o, b.qkv, b.ln1, b.xmid, sb.x[i]]
+            self._prefetch(ts)
 
     def _need(self, name: str) -> None:
         """Orders the current stream after the optimizer's update of the group that holds parameter ``name`` (once per
@@ -480,7 +503,10 @@ class MAEEngine:
         pl.vol = vol
         pl.noise.copy_(noise)
         self.refresh_shadow()
-        self._run(pl, ("enc", vol.data_ptr()), lambda: self.encode(pl, vol, pl.noise))
+        def body():
+            self.encode(pl, vol, pl.noise)
+            self.lanes.join()
+        self._run(pl, ("enc", vol.data_ptr()), body)
         return pl
 
     def forward(self, vol: torch.Tensor, noise: torch.Tensor, keep: int, want_loss: bool = True,
@@ -500,6 +526,7 @@ class MAEEngine:
             self.decode(pl, pred_f32)
             if want_loss:
                 ops.masked_mse_fwd(pl.pred, vol, pl.mask, pl.patch_sums, pl.loss_out, self.p)
+            self.lanes.join()          # the side lane carries the L2 prefetches of the forward
         self._run(pl, ("fwd", vol.data_ptr(), pred_f32, want_loss), body)
         self.params_in_flight = False      # the pass above waited for every parameter group
         return pl
@@ -515,6 +542,7 @@ class MAEEngine:
         discarded by the gather at :147, so embedding them is dead work) + pos, cls row, blocks, final norm."""
         B, keep, D = pl.B, pl.keep, self.enc.dim
         self._waited = set()
+        self._prefetch([self._w("patch_embed.proj.weight")] + ([self._block_p16("blocks", 0)] if self.enc.depth else []))
         ops.random_masking(noise, pl.ids_shuffle, pl.ids_restore, pl.mask, keep)
         ops.build_row_maps(pl.ids_shuffle, keep, pl.maps)
         ops.im2col_patches(vol, pl.ids_shuffle, pl.cols, self.p, keep)
@@ -524,7 +552,8 @@ class MAEEngine:
                  bias=self._p("patch_embed.proj.bias"), addend=self.pos, add_rows=pl.maps["pe_pos_rows"], ldadd=D,
                  out_f32=x0, out_rows=pl.maps["enc_tok_rows"], workspace=self.ws_main)
         ops.fill_rows(x0, pl.maps["enc_cls_rows"], B, D, self._p("cls_token"), None, self.pos, None)
-        self._stack_fwd(self.enc, pl.enc, pl.Me, B, pl.Ne)
+        self._stack_fwd(self.enc, pl.enc, pl.Me, B, pl.Ne,
+                        after=[self._w("decoder_embed.weight")] + ([self._block_p16("decoder_blocks", 0)] if self.dec.depth else []))
         self._need("norm.weight")
         ops.layernorm_fwd(pl.enc.x[-1], self._p("norm.weight"), self._p("norm.bias"), pl.latent, pl.mean_n, pl.rstd_n,
                           self.eps, y_f32=pl.latent32)
@@ -543,7 +572,7 @@ class MAEEngine:
         if pl.nmask > 0:
             ops.fill_rows(xd0, pl.maps["masked_dec_rows"], B * pl.nmask, Dd, self._p("mask_token"), None, self.dpos,
                           pl.maps["masked_pos_rows"])
-        self._stack_fwd(self.dec, pl.dec, pl.Md, B, pl.Nd)
+        self._stack_fwd(self.dec, pl.dec, pl.Md, B, pl.Nd, after=[self._w("decoder_pred.weight")])
         self._need("decoder_norm.weight")
         ops.layernorm_fwd(pl.dec.x[-1], self._p("decoder_norm.weight"), self._p("decoder_norm.bias"), pl.hN,
                           pl.mean_dn, pl.rstd_dn, self.eps)
@@ -551,14 +580,19 @@ class MAEEngine:
                  out_bf16=pl.pred.view(pl.Md, self.P), out_f32=pl.pred32.view(pl.Md, self.P) if pred_f32 else None,
                  workspace=self.ws_main)
 
-    def _stack_fwd(self, st: StackSpec, sb, M: int, B: int, N: int) -> None:
-        """model/vit.py:139-144 (Block), :112-124 (Attention), :90-96 (Mlp3D)."""
+    def _stack_fwd(self, st: StackSpec, sb, M: int, B: int, N: int, after=()) -> None:
+        """model/vit.py:139-144 (Block), :112-124 (Attention), :90-96 (Mlp3D).  ``after``: weights used right after the
+        stack (prefetched into L2 during the last block)."""
         D, hid, H, hd = st.dim, st.hidden, st.heads, st.head_dim
         scale = hd ** -0.5
         ws = self.ws_main
         for i in range(st.depth):
             pre = f"{st.prefix}.{i}"
             b, x_in, x_out = sb.blocks[i], sb.x[i], sb.x[i + 1]
+            if i + 1 < st.depth:
+                self._prefetch_block(st, sb, i + 1, with_acts=False)
+            elif after:
+                self._prefetch(list(after))
             self._need(f"{pre}.norm1.weight")
             ops.layernorm_fwd(x_in, self._p(f"{pre}.norm1.weight"), self._p(f"{pre}.norm1.bias"), b.ln1, b.mean1,
                               b.rstd1, self.eps)
@@ -627,6 +661,7 @@ class MAEEngine:
         dec_all = list(reversed(range(self.dec.depth)))
 
         def stage_pred():
+            self._prefetch_block(self.dec, pl.dec, self.dec.depth - 1, with_acts=True)
             # ---- loss: d recon / d pred (model/vit_autoenc.py:226-227), zeros for kept patches and the cls row
             lanes.before_write("dpred")
             ops.masked_mse_bwd(pl.pred, pl.vol, pl.mask, pl.loss_out[1:], pl.dloss, pl.dpred, self.p)
@@ -651,6 +686,8 @@ class MAEEngine:
 
         def stage_mid():
             cur = state["cur"]
+            self._prefetch([self._w("decoder_embed.weight"), pl.latent])
+            self._prefetch_block(self.enc, pl.enc, self.enc.depth - 1, with_acts=True)
             dxd = pl.dres[cur][:pl.Md * Dd].view(pl.Md, Dd)
             # ---- mask tokens, decoder_embed (vit_autoenc.py:181-190)
             lanes.before_write("g_embed")
@@ -675,6 +712,7 @@ class MAEEngine:
             state["cur"] = self._stack_bwd(self.enc, pl.enc, pl, pl.Me, B, pl.Ne, cur, acc, enc_hi)
 
         def stage_enc_top():   # encoder-only pass: the latent gradient is the only upstream gradient of the final norm
+            self._prefetch_block(self.enc, pl.enc, self.enc.depth - 1, with_acts=True)
             last_enc = f"blocks.{self.enc.depth - 1}.mlp.fc2.bias" if self.enc.depth else None
             cur = self._ln_bwd(pl, pl.dlatent, pl.enc.x[-1], "norm", pl.mean_n, pl.rstd_n, None, 0, pl.Me, D, acc, last_enc)
             state["cur"] = self._stack_bwd(self.enc, pl.enc, pl, pl.Me, B, pl.Ne, cur, acc, enc_hi)
@@ -731,10 +769,8 @@ class MAEEngine:
         """LayerNorm backward.  Main lane (critical path): dres[out_idx] = (dres[dx_in_idx] if given) + LN'(dy), plus its
         bf16 copy dres16[out_idx].  Side lane: the column reductions -- affine gradients and ``bias_name`` (the bias whose
         gradient is the column sum of the new residual gradient).  ``dy`` must come from _ln_in().  Returns out_idx."""
-        nb = ops.layernorm_bwd_blocks(M)
         k = pl.ln_calls & 1
         pl.ln_calls += 1
-        partials = pl.ln_partials[k][:3 * nb * D].view(3, nb, D)
         dx_in = None if dx_in_idx is None else pl.dres[dx_in_idx][:M * D].view(M, D)
         dx_out = pl.dres[out_idx][:M * D].view(M, D)
         dx16 = pl.dres16[out_idx][:M * D].view(M, D)
@@ -743,8 +779,9 @@ class MAEEngine:
         gb = self._g(bias_name) if bias_name is not None else None
 
         def side():
-            ops.layernorm_param_grads(dy, x, mean, rstd, dx_out if gb is not None else None, partials, dy2=dy2)
-            ops.reduce_partials(partials, nb, D, self._g(f"{name}.weight"), self._g(f"{name}.bias"), gb, accumulate=acc)
+            ops.layernorm_param_grads(dy, x, mean, rstd, dx_out if gb is not None else None, pl.ln_ws,
+                                      dgamma=self._g(f"{name}.weight"), dbeta=self._g(f"{name}.bias"), dbias=gb,
+                                      accumulate=acc, dy2=dy2)
         self._side(side, reads=(("d_ln", k), ("dres", out_idx)))
         return out_idx
 
@@ -762,6 +799,7 @@ class MAEEngine:
             pre = f"{st.prefix}.{i}"
             b, x_in = sb.blocks[i], sb.x[i]
             hb = i & 1
+            self._prefetch_block(st, sb, i - 1, with_acts=True)
             d_hid = pl.d_hid[hb][:M * hid].view(M, hid)
             dqkv = pl.dqkv[hb][:M * 3 * D].view(M, 3 * D)
             dres16 = pl.dres16[cur][:M * D].view(M, D)

@@ -220,13 +220,22 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in, dx_out, dx_out_bf16, dy2=None
           "vitae_layernorm_bwd")
 
 
-def layernorm_param_grads(dy, x, mean, rstd, dx_out, partials, dy2=None) -> None:
-    """partials [3, layernorm_bwd_blocks(rows), D] <- per-slice sums of dy*xhat, dy, dx_out (finish: reduce_partials)."""
+def layernorm_param_grads_workspace_bytes(rows: int, D: int) -> int:
+    return _lib.load().vitae_layernorm_param_grads_workspace_bytes(rows, D)
+
+
+def layernorm_param_grads(dy, x, mean, rstd, dx_out, workspace, dgamma=None, dbeta=None, dbias=None,
+                          accumulate: bool = False, dy2=None) -> None:
+    """dgamma = sum dy*xhat, dbeta = sum dy, dbias = column sums of dx_out, one launch; workspace: zero-filled uint8 tensor of
+    >= layernorm_param_grads_workspace_bytes(rows, D) bytes (see header)."""
     lib = _lib.load()
     rows, D = x.numel() // x.shape[-1], x.shape[-1]
+    if workspace.numel() * workspace.element_size() < lib.vitae_layernorm_param_grads_workspace_bytes(rows, D):
+        raise _lib.VitaeError("layernorm_param_grads: workspace too small")
     dy16, dy32 = _dy_pair(dy, dy2)
     check(lib.vitae_layernorm_param_grads(dy16, dy32, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr(dx_out),
-                                          partials.data_ptr(), rows, D, _stream()), "vitae_layernorm_param_grads")
+                                          workspace.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), int(accumulate), rows,
+                                          D, _stream()), "vitae_layernorm_param_grads")
 
 
 def colsum(inp, rows: int, cols: int, out, workspace, accumulate: bool = False, ld: Optional[int] = None) -> None:
@@ -322,6 +331,19 @@ def masked_mse_bwd(pred, vol, mask, mask_sum, dloss, dpred, p: int) -> None:
     check(lib.vitae_masked_mse_bwd(pred.data_ptr(), int(pred.dtype == _BF16), vol.data_ptr(), mask.data_ptr(),
                                    mask_sum.data_ptr(), dloss.data_ptr(), dpred.data_ptr(), B, C, V, p, _stream()),
           "vitae_masked_mse_bwd")
+
+
+def prefetch_l2(tensors) -> None:
+    """Pulls the storage of up to 12 tensors (contiguous) into L2 on the current stream (include/vitae_b200.h)."""
+    ts = [t for t in tensors if t is not None and t.numel() > 0]
+    if not ts:
+        return
+    lib = _lib.load()
+    for i in range(0, len(ts), 12):
+        part = ts[i:i + 12]
+        ptrs = (ctypes.c_void_p * len(part))(*[t.data_ptr() for t in part])
+        sizes = (ctypes.c_size_t * len(part))(*[t.numel() * t.element_size() for t in part])
+        check(lib.vitae_prefetch_l2(ptrs, sizes, len(part), _stream()), "vitae_prefetch_l2")
 
 
 def cast_params_bf16(table, ntensors: int, dst, total: int) -> None:

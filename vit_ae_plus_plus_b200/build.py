@@ -43,9 +43,11 @@ def build(force: bool = False, verbose: bool = True) -> str:
     flags = list(NVCC_FLAGS)
     if os.environ.get("VITAE_TRACE") == "1":      # debug build: per-phase clock stamps in the GEMM (tools/gemm_trace.py)
         flags.append("-DVITAE_GEMM_TRACE")
+    if os.environ.get("VITAE_EPI_WARPS"):          # experiment: 4 or 8 epilogue warps in the GEMM
+        flags.append("-DVITAE_EPI_WARPS=" + os.environ["VITAE_EPI_WARPS"])
     if os.environ.get("VITAE_EPI_NOGELU") == "1":  # experiment only: GELU code compiled out of the GEMM epilogue
         flags.append("-DVITAE_EPI_NOGELU")
-    digest = _digest() + ("+trace" if "-DVITAE_GEMM_TRACE" in flags else "")
+    digest = _digest() + "".join(f for f in flags if f.startswith("-DVITAE"))
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB_PATH
     nvcc = _nvcc()

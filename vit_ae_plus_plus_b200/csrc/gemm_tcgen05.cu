@@ -30,8 +30,11 @@ namespace vitae {
 
 constexpr int BM = 128;
 constexpr int BK = 64;             // K elements per sub-block (= one 128-byte swizzled row)
-constexpr int GEMM_THREADS = 320;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
-constexpr int EPI_THREADS = 256;   // two warps per TMEM lane quadrant, each takes half of the tile's columns (BN >= 128)
+#ifndef VITAE_EPI_WARPS
+#define VITAE_EPI_WARPS 8          // 8: two warps per TMEM lane quadrant, each takes half of the tile's columns (BN >= 128)
+#endif
+constexpr int EPI_THREADS = VITAE_EPI_WARPS * 32;
+constexpr int GEMM_THREADS = 64 + EPI_THREADS;   // warp 0: TMA producer, warp 1: MMA issuer, then the epilogue warps
 
 // generic epilogue description (finalize kernel); mirrors vitae_gemm_epilogue
 struct EpiParams {
@@ -260,11 +263,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         for (int c = et; c < BN; c += EPI_THREADS) bias_s[c] = (ep.bias && n0 + c < N) ? ep.bias[n0 + c] : 0.f;
         const float alpha = ep.alpha * (ep.alpha_ptr ? *ep.alpha_ptr : 1.0f);
         named_bar_sync(1, EPI_THREADS);
-        constexpr int CW = BN >= 128 ? BN / 2 : BN;      // columns per epilogue warp
+        constexpr int CW = (BN >= 128 && VITAE_EPI_WARPS == 8) ? BN / 2 : BN;      // columns per epilogue warp
         constexpr bool TWO_OUT = KIND == EPI_BF16_GELU || KIND == EPI_BF16_F32;
         // staging per warp: 8 KB = two 32-row x 128-byte boxes; one output: they alternate, two outputs: one each
         const uint32_t stg = base + (warp - 2) * 8192;
-        const bool active = BN >= 128 || half == 0;
+        const bool active = (BN >= 128 && VITAE_EPI_WARPS == 8) || half == 0;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         if (threadIdx.x == 64) GEMM_TRACE(7);

@@ -161,6 +161,7 @@ layernorm_param_grads_kernel(const __nv_bfloat16* __restrict__ dy16, const float
     const int r0 = blockIdx.y * rows_per_slice, r1 = min(rows, r0 + rows_per_slice);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     if (col < D) {
+#pragma unroll 4
         for (int r = r0 + ty; r < r1; r += 8) {
             const size_t o = static_cast<size_t>(r) * D + col;
             const float d = (dy16 ? __bfloat162float(dy16[o]) : 0.f) + (dy32 ? dy32[o] : 0.f);
@@ -185,11 +186,21 @@ layernorm_param_grads_kernel(const __nv_bfloat16* __restrict__ dy16, const float
     __syncthreads();
     if (ticket_sh != static_cast<unsigned int>(nsl - 1)) return;
     __threadfence();
+    // last block of this strip: the 8 row lanes share the slices (fixed assignment and order -> deterministic)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float t = 0.f;
+        if (col < D)
+            for (int y = ty; y < nsl; y += 8) t += __ldcg(partials + (static_cast<size_t>(k) * nsl + y) * D + col);
+        red[k][ty][tx] = t;
+    }
+    __syncthreads();
     if (ty < 3 && col < D) {
         float* out = ty == 0 ? out0 : (ty == 1 ? out1 : out2);
         if (out) {
             float t = 0.f;
-            for (int y = 0; y < nsl; ++y) t += __ldcg(partials + (static_cast<size_t>(ty) * nsl + y) * D + col);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += red[ty][k][tx];
             out[col] = accumulate ? out[col] + t : t;
         }
     }
@@ -304,8 +315,17 @@ colsum_kernel(const T* __restrict__ in, int rows, int cols, int ld, float* __res
     if (ticket_sh != gridDim.y - 1) return;
     __threadfence();
     if (col < cols) {
-        float t = 0.f;
-        for (int y = 0; y < static_cast<int>(gridDim.y); ++y) t += __ldcg(ws_partials + static_cast<size_t>(y) * cols + col);
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;   // four independent loads in flight, fixed association
+        const int ns = static_cast<int>(gridDim.y);
+        int y = 0;
+        for (; y + 4 <= ns; y += 4) {
+            t0 += __ldcg(ws_partials + static_cast<size_t>(y) * cols + col);
+            t1 += __ldcg(ws_partials + static_cast<size_t>(y + 1) * cols + col);
+            t2 += __ldcg(ws_partials + static_cast<size_t>(y + 2) * cols + col);
+            t3 += __ldcg(ws_partials + static_cast<size_t>(y + 3) * cols + col);
+        }
+        for (; y < ns; ++y) t0 += __ldcg(ws_partials + static_cast<size_t>(y) * cols + col);
+        const float t = (t0 + t1) + (t2 + t3);
         out[col] = accumulate ? out[col] + t : t;
     }
     if (threadIdx.x == 0) counters[blockIdx.x] = 0u;
@@ -400,7 +420,7 @@ static inline int colsum_slices(int rows, int cols) {
     const int strips = ceil_div(cols, CS_COLS);
     int s = std::max(1, (2 * 148) / strips);
     s = std::min(s, std::max(1, rows / 32));
-    return s;
+    return std::min(s, 16);
 }
 
 extern "C" size_t vitae_colsum_workspace_bytes(int rows, int cols) {

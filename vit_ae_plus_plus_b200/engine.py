@@ -155,6 +155,7 @@ class _Lanes:
         self.stream = torch.cuda.Stream(device=device, priority=int(os.environ.get("VITAE_SIDE_PRIORITY", "-1")))
         self.readers: Dict[object, torch.cuda.Event] = {}
         self.dirty = False
+        self.extra_dirty: Optional[torch.cuda.Stream] = None   # another forked stream to join (L2 prefetches)
 
     def side(self, fn, reads=()) -> None:
         main = torch.cuda.current_stream()
@@ -177,6 +178,11 @@ class _Lanes:
                 main.wait_event(ev)
 
     def join(self) -> None:
+        if self.extra_dirty is not None:
+            ev = torch.cuda.Event()
+            ev.record(self.extra_dirty)
+            torch.cuda.current_stream().wait_event(ev)
+            self.extra_dirty = None
         if self.dirty:
             ev = torch.cuda.Event()
             ev.record(self.stream)
@@ -340,12 +346,14 @@ class MAEEngine:
         self.dpos = decoder_pos_embed.detach().reshape(self.L + 1, Dd).contiguous()
         self.plans: Dict[Tuple[int, int], MAEPlan] = {}
         self.lanes = _Lanes(dev)
+        self.pf_stream = torch.cuda.Stream(device=dev)
         self.ws_main, self.ws_side = ops.GrowBuf(dev), ops.GrowBuf(dev)
         self.use_graphs = True
         self.use_side_lane = True
         # pull the next block's weights (and, in backward, its saved activations) into the 126 MB L2 while the current
         # block computes: every kernel is a few microseconds long and would otherwise start with a cold HBM load
-        self.use_l2_prefetch = os.environ.get("VITAE_L2_PREFETCH", "1") != "0"
+        # (opt-in, VITAE_L2_PREFETCH=1: measured on B200 at batch 4 it does not pay -- 4.71 ms/step with, 4.65 without)
+        self.use_l2_prefetch = os.environ.get("VITAE_L2_PREFETCH", "0") == "1"
         self.graph_replayed_launches = 0   # kernels executed through graph replays (vitae_launch_count sees enqueues)
         self.optim: Optional["FusedAdamW"] = None
         self.want_latent32 = False         # set before the first plan is built (ContrastiveMAEViT)
@@ -401,9 +409,17 @@ class MAEEngine:
         return self.flat.p16[a:o + k]
 
     def _prefetch(self, tensors) -> None:
+        """L2 prefetch on its own stream (forked from the current point of the main lane, joined by _Lanes.join): it must
+        not queue behind the side lane's weight-gradient GEMMs."""
         if self.use_l2_prefetch and self.use_side_lane:
             ts = [t for t in tensors if t is not None]
-            self._side(lambda: ops.prefetch_l2(ts))
+            main = torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.pf_stream.wait_event(ev)
+            with torch.cuda.stream(self.pf_stream):
+                ops.prefetch_l2(ts)
+            self.lanes.extra_dirty = self.pf_stream
 
     def _prefetch_block(self, st: StackSpec, sb, i: int, with_acts: bool) -> None:
         if 0 <= i < st.depth:
@@ -655,9 +671,13 @@ class MAEEngine:
         cws, wsm, wss = pl.colsum_ws, self.ws_main, self.ws_side
         lanes = self.lanes
         state = {"cur": 0}
-        enc_split = self.enc.depth // 2
-        enc_hi = list(reversed(range(enc_split, self.enc.depth)))
-        enc_lo = list(reversed(range(0, enc_split)))
+        # encoder blocks in groups of (about) 3, top first: the first group shares a stage with the decoder embed / encoder
+        # norm, every further group is a stage of its own (finer slices near the end of backward leave less of the
+        # gradient exchange exposed after the last kernel)
+        gsz = 3
+        enc_desc = list(reversed(range(self.enc.depth)))
+        enc_groups = [enc_desc[k:k + gsz] for k in range(0, len(enc_desc), gsz)] or [[]]
+        enc_hi, enc_rest = enc_groups[0], enc_groups[1:]
         dec_all = list(reversed(range(self.dec.depth)))
 
         def stage_pred():
@@ -717,8 +737,10 @@ class MAEEngine:
             cur = self._ln_bwd(pl, pl.dlatent, pl.enc.x[-1], "norm", pl.mean_n, pl.rstd_n, None, 0, pl.Me, D, acc, last_enc)
             state["cur"] = self._stack_bwd(self.enc, pl.enc, pl, pl.Me, B, pl.Ne, cur, acc, enc_hi)
 
-        def stage_enc_lo():
-            state["cur"] = self._stack_bwd(self.enc, pl.enc, pl, pl.Me, B, pl.Ne, state["cur"], acc, enc_lo)
+        def stage_enc_group(layers):
+            def run():
+                state["cur"] = self._stack_bwd(self.enc, pl.enc, pl, pl.Me, B, pl.Ne, state["cur"], acc, layers)
+            return run
 
         def stage_embed():
             dx0 = pl.dres[state["cur"]][:pl.Me * D].view(pl.Me, D)
@@ -741,8 +763,8 @@ class MAEEngine:
             if dec_all:
                 parts.append((stage_dec, off(f"decoder_blocks.{dec_all[0]}.mlp.fc2.weight")))
             parts.append((stage_mid, off("mask_token")))
-        if enc_lo:
-            parts.append((stage_enc_lo, off(f"blocks.{enc_lo[0]}.mlp.fc2.weight")))
+        for grp in enc_rest:
+            parts.append((stage_enc_group(grp), off(f"blocks.{grp[0]}.mlp.fc2.weight")))
         parts.append((stage_embed, off("cls_token")))
 
         def joined(fns):

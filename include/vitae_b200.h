@@ -189,6 +189,24 @@ int vitae_masked_mse_bwd(const void* pred, int pred_is_bf16, const float* vol, c
                          const float* mask_sum, const float* dloss, void* dpred_bf16, int B, int C, int V, int p,
                          void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Edge-map loss (shipped default use_edge_map = yes) -- model/vit_autoenc.py:221-224 with
+ * model/model_utils/sobel_filter.py:10-45 and gaussian_filter.py:5-26:
+ *   raw_edge = mean_{b,v} ( sum_c |sobel(unpatchify(pred)_c)|(v) - sum_c |sobel(blur(target_c))|(v) )^2
+ * scratch: vitae_edge_scratch_floats(B, C, V) floats, shared by the three calls of one step (target, fwd, bwd).
+ * vitae_edge_target: E_tgt fp32 [B, V^3] from the fp32 volume [B, C, V, V, V]; taps: HOST array of the ntaps (odd, <= 16)
+ *   normalised 1-D Gaussian taps (the reference's dense ks^3 kernel is their outer product).
+ * vitae_edge_loss_fwd: loss_out[0] = raw_edge for pred bf16 [B, L+1, P] (cls row first); keeps the residual in
+ *   resid fp32 [B, V^3] and the normalised Sobel gradients in scratch for the backward.
+ * vitae_edge_loss_bwd: dpred_bf16 [B, L+1, P] += (*upstream) * d raw_edge / d pred  (|grad| = 0 contributes 0). */
+size_t vitae_edge_scratch_floats(int B, int C, int V);
+int vitae_edge_target(const float* vol, const float* taps, int ntaps, float* scratch, float* E_tgt, int B, int C, int V,
+                      void* stream);
+int vitae_edge_loss_fwd(const void* pred_bf16, const float* E_tgt, float* scratch, float* resid, float* loss_out, int B,
+                        int C, int V, int p, void* stream);
+int vitae_edge_loss_bwd(const float* resid, const float* scratch, const float* upstream, void* dpred_bf16, int B, int C,
+                        int V, int p, void* stream);
+
 /* Pulls up to 12 device regions into L2 (cp.async.bulk.prefetch.L2): the next transformer block's weights and saved
  * activations while the current block computes (every kernel of the path is a few microseconds long and would otherwise
  * start with a cold HBM load).  ptrs / bytes: HOST arrays read during the call.  No reference counterpart (performance

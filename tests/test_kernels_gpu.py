@@ -287,3 +287,40 @@ def test_cast_params_and_adamw_match_torch():
     found_inf.fill_(1.0)
     ops.adamw_step(p, torch.randn(n, device=DEV), m, v, shadow, n, 1e-3, 0.9, 0.95, 1e-8, 0.05, 4, inv_scale, found_inf)
     assert torch.equal(p, before)                                   # GradScaler semantics: skipped on inf (utils/misc.py:267)
+
+
+@pytest.mark.parametrize("B,C,V,p", [(2, 1, 32, 8), (1, 4, 32, 16), (2, 2, 48, 16)])
+def test_edge_map_loss_kernels_match_oracle(B, C, V, p):
+    """vitae_edge_target / vitae_edge_loss_fwd / vitae_edge_loss_bwd against the oracle's restatement of
+    model/vit_autoenc.py:221-224 (Sobel of unpatchify(pred) vs Sobel of the Gaussian-blurred target) and its autograd."""
+    from vit_ae_plus_plus_b200 import ops
+    g = torch.Generator().manual_seed(B * 100 + C * 10 + V)
+    vol = torch.randn(B, C, V, V, V, generator=g)
+    L, P = (V // p) ** 3, p ** 3 * C
+    pred16 = (torch.randn(B, L, P, generator=g) * 0.7).bfloat16()     # the kernels read the bf16 pred of the GEMM epilogue
+    pr = pred16.float().requires_grad_(True)
+    ref = O.edge_map_mse(pr, O.patchify(vol, p), p)
+    ref.backward()
+    e_ref = O.sobel_edge_map(O.gaussian_blur_3d(vol, 2.0))
+
+    full = torch.zeros(B, L + 1, P, dtype=torch.bfloat16, device=DEV)
+    full[:, 1:] = pred16.to(DEV)
+    scratch = torch.empty(ops.edge_scratch_floats(B, C, V), device=DEV)
+    e_tgt = torch.empty(B, V, V, V, device=DEV)
+    resid = torch.empty(B, V, V, V, device=DEV)
+    out = torch.zeros(1, device=DEV)
+    ops.edge_target(vol.to(DEV), ops.gaussian_taps(2.0), scratch, e_tgt)
+    assert _rel(e_tgt.cpu(), e_ref) < 2e-5
+    ops.edge_loss_fwd(full, e_tgt, scratch, resid, out, B, C, V, p)
+    assert abs(out.item() - ref.item()) < 1e-4 * abs(ref.item())
+    dpred = torch.zeros(B, L + 1, P, dtype=torch.bfloat16, device=DEV)
+    base = (torch.randn(B, L + 1, P, generator=g) * 1e-3).bfloat16()    # existing content (masked-MSE gradient) is added to
+    dpred.copy_(base)
+    upstream = torch.tensor([3.0], device=DEV)
+    ops.edge_loss_bwd(resid, scratch, upstream, dpred, B, C, V, p)
+    torch.cuda.synchronize()
+    got = dpred.float().cpu() - base.float()
+    assert got[:, 0].abs().max().item() == 0                           # the cls row is not part of the volume
+    want = 3.0 * pr.grad
+    err = (got[:, 1:] - want).abs().max().item() / want.abs().max().item()
+    assert err < 2e-2, err                                             # bf16 accumulation target

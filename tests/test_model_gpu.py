@@ -295,7 +295,8 @@ def test_latent_gradient_paths_match_oracle(graphs):
     for rep in range(3 if graphs else 1):
         m.zero_grad(set_to_none=True)
         eng.use_graphs = graphs
-        recon, pred, mask, lat1, lat2 = VA._ContrastiveStep.apply(m.cls_token, m, x1.cuda(), x2.cuda(), n1.cuda(), n2.cuda(), keep)
+        recon, _edge, pred, mask, lat1, lat2 = VA._ContrastiveStep.apply(m.cls_token, m, x1.cuda(), x2.cuda(), n1.cuda(),
+                                                                         n2.cuda(), keep, False)
         (recon + (lat1 * G1.cuda()).sum() + (lat2 * G2.cuda()).sum()).backward()
         torch.cuda.synchronize()
         assert relmax(lat1, lat1o.reshape(G1.shape)) < TOL and relmax(lat2, lat2o.reshape(G2.shape)) < TOL

@@ -70,6 +70,10 @@ SIGNATURES = {
                                      c_void_p]),
     "vitae_masked_mse_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                      c_int, c_int, c_void_p]),
+    "vitae_edge_scratch_floats": (c_size_t, [c_int, c_int, c_int]),
+    "vitae_edge_target": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vitae_edge_loss_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "vitae_edge_loss_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "vitae_prefetch_l2": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "vitae_cast_params_bf16": (c_int, [c_void_p, c_int, c_void_p, c_longlong, c_void_p]),
     "vitae_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float,

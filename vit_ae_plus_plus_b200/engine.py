@@ -248,6 +248,7 @@ class MAEPlan:
         D, Dd = eng.enc.dim, eng.dec.dim
         self.latent = a.new((self.Me, D), _BF16)
         self.dlatent: Optional[torch.Tensor] = None   # fp32 upstream gradient of the latent (contrastive predictor)
+        self.edge_scratch = self.edge_tgt = self.edge_resid = self.edge_out = self.dedge = None
         # fp32 copy of the latent for consumers outside the kernels (contrastive predictor): the cosine loss is sensitive
         # to bf16 rounding of its inputs (3 % gradient error from that rounding alone)
         self.latent32 = a.new((self.Me, D), _F32) if eng.want_latent32 else None
@@ -288,6 +289,16 @@ class MAEPlan:
         self.graphs: Dict[tuple, _GraphSlot] = {}
         self.nbytes = a.nbytes
         self.vol: Optional[torch.Tensor] = None   # the volume of the current step (read in place by the kernels)
+
+    def edge_buffers(self, eng: "MAEEngine") -> None:
+        """Scratch of the fused edge-map loss (allocated on first use: 5 volume-sized fp32 buffers)."""
+        if self.edge_scratch is None:
+            B, C, V = self.B, eng.C, eng.V
+            self.edge_scratch = torch.empty(ops.edge_scratch_floats(B, C, V), dtype=_F32, device=eng.device)
+            self.edge_tgt = torch.empty((B, V, V, V), dtype=_F32, device=eng.device)
+            self.edge_resid = torch.empty((B, V, V, V), dtype=_F32, device=eng.device)
+            self.edge_out = torch.zeros((1,), dtype=_F32, device=eng.device)
+            self.dedge = torch.zeros((1,), dtype=_F32, device=eng.device)
 
     def pred_view(self, dtype) -> torch.Tensor:
         """The reference's ``pred`` [N, L, P] (cls row dropped, vit_autoenc.py:200-201) as a view of the workspace."""
@@ -357,6 +368,7 @@ class MAEEngine:
         self.graph_replayed_launches = 0   # kernels executed through graph replays (vitae_launch_count sees enqueues)
         self.optim: Optional["FusedAdamW"] = None
         self.want_latent32 = False         # set before the first plan is built (ContrastiveMAEViT)
+        self.edge_taps = ops.gaussian_taps(2.0)   # sigma = 2 at the call site, model/vit_autoenc.py:222
         # Parameter groups in FORWARD order (contiguous slices of the flat buffers, which are laid out in backward order):
         # the optimizer can update them one after the other on its own stream while the next forward, which waits for
         # group g right before its first kernel that reads it, is already running (FusedAdamW.step(overlap=True)).
@@ -526,8 +538,9 @@ class MAEEngine:
         return pl
 
     def forward(self, vol: torch.Tensor, noise: torch.Tensor, keep: int, want_loss: bool = True,
-                pred_f32: bool = False) -> MAEPlan:
-        """vol fp32 [B,C,V,V,V] (contiguous, CUDA); noise fp32 [B,L].  Fills plan.pred / mask / loss_out."""
+                pred_f32: bool = False, want_edge: bool = False) -> MAEPlan:
+        """vol fp32 [B,C,V,V,V] (contiguous, CUDA); noise fp32 [B,L].  Fills plan.pred / mask / loss_out (and, with
+        ``want_edge``, plan.edge_out = raw edge-map loss of model/vit_autoenc.py:221-224)."""
         B = vol.shape[0]
         pl = self.plan(B, keep)
         vol = self._resident(pl, vol)
@@ -536,14 +549,20 @@ class MAEEngine:
         if pred_f32 and pl.pred32 is None:
             pl.pred32 = torch.empty((pl.B, pl.Nd, self.P), dtype=_F32, device=self.device)
         self.refresh_shadow()
+        if want_edge:
+            pl.edge_buffers(self)
 
         def body():
             self.encode(pl, vol, pl.noise)
             self.decode(pl, pred_f32)
             if want_loss:
                 ops.masked_mse_fwd(pl.pred, vol, pl.mask, pl.patch_sums, pl.loss_out, self.p)
+            if want_edge:
+                ops.edge_target(vol, self.edge_taps, pl.edge_scratch, pl.edge_tgt)
+                ops.edge_loss_fwd(pl.pred, pl.edge_tgt, pl.edge_scratch, pl.edge_resid, pl.edge_out, pl.B, self.C, self.V,
+                                  self.p)
             self.lanes.join()          # the side lane carries the L2 prefetches of the forward
-        self._run(pl, ("fwd", vol.data_ptr(), pred_f32, want_loss), body)
+        self._run(pl, ("fwd", vol.data_ptr(), pred_f32, want_loss, want_edge), body)
         self.params_in_flight = False      # the pass above waited for every parameter group
         return pl
 
@@ -627,7 +646,7 @@ class MAEEngine:
     # ------------------------------------------------------------------------------------------------ backward
     def backward(self, pl: MAEPlan, dloss: Optional[torch.Tensor], dpred_extra: Optional[torch.Tensor] = None,
                  accumulate: bool = False, sync_grads: bool = False, dlatent: Optional[torch.Tensor] = None,
-                 encoder_only: bool = False) -> None:
+                 encoder_only: bool = False, dedge: Optional[torch.Tensor] = None) -> None:
         """Gradient of (dloss * recon_loss [+ <dpred_extra, pred>]) w.r.t. every trainable parameter, written to
         (accumulate=False) or added into (True) the flat gradient buffer.  Hand-derived reverse of forward().
 
@@ -642,6 +661,10 @@ class MAEEngine:
             pl.dloss.zero_()
         else:
             pl.dloss.copy_(dloss.reshape(1))
+        if dedge is not None:      # upstream gradient of the raw edge-map loss (forward(want_edge=True) must have run)
+            if pl.edge_resid is None:
+                raise ops._lib.VitaeError("edge-map gradient without an edge-map forward")
+            pl.dedge.copy_(dedge.reshape(1))
         if dlatent is not None:
             if pl.dlatent is None:
                 pl.dlatent = torch.empty((pl.Me, self.enc.dim), dtype=_F32, device=self.device)
@@ -650,21 +673,21 @@ class MAEEngine:
             raise ops._lib.VitaeError("encoder-only backward needs the latent gradient")
         staged = sync_grads and dp.world_size() > 1
         stages = self._backward_stages(pl, dpred_extra, accumulate, split=staged, with_dlatent=dlatent is not None,
-                                       encoder_only=encoder_only)
+                                       encoder_only=encoder_only, with_edge=dedge is not None)
         reducer = dp.GradReducer() if staged else None
         for i, (fn, (a, b)) in enumerate(stages):
             if dpred_extra is not None and i == 0:   # auxiliary torch-side terms that consume ``pred``: not graphed
                 fn()
             else:
                 self._run(pl, ("bwd", i, len(stages), pl.vol.data_ptr(), bool(accumulate), dlatent is not None,
-                               encoder_only), fn)
+                               encoder_only, dedge is not None), fn)
             if reducer is not None:
                 reducer.launch(self.flat.g32[a:b])
         if reducer is not None:
             reducer.wait()
 
     def _backward_stages(self, pl: MAEPlan, dpred_extra: Optional[torch.Tensor], acc: bool, split: bool,
-                         with_dlatent: bool = False, encoder_only: bool = False):
+                         with_dlatent: bool = False, encoder_only: bool = False, with_edge: bool = False):
         """[(enqueue function, (start, end) slice of the flat gradient buffer it completes)], in execution order.
         split=False: one stage.  The stages share ``state['cur']`` (which of the two residual-gradient buffers is live)."""
         B, D, Dd, P = pl.B, self.enc.dim, self.dec.dim, self.P
@@ -685,6 +708,8 @@ class MAEEngine:
             # ---- loss: d recon / d pred (model/vit_autoenc.py:226-227), zeros for kept patches and the cls row
             lanes.before_write("dpred")
             ops.masked_mse_bwd(pl.pred, pl.vol, pl.mask, pl.loss_out[1:], pl.dloss, pl.dpred, self.p)
+            if with_edge:       # + dedge * d raw_edge / d pred (transposed Sobel stencil over the kept residual)
+                ops.edge_loss_bwd(pl.edge_resid, pl.edge_scratch, pl.dedge, pl.dpred, pl.B, self.C, self.V, self.p)
             if dpred_extra is not None:
                 pl.dpred[:, 1:, :].add_(dpred_extra.to(_BF16))
             dpred = pl.dpred.view(pl.Md, P)

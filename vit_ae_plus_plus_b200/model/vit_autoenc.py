@@ -13,7 +13,7 @@ Differences a caller can observe (all documented in DESIGN.md):
     tests can feed the same mask to the reference; default behaviour draws it exactly like the reference does;
   * ties in ``noise`` are ordered stably (the reference's un-stable ``argsort`` leaves them unspecified);
   * ``pred`` / ``mask`` returned by ``forward`` are views of per-shape workspaces that the next ``forward`` overwrites;
-  * ``loss_list[1]`` (raw edge-map loss) is only evaluated when ``edge_map_weight != 0`` or ``report_edge_loss`` is
+  * ``loss_list[1]`` (raw edge-map loss, fused Sobel / Gaussian stencil kernels) is only evaluated when ``edge_map_weight != 0`` or ``report_edge_loss`` is
     set; the VGG perceptual term (never differentiable in the reference, perceptual_loss.py:68-69) is supported for
     ``perceptual_weight == 0`` only (the shipped default, config.ini:34).
 """
@@ -30,7 +30,7 @@ from torch import nn
 from .. import ops
 from .._lib import VitaeError
 from ..engine import MAEEngine
-from .model_utils import EdgeMapLoss, sincos_pos_embed_3d
+from .model_utils import sincos_pos_embed_3d
 
 
 def _triple(v):
@@ -128,25 +128,26 @@ class _MAEStep(torch.autograd.Function):
     by the kernels straight into ``param.grad`` (views of the flat gradient buffer), so backward returns None."""
 
     @staticmethod
-    def forward(ctx, anchor, module, vol, noise, keep):
+    def forward(ctx, anchor, module, vol, noise, keep, want_edge):
         eng = module._engine
-        pl = eng.forward(vol, noise, keep, want_loss=True, pred_f32=module.pred_dtype == torch.float32)
+        pl = eng.forward(vol, noise, keep, want_loss=True, pred_f32=module.pred_dtype == torch.float32, want_edge=want_edge)
         pl.step_id += 1
-        ctx.module, ctx.pl, ctx.step_id = module, pl, pl.step_id
+        ctx.module, ctx.pl, ctx.step_id, ctx.want_edge = module, pl, pl.step_id, want_edge
         ctx.set_materialize_grads(False)
         recon = pl.loss_out[0].clone()
+        raw_edge = pl.edge_out[0].clone() if want_edge else torch.zeros((), device=vol.device)
         mask = pl.mask.clone()
         pred = pl.pred_view(module.pred_dtype)
         ctx.mark_non_differentiable(mask)
-        return recon, pred, mask
+        return recon, raw_edge, pred, mask
 
     @staticmethod
-    def backward(ctx, drecon, dpred, _dmask):
+    def backward(ctx, drecon, dedge, dpred, _dmask):
         module, pl = ctx.module, ctx.pl
         if pl.step_id != ctx.step_id:
             raise VitaeError("backward() after a later forward() of the same shape: the activation workspace was reused")
-        module._backward(pl, drecon, dpred)
-        return None, None, None, None, None
+        module._backward(pl, drecon, dpred, dedge=dedge if ctx.want_edge else None)
+        return None, None, None, None, None, None
 
 
 class MaskedAutoencoderViT(nn.Module):
@@ -171,7 +172,6 @@ class MaskedAutoencoderViT(nn.Module):
                                              for _ in range(decoder_depth)])
         self.decoder_norm = Affine(decoder_embed_dim, eps)
         self.decoder_pred = Dense(decoder_embed_dim, self.patch_embed.patch_size[0] ** 3 * in_chans)
-        self.edge_loss = EdgeMapLoss(sigma=2.0)
         self.args = args
         self.perceptual_weight = 0 if args is None else getattr(args, "perceptual_weight", 0)
         print(f"Using perceptual weight of {self.perceptual_weight}")
@@ -247,7 +247,7 @@ class MaskedAutoencoderViT(nn.Module):
                 module.require_backward_grad_sync = self.prev
         return _NoSync()
 
-    def _backward(self, pl, drecon, dpred, dlatent=None, second=None):
+    def _backward(self, pl, drecon, dpred, dlatent=None, second=None, dedge=None):
         eng = self._engine
         flat = eng.flat
         state = flat.grads_alias()
@@ -264,7 +264,7 @@ class MaskedAutoencoderViT(nn.Module):
         # contrastive view 2) backward still have to be added first
         sync = self.require_backward_grad_sync
         overlap_sync = sync and saved is None and second is None
-        eng.backward(pl, drecon, dpred_extra=dpred, accumulate=acc, sync_grads=overlap_sync, dlatent=dlatent)
+        eng.backward(pl, drecon, dpred_extra=dpred, accumulate=acc, sync_grads=overlap_sync, dlatent=dlatent, dedge=dedge)
         if second is not None and second[1] is not None:
             eng.backward(second[0], None, accumulate=True, dlatent=second[1], encoder_only=True)
         if state is not True:
@@ -360,15 +360,25 @@ class MaskedAutoencoderViT(nn.Module):
             sums = torch.empty(B * L, device=imgs.device)
             out = torch.empty(2, device=imgs.device)
             ops.masked_mse_fwd(full, imgs, mask.float().contiguous(), sums, out, eng.p)
-            return self._loss_list(out[0].clone(), pred, imgs, edge_map_weight)
+            raw_edge = None
+            if edge_map_weight != 0 or self.report_edge_loss:
+                C, V = eng.C, eng.V
+                scratch = torch.empty(ops.edge_scratch_floats(B, C, V), device=imgs.device)
+                e_tgt, resid = torch.empty(B, V, V, V, device=imgs.device), torch.empty(B, V, V, V, device=imgs.device)
+                eo = torch.empty(1, device=imgs.device)
+                ops.edge_target(imgs, eng.edge_taps, scratch, e_tgt)
+                ops.edge_loss_fwd(full.to(torch.bfloat16), e_tgt, scratch, resid, eo, B, C, V, eng.p)
+                raw_edge = eo[0].clone()
+            return self._loss_list(out[0].clone(), raw_edge, edge_map_weight)
 
-    def _loss_list(self, recon, pred, vol, edge_map_weight):
+    def _loss_list(self, recon, raw_edge, edge_map_weight):
+        """[edge_w * raw_edge + recon + percep, raw_edge, recon, percep] (model/vit_autoenc.py:231-232); ``raw_edge`` None:
+        the edge-map term was not evaluated (weight 0 and report_edge_loss off) and is reported as 0."""
         if self.perceptual_weight != 0:
             raise VitaeError("perceptual_weight != 0 needs the reference's VGG-16 checkpoint (model/ckp-399.pth, not "
                              "shipped); only the shipped default 0 is supported")
         percep = torch.zeros((), device=recon.device)
-        if edge_map_weight != 0 or self.report_edge_loss:
-            raw_edge = self.edge_loss(self.unpatchify(pred.float()), vol)      # interim torch ops, SURVEY row f-1
+        if raw_edge is not None:
             loss = edge_map_weight * raw_edge + recon + percep
         else:
             raw_edge = torch.zeros((), device=recon.device)
@@ -384,13 +394,15 @@ class MaskedAutoencoderViT(nn.Module):
         keep = self._len_keep(mask_ratio)
         if keep < 1:
             raise VitaeError(f"mask_ratio={mask_ratio} keeps no patch")
+        want_edge = edge_map_weight != 0 or self.report_edge_loss
         if torch.is_grad_enabled() and self.cls_token.requires_grad:
-            recon, pred, mask = _MAEStep.apply(self.cls_token, self, x, noise, keep)
+            recon, raw_edge, pred, mask = _MAEStep.apply(self.cls_token, self, x, noise, keep, want_edge)
         else:
-            pl = eng.forward(x, noise, keep, want_loss=True, pred_f32=self.pred_dtype == torch.float32)
+            pl = eng.forward(x, noise, keep, want_loss=True, pred_f32=self.pred_dtype == torch.float32, want_edge=want_edge)
             pl.step_id += 1
             recon, pred, mask = pl.loss_out[0].clone(), pl.pred_view(self.pred_dtype), pl.mask.clone()
-        return self._loss_list(recon, pred, x, edge_map_weight), pred, mask
+            raw_edge = pl.edge_out[0].clone() if want_edge else None
+        return self._loss_list(recon, raw_edge if want_edge else None, edge_map_weight), pred, mask
 
 
 class _ContrastiveStep(torch.autograd.Function):
@@ -399,27 +411,29 @@ class _ContrastiveStep(torch.autograd.Function):
     encoder-only backward of view 2 accumulating into the same gradient buffers.  A single node fixes that order."""
 
     @staticmethod
-    def forward(ctx, anchor, module, vol1, vol2, noise1, noise2, keep):
+    def forward(ctx, anchor, module, vol1, vol2, noise1, noise2, keep, want_edge):
         eng = module._engine
-        pl1 = eng.forward(vol1, noise1, keep, want_loss=True, pred_f32=module.pred_dtype == torch.float32)
+        pl1 = eng.forward(vol1, noise1, keep, want_loss=True, pred_f32=module.pred_dtype == torch.float32,
+                          want_edge=want_edge)
         pl2 = eng.forward_encoder_only(vol2, noise2, keep, slot=1)
         pl1.step_id += 1
         pl2.step_id += 1
-        ctx.module, ctx.pl1, ctx.pl2, ctx.ids = module, pl1, pl2, (pl1.step_id, pl2.step_id)
+        ctx.module, ctx.pl1, ctx.pl2, ctx.ids, ctx.want_edge = module, pl1, pl2, (pl1.step_id, pl2.step_id), want_edge
         ctx.set_materialize_grads(False)
         recon, mask = pl1.loss_out[0].clone(), pl1.mask.clone()
+        raw_edge = pl1.edge_out[0].clone() if want_edge else torch.zeros((), device=vol1.device)
         pred = pl1.pred_view(module.pred_dtype)
         latent1, latent2 = pl1.latent32.clone(), pl2.latent32.clone()  # [B*Ne, D], model/vit_autoenc.py:280-281
         ctx.mark_non_differentiable(mask)
-        return recon, pred, mask, latent1, latent2
+        return recon, raw_edge, pred, mask, latent1, latent2
 
     @staticmethod
-    def backward(ctx, drecon, dpred, _dmask, dlat1, dlat2):
+    def backward(ctx, drecon, dedge, dpred, _dmask, dlat1, dlat2):
         module, pl1, pl2 = ctx.module, ctx.pl1, ctx.pl2
         if (pl1.step_id, pl2.step_id) != ctx.ids:
             raise VitaeError("backward() after a later forward() of the same shape: the activation workspace was reused")
-        module._backward(pl1, drecon, dpred, dlatent=dlat1, second=(pl2, dlat2))
-        return None, None, None, None, None, None, None
+        module._backward(pl1, drecon, dpred, dlatent=dlat1, second=(pl2, dlat2), dedge=dedge if ctx.want_edge else None)
+        return None, None, None, None, None, None, None, None
 
 
 class ContrastiveMAEViT(MaskedAutoencoderViT):
@@ -478,17 +492,21 @@ class ContrastiveMAEViT(MaskedAutoencoderViT):
         keep = self._len_keep(mask_ratio)
         if keep < 1:
             raise VitaeError(f"mask_ratio={mask_ratio} keeps no patch")
+        want_edge = edge_map_weight != 0 or self.report_edge_loss
         if torch.is_grad_enabled() and self.cls_token.requires_grad:
-            recon, pred, mask, lat1, lat2 = _ContrastiveStep.apply(self.cls_token, self, x1, x2, n1, n2, keep)
+            recon, raw_edge, pred, mask, lat1, lat2 = _ContrastiveStep.apply(self.cls_token, self, x1, x2, n1, n2, keep,
+                                                                             want_edge)
         else:
-            pl1 = eng.forward(x1, n1, keep, want_loss=True, pred_f32=self.pred_dtype == torch.float32)
+            pl1 = eng.forward(x1, n1, keep, want_loss=True, pred_f32=self.pred_dtype == torch.float32, want_edge=want_edge)
             pl2 = eng.forward_encoder_only(x2, n2, keep, slot=1)
             pl1.step_id += 1
             pl2.step_id += 1
             recon, pred, mask = pl1.loss_out[0].clone(), pl1.pred_view(self.pred_dtype), pl1.mask.clone()
+            raw_edge = pl1.edge_out[0].clone() if want_edge else None
             lat1, lat2 = pl1.latent32.clone(), pl2.latent32.clone()
         p1, p2 = self.predictor(lat1), self.predictor(lat2)
-        return self._loss_list(recon, pred, x1, edge_map_weight), pred, mask, p1, p2, lat1.detach(), lat2.detach()
+        return (self._loss_list(recon, raw_edge if want_edge else None, edge_map_weight), pred, mask, p1, p2, lat1.detach(),
+                lat2.detach())
 
 
 def mae_vit_large_patch16_dec512d8b(**kwargs):

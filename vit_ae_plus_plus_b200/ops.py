@@ -333,6 +333,42 @@ def masked_mse_bwd(pred, vol, mask, mask_sum, dloss, dpred, p: int) -> None:
           "vitae_masked_mse_bwd")
 
 
+def edge_scratch_floats(B: int, C: int, V: int) -> int:
+    return _lib.load().vitae_edge_scratch_floats(B, C, V)
+
+
+def gaussian_taps(sigma: float = 2.0):
+    """The reference's 1-D taps (model/model_utils/gaussian_filter.py:5-13, incl. the linspace(-ks//2, ks//2+1, ks) quirk)
+    as a python list of fp32 values."""
+    ks = int(sigma * 5)
+    ks += 1 - ks % 2
+    ts = torch.linspace(-ks // 2, ks // 2 + 1, ks)
+    t = torch.exp(-(ts / sigma) ** 2 / 2)
+    return (t / t.sum()).tolist()
+
+
+def edge_target(vol, taps, scratch, e_tgt) -> None:
+    lib = _lib.load()
+    _req(vol, _F32, "edge volume")
+    B, C, V = vol.shape[0], vol.shape[1], vol.shape[2]
+    host = (ctypes.c_float * len(taps))(*taps)
+    check(lib.vitae_edge_target(vol.data_ptr(), ctypes.cast(host, ctypes.c_void_p), len(taps), scratch.data_ptr(),
+                                e_tgt.data_ptr(), B, C, V, _stream()), "vitae_edge_target")
+
+
+def edge_loss_fwd(pred_bf16, e_tgt, scratch, resid, loss_out, B: int, C: int, V: int, p: int) -> None:
+    lib = _lib.load()
+    _req(pred_bf16, _BF16, "edge pred")
+    check(lib.vitae_edge_loss_fwd(pred_bf16.data_ptr(), e_tgt.data_ptr(), scratch.data_ptr(), resid.data_ptr(),
+                                  loss_out.data_ptr(), B, C, V, p, _stream()), "vitae_edge_loss_fwd")
+
+
+def edge_loss_bwd(resid, scratch, upstream, dpred_bf16, B: int, C: int, V: int, p: int) -> None:
+    lib = _lib.load()
+    check(lib.vitae_edge_loss_bwd(resid.data_ptr(), scratch.data_ptr(), upstream.data_ptr(), dpred_bf16.data_ptr(), B, C, V,
+                                  p, _stream()), "vitae_edge_loss_bwd")
+
+
 def prefetch_l2(tensors) -> None:
     """Pulls the storage of up to 12 tensors (contiguous) into L2 on the current stream (include/vitae_b200.h)."""
     ts = [t for t in tensors if t is not None and t.numel() > 0]

@@ -230,7 +230,8 @@ int vitae_adamw_step(float* param, const float* grad, float* exp_avg, float* exp
  * k_fold_cross_valid_combined_brats.py:168-169.
  * ctl: device fp32[8] = {[0] loss scale, [1] growth tracker, [2] found_inf of this step, [3] 1/scale used by this
  * step, [4] unscaled global gradient L2 norm, [5] optimizer steps taken (skipped steps do not count)}.
- * vitae_optim_prepare: one pass over grad -> ctl[2..4]; then GradScaler.update on ctl[0..1] (use_scaler != 0) and
+ * vitae_optim_prepare: one pass over grad (and the optional second region grad2: parameters that live outside the main flat
+ * buffer, e.g. the contrastive predictor) -> ctl[2..4]; then GradScaler.update on ctl[0..1] (use_scaler != 0) and
  * ctl[5] += 1 unless the step is skipped.  workspace: vitae_optim_workspace_bytes() bytes.
  * vitae_adamw_flat: AdamW over [0, n) (n % 64 == 0); group_of_chunk[i >> 6] = parameter group of element i
  * (>= ngroups: frozen / padding, left untouched); hyper: HOST fp32 [ngroups][8] = {lr, beta1, beta2, eps,
@@ -238,8 +239,8 @@ int vitae_adamw_step(float* param, const float* grad, float* exp_avg, float* exp
  * shadow param_bf16 (GEMM operands) when non-NULL.  All pointers may be offset to a 64-aligned sub-range of the flat
  * buffers (group_of_chunk offset by start/64): the step can be issued layer group by layer group.  max_blocks > 0 caps the
  * grid (a step that overlaps the next forward must leave SM slots to it); 0 = default. */
-int vitae_optim_prepare(const float* grad, long long n, float* ctl, float* workspace, float growth_factor,
-                        float backoff_factor, int growth_interval, int use_scaler, void* stream);
+int vitae_optim_prepare(const float* grad, long long n, const float* grad2, long long n2, float* ctl, float* workspace,
+                        float growth_factor, float backoff_factor, int growth_interval, int use_scaler, void* stream);
 size_t vitae_optim_workspace_bytes(void);
 int vitae_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16,
                      long long n, const unsigned char* group_of_chunk, const float* hyper, int ngroups,

@@ -78,7 +78,8 @@ SIGNATURES = {
     "vitae_cast_params_bf16": (c_int, [c_void_p, c_int, c_void_p, c_longlong, c_void_p]),
     "vitae_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float,
                                  c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
-    "vitae_optim_prepare": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_float, c_float, c_int, c_int, c_void_p]),
+    "vitae_optim_prepare": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_float, c_float, c_int,
+                                    c_int, c_void_p]),
     "vitae_optim_workspace_bytes": (c_size_t, []),
     "vitae_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_int,
                                  c_void_p, c_int, c_void_p]),

@@ -563,16 +563,24 @@ extern "C" int vitae_adamw_step(float* param, const float* grad, float* exp_avg,
 
 constexpr int OPT_NORM_BLOCKS = 148 * 4;
 
-extern "C" size_t vitae_optim_workspace_bytes(void) { return OPT_NORM_BLOCKS * sizeof(float); }
+extern "C" size_t vitae_optim_workspace_bytes(void) { return 2 * OPT_NORM_BLOCKS * sizeof(float); }
 
-extern "C" int vitae_optim_prepare(const float* grad, long long n, float* ctl, float* workspace, float growth_factor,
-                                   float backoff_factor, int growth_interval, int use_scaler, void* stream) {
+extern "C" int vitae_optim_prepare(const float* grad, long long n, const float* grad2, long long n2, float* ctl,
+                                   float* workspace, float growth_factor, float backoff_factor, int growth_interval,
+                                   int use_scaler, void* stream) {
     VITAE_REQUIRE(grad && ctl && workspace && n > 0, "optim_prepare: bad arguments");
-    VITAE_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0, "optim_prepare: grad must be 16-byte aligned");
-    const int blocks = static_cast<int>(std::min<long long>(ceil_div<long long>(n, 1024), OPT_NORM_BLOCKS));
+    VITAE_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad2) & 15) == 0,
+                  "optim_prepare: grad buffers must be 16-byte aligned");
+    int blocks = static_cast<int>(std::min<long long>(ceil_div<long long>(n, 1024), OPT_NORM_BLOCKS));
     launch_kernel(grad_sqnorm_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), grad, n, workspace);
     VITAE_CHECK_LAUNCH("grad_sqnorm");
-    launch_kernel(optim_finalize_kernel, dim3(1), dim3(256), 0, as_stream(stream), workspace, blocks, ctl, growth_factor, backoff_factor, growth_interval, use_scaler);
+    if (grad2 && n2 > 0) {   // a second gradient region (parameters outside the main flat buffer) joins the same norm
+        const int blocks2 = static_cast<int>(std::min<long long>(ceil_div<long long>(n2, 1024), OPT_NORM_BLOCKS));
+        launch_kernel(grad_sqnorm_kernel, dim3(blocks2), dim3(256), 0, as_stream(stream), grad2, n2, workspace + blocks);
+        VITAE_CHECK_LAUNCH("grad_sqnorm");
+        blocks += blocks2;
+    }
+    launch_kernel(optim_finalize_kernel, dim3(1), dim3(256), 0, as_stream(stream), static_cast<const float*>(workspace), blocks, ctl, growth_factor, backoff_factor, growth_interval, use_scaler);
     VITAE_CHECK_LAUNCH("optim_finalize");
     return 0;
 }

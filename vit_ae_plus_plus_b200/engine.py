@@ -932,6 +932,9 @@ class FusedAdamW:
         self.bound: Optional[int] = None       # id of the bound optimizer
         self.bound_sig = None
         self.host_steps = 0
+        # parameters of the optimizer that live outside the engine's flat buffers (contrastive predictor)
+        self.ex_total, self.ex_items, self.ex_ptrs, self.ex_steps = 0, [], set(), []
+        self.ex_p32 = self.ex_g32 = self.ex_m = self.ex_v = self.ex_group_map = None
 
     @staticmethod
     def supports(optimizer) -> bool:
@@ -942,7 +945,9 @@ class FusedAdamW:
 
     def bind(self, optimizer) -> bool:
         """Maps the optimizer's parameter groups onto 64-element chunks of the flat buffer and adopts / installs its
-        state.  Returns False when a parameter of the optimizer is not one of this engine's flat views."""
+        state.  Parameters of the optimizer that are not flat views of this engine (the contrastive predictor) are moved
+        into a second, small flat buffer of their own ("extras": their ``.data`` is re-pointed, values kept) and updated by
+        the same kernel.  Returns False when the optimizer cannot be driven by the fused step."""
         flat = self.eng.flat
         by_ptr = {flat.v32[n].data_ptr(): n for n in flat.order}
         sig = tuple(tuple(p.data_ptr() for p in g["params"]) for g in optimizer.param_groups)
@@ -950,13 +955,19 @@ class FusedAdamW:
             return True
         if len(optimizer.param_groups) > 8:
             return False
+        extras = [(gi, p) for gi, g in enumerate(optimizer.param_groups) for p in g["params"]
+                  if p.data_ptr() not in by_ptr and p.data_ptr() not in self.ex_ptrs]
+        if any((not p.is_cuda) or p.dtype != _F32 or p.device != flat.p32.device for _, p in extras):
+            return False
+        if extras or self.ex_total:
+            self._build_extras(optimizer, by_ptr)
         gm = torch.full((flat.total // _ALIGN,), 255, dtype=torch.uint8)
         steps = []
         for gi, group in enumerate(optimizer.param_groups):
             for p in group["params"]:
                 n = by_ptr.get(p.data_ptr())
                 if n is None:
-                    return False
+                    continue            # an extra: handled by _build_extras
                 o, k, shp = flat.offsets[n]
                 gm[o // _ALIGN:(o + k + _ALIGN - 1) // _ALIGN] = gi
                 st = optimizer.state.get(p)
@@ -966,14 +977,49 @@ class FusedAdamW:
                         mv.copy_(st["exp_avg"]); vv.copy_(st["exp_avg_sq"])
                     steps.append(float(st["step"]))
                 optimizer.state[p] = {"step": torch.tensor(0.0), "exp_avg": mv, "exp_avg_sq": vv}
+        steps += self.ex_steps
         self.group_map.copy_(gm)
         self.host_steps = int(max(steps)) if steps else 0
         self.ctl[5] = float(self.host_steps)
         for group in optimizer.param_groups:
             for p in group["params"]:
                 optimizer.state[p]["step"].fill_(float(self.host_steps))
-        self.bound, self.bound_sig = id(optimizer), sig
+        self.bound = id(optimizer)
+        self.bound_sig = tuple(tuple(p.data_ptr() for p in g["params"]) for g in optimizer.param_groups)
         return True
+
+    def _build_extras(self, optimizer, by_ptr) -> None:
+        """(Re)builds the extras flat buffers from every optimizer parameter that is not an engine view."""
+        dev = self.eng.device
+        items, off = [], 0
+        for gi, group in enumerate(optimizer.param_groups):
+            for p in group["params"]:
+                if p.data_ptr() in by_ptr:
+                    continue
+                items.append((gi, p, off))
+                off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        total = off
+        p32, g32 = torch.zeros(total, dtype=_F32, device=dev), torch.zeros(total, dtype=_F32, device=dev)
+        m, v = torch.zeros(total, dtype=_F32, device=dev), torch.zeros(total, dtype=_F32, device=dev)
+        gm = torch.full((max(1, total // _ALIGN),), 255, dtype=torch.uint8)
+        self.ex_steps, self.ex_items, self.ex_ptrs = [], [], set()
+        with torch.no_grad():
+            for gi, p, o in items:
+                k, shp = p.numel(), p.shape
+                pv = p32[o:o + k].view(shp)
+                pv.copy_(p.data)
+                st = optimizer.state.get(p)
+                mv, vv = m[o:o + k].view(shp), v[o:o + k].view(shp)
+                if st and "exp_avg" in st:
+                    mv.copy_(st["exp_avg"]); vv.copy_(st["exp_avg_sq"])
+                    self.ex_steps.append(float(st["step"]))
+                p.data = pv
+                optimizer.state[p] = {"step": torch.tensor(0.0), "exp_avg": mv, "exp_avg_sq": vv}
+                gm[o // _ALIGN:(o + k + _ALIGN - 1) // _ALIGN] = gi
+                self.ex_items.append((p, g32[o:o + k].view(shp)))
+                self.ex_ptrs.add(pv.data_ptr())
+        self.ex_p32, self.ex_g32, self.ex_m, self.ex_v, self.ex_total = p32, g32, m, v, total
+        self.ex_group_map = gm.to(dev)
 
     def step(self, optimizer, scaler=None, overlap: bool = False) -> torch.Tensor:
         """One optimizer step on the gradients currently in the flat gradient buffer; returns the (unscaled) global
@@ -989,9 +1035,19 @@ class FusedAdamW:
         gf, bf, gi = (scaler.get_growth_factor(), scaler.get_backoff_factor(), scaler.get_growth_interval()) \
             if use_scaler else (2.0, 0.5, 2000)
         eng.wait_params()
-        ops.optim_prepare(flat.g32, flat.total, self.ctl, self.ws, gf, bf, gi, use_scaler)
+        if self.ex_total:      # gradients of the extras come from torch autograd: gather them into their flat buffer
+            have = [(dst, p.grad) for p, dst in self.ex_items if p.grad is not None]
+            if len(have) != len(self.ex_items):
+                self.ex_g32.zero_()
+            if have:
+                torch._foreach_copy_([d for d, _ in have], [g for _, g in have])
+        ops.optim_prepare(flat.g32, flat.total, self.ctl, self.ws, gf, bf, gi, use_scaler,
+                          grad2=self.ex_g32 if self.ex_total else None, n2=self.ex_total)
         rows = [(g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"]) for g in optimizer.param_groups]
         norm = self.ctl[4].clone()
+        if self.ex_total:
+            ops.adamw_flat(self.ex_p32, self.ex_g32, self.ex_m, self.ex_v, None, self.ex_total, self.ex_group_map, rows,
+                           self.ctl)
         if overlap:
             main = torch.cuda.current_stream()
             ev = torch.cuda.Event()

@@ -403,11 +403,11 @@ def optim_workspace_bytes() -> int:
 
 
 def optim_prepare(grad, n: int, ctl, workspace, growth_factor: float, backoff_factor: float, growth_interval: int,
-                  use_scaler: bool) -> None:
+                  use_scaler: bool, grad2=None, n2: int = 0) -> None:
     lib = _lib.load()
     _req(grad, _F32, "optim grad"); _req(ctl, _F32, "optim ctl")
-    check(lib.vitae_optim_prepare(grad.data_ptr(), n, ctl.data_ptr(), workspace.data_ptr(), growth_factor, backoff_factor,
-                                  growth_interval, int(use_scaler), _stream()), "vitae_optim_prepare")
+    check(lib.vitae_optim_prepare(grad.data_ptr(), n, _ptr(grad2), n2, ctl.data_ptr(), workspace.data_ptr(), growth_factor,
+                                  backoff_factor, growth_interval, int(use_scaler), _stream()), "vitae_optim_prepare")
 
 
 def adamw_flat(param, grad, exp_avg, exp_avg_sq, param_bf16, n: int, group_of_chunk, hyper_rows, ctl, start: int = 0,

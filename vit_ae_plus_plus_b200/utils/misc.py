@@ -234,11 +234,14 @@ class NativeScalerWithGradNormCount:
         from ..engine import FusedAdamW
         if not FusedAdamW.supports(optimizer):
             return None
-        try:
-            p0 = optimizer.param_groups[0]["params"][0]
-        except (IndexError, KeyError):
-            return None
-        ref = getattr(p0, "_vitae_engine", None)
+        ref = None
+        for group in optimizer.param_groups:       # the first parameter that belongs to one of this package's engines
+            for p in group["params"]:
+                ref = getattr(p, "_vitae_engine", None)
+                if ref is not None:
+                    break
+            if ref is not None:
+                break
         eng = ref() if ref is not None else None
         if eng is None or not eng.flat.still_aliased():
             return None

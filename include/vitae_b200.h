@@ -127,6 +127,26 @@ int vitae_colsum(const void* in_bf16, const float* in_f32, int rows, int cols, i
                  void* workspace, void* stream);
 size_t vitae_colsum_workspace_bytes(int rows, int cols);
 
+/* All column reductions of one transformer block's backward in one launch: each job is a plain column sum
+ * (x == NULL: out0[c] = sum_r a[r*ld + c], a bf16 or fp32) or a LayerNorm affine-gradient reduction (out0 = dgamma =
+ * sum_r dy*xhat, out1 = dbeta = sum_r dy, with dy = a (+ a2) and xhat = (x - mean) * rstd; x fp32 [rows, cols]).  Up to 6
+ * jobs over matrices with the same number of rows; jobs is a HOST array read during the call; accumulate adds into the
+ * outputs.  workspace: vitae_block_colreduce_workspace_bytes(rows, sum of the jobs' cols each rounded up to 256) bytes,
+ * ZERO-FILLED before its first use (ticket counters, self-resetting), not shared by concurrent calls.  Deterministic. */
+typedef struct vitae_col_job {
+    const void* a;
+    const float* a2;
+    const float* x;
+    const float* mean;
+    const float* rstd;
+    float* out0;
+    float* out1;
+    int32_t cols, ld, a_is_bf16, reserved;
+} vitae_col_job;
+int vitae_block_colreduce(const vitae_col_job* jobs, int njobs, int rows, int accumulate, void* workspace,
+                          size_t workspace_bytes, void* stream);
+size_t vitae_block_colreduce_workspace_bytes(int rows, int total_cols_padded);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Fused multi-head self-attention, flash-style (scores never leave the SM) -- model/vit.py:112-121:
  *   qkv bf16 [B, N, 3, H, hd] (the qkv Linear output as-is), out bf16 [B, N, H*hd], lse fp32 [B, H, N].

@@ -37,6 +37,13 @@ class GemmEpilogue(Structure):
     ]
 
 
+class ColJob(Structure):
+    # mirrors struct vitae_col_job (include/vitae_b200.h)
+    _fields_ = [("a", c_void_p), ("a2", c_void_p), ("x", c_void_p), ("mean", c_void_p), ("rstd", c_void_p),
+                ("out0", c_void_p), ("out1", c_void_p), ("cols", c_int32), ("ld", c_int32), ("a_is_bf16", c_int32),
+                ("reserved", c_int32)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/vitae_b200.h
 SIGNATURES = {
     "vitae_abi_version": (c_int, []),
@@ -56,6 +63,8 @@ SIGNATURES = {
     "vitae_layernorm_param_grads_workspace_bytes": (c_size_t, [c_int, c_int]),
     "vitae_layernorm_bwd_blocks": (c_int, [c_int]),
     "vitae_reduce_partials": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "vitae_block_colreduce": (c_int, [POINTER(ColJob), c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "vitae_block_colreduce_workspace_bytes": (c_size_t, [c_int, c_int]),
     "vitae_colsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "vitae_colsum_workspace_bytes": (c_size_t, [c_int, c_int]),
     "vitae_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),

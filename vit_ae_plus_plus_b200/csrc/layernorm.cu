@@ -1,6 +1,8 @@
 // LayerNorm forward / backward (one warp per row, warp-shuffle reductions, float4 I/O) and the column-sum
 // reduction used for bias / LayerNorm-affine gradients.  HBM-bound kernels.
 #include "common.h"
+#include <string.h>
+
 #include "ptx.cuh"
 
 namespace vitae {
@@ -331,9 +333,188 @@ colsum_kernel(const T* __restrict__ in, int rows, int cols, int ld, float* __res
     if (threadIdx.x == 0) counters[blockIdx.x] = 0u;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// All column reductions of one transformer block's backward in ONE launch (they used to be six: two bias column sums,
+// two LayerNorm affine-gradient reductions, two residual-gradient column sums; each a few microseconds of pure latency).
+// A job is either a plain column sum of a bf16 / fp32 matrix (out0[c] = sum_r a[r, c]) or a LayerNorm reduction
+// (out0 = dgamma = sum_r dy * xhat, out1 = dbeta = sum_r dy with dy = a (+ a2)).  Grid = (256-column strips of all jobs,
+// row slices); lane = 8 consecutive columns, warp = one row, the 8 warps stride the rows of the slice; slices are added in
+// fixed order by the last block of a strip to arrive (ticket) -> deterministic.
+// ---------------------------------------------------------------------------------------------------------------
+struct ColJob {
+    const void* a;        // bf16 or fp32 [rows, ld]
+    const float* a2;      // optional second upstream gradient (fp32, LayerNorm jobs)
+    const float* x;       // LayerNorm job: forward input fp32 [rows, cols]; nullptr: plain column sum
+    const float* mean;
+    const float* rstd;
+    float* out0;
+    float* out1;
+    int cols, ld, a_is_bf16, strip0;
+};
+struct ColJobs {
+    ColJob j[6];
+    int n, rows, rows_per_slice, accumulate, total_cols;   // total_cols = 256 * total strips
+};
+
+__device__ __forceinline__ void col_load8(const ColJob& jb, size_t off, float (&v)[8]) {
+    if (jb.a_is_bf16) cs_load8<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(jb.a) + off, v);
+    else cs_load8<float>(static_cast<const float*>(jb.a) + off, v);
+}
+
+__global__ void __launch_bounds__(256)
+block_colreduce_kernel(const ColJobs jobs, float* __restrict__ partials, unsigned int* __restrict__ counters) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float red[2][8][CS_COLS + 8];
+    __shared__ unsigned int ticket_sh;
+    int ji = 0;
+#pragma unroll
+    for (int k = 1; k < 6; ++k)
+        if (k < jobs.n && static_cast<int>(blockIdx.x) >= jobs.j[k].strip0) ji = k;
+    const ColJob& jb = jobs.j[ji];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = (blockIdx.x - jb.strip0) * CS_COLS + lane * 8;
+    const int r0 = blockIdx.y * jobs.rows_per_slice, r1 = min(jobs.rows, r0 + jobs.rows_per_slice);
+    const bool ln = jb.x != nullptr;
+    float acc0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, acc1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c < jb.cols) {
+        if (!ln) {
+            int r = r0 + warp;
+            for (; r + 24 < r1; r += 32) {
+                float v0[8], v1[8], v2[8], v3[8];
+                col_load8(jb, static_cast<size_t>(r) * jb.ld + c, v0);
+                col_load8(jb, static_cast<size_t>(r + 8) * jb.ld + c, v1);
+                col_load8(jb, static_cast<size_t>(r + 16) * jb.ld + c, v2);
+                col_load8(jb, static_cast<size_t>(r + 24) * jb.ld + c, v3);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc0[i] += (v0[i] + v1[i]) + (v2[i] + v3[i]);
+            }
+            for (; r < r1; r += 8) {
+                float v0[8];
+                col_load8(jb, static_cast<size_t>(r) * jb.ld + c, v0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc0[i] += v0[i];
+            }
+        } else {
+#pragma unroll 2
+            for (int r = r0 + warp; r < r1; r += 8) {
+                float d[8], xv[8];
+                col_load8(jb, static_cast<size_t>(r) * jb.ld + c, d);
+                cs_load8<float>(jb.x + static_cast<size_t>(r) * jb.cols + c, xv);
+                if (jb.a2) {
+                    float e[8];
+                    cs_load8<float>(jb.a2 + static_cast<size_t>(r) * jb.cols + c, e);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) d[i] += e[i];
+                }
+                const float mu = jb.mean[r], rs = jb.rstd[r];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    acc0[i] += d[i] * ((xv[i] - mu) * rs);
+                    acc1[i] += d[i];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        red[0][warp][lane * 8 + i] = acc0[i];
+        red[1][warp][lane * 8 + i] = acc1[i];
+    }
+    __syncthreads();
+    const int col = (blockIdx.x - jb.strip0) * CS_COLS + threadIdx.x;     // one column per thread from here on
+    const size_t gcol = static_cast<size_t>(blockIdx.x) * CS_COLS + threadIdx.x;
+    const int nsl = gridDim.y;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        s0 += red[0][w][threadIdx.x];
+        s1 += red[1][w][threadIdx.x];
+    }
+    if (nsl == 1) {
+        if (col < jb.cols) {
+            jb.out0[col] = jobs.accumulate ? jb.out0[col] + s0 : s0;
+            if (ln && jb.out1) jb.out1[col] = jobs.accumulate ? jb.out1[col] + s1 : s1;
+        }
+        return;
+    }
+    partials[(static_cast<size_t>(0) * nsl + blockIdx.y) * jobs.total_cols + gcol] = s0;
+    if (ln) partials[(static_cast<size_t>(1) * nsl + blockIdx.y) * jobs.total_cols + gcol] = s1;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) ticket_sh = atomicAdd(&counters[blockIdx.x], 1u);
+    __syncthreads();
+    if (ticket_sh != static_cast<unsigned int>(nsl - 1)) return;
+    __threadfence();
+    if (col < jb.cols) {
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            float* out = o == 0 ? jb.out0 : jb.out1;
+            if ((o == 1 && !ln) || out == nullptr) continue;
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;   // four loads in flight, fixed association
+            const float* pp = partials + static_cast<size_t>(o) * nsl * jobs.total_cols + gcol;
+            int y = 0;
+            for (; y + 4 <= nsl; y += 4) {
+                t0 += __ldcg(pp + static_cast<size_t>(y) * jobs.total_cols);
+                t1 += __ldcg(pp + static_cast<size_t>(y + 1) * jobs.total_cols);
+                t2 += __ldcg(pp + static_cast<size_t>(y + 2) * jobs.total_cols);
+                t3 += __ldcg(pp + static_cast<size_t>(y + 3) * jobs.total_cols);
+            }
+            for (; y < nsl; ++y) t0 += __ldcg(pp + static_cast<size_t>(y) * jobs.total_cols);
+            const float t = (t0 + t1) + (t2 + t3);
+            out[col] = jobs.accumulate ? out[col] + t : t;
+        }
+    }
+    if (threadIdx.x == 0) counters[blockIdx.x] = 0u;
+}
+
 }  // namespace vitae
 
 using namespace vitae;
+
+// One launch for up to 6 column-reduction jobs over matrices with the same number of rows (see block_colreduce_kernel).
+// jobs: HOST array of vitae_col_job, read during the call.  workspace: vitae_block_colreduce_workspace_bytes(...) bytes,
+// zero-filled before first use (ticket counters, self-resetting), not shared by concurrent calls.
+static inline int bcr_slices(int rows, int strips) {
+    int s = std::max(1, (3 * 148) / std::max(1, strips));
+    s = std::min(s, std::max(1, rows / 32));
+    return std::min(s, 16);
+}
+
+extern "C" size_t vitae_block_colreduce_workspace_bytes(int rows, int total_cols_padded) {
+    const int strips = total_cols_padded / CS_COLS;
+    return 4096 + static_cast<size_t>(2) * bcr_slices(rows, strips) * total_cols_padded * sizeof(float);
+}
+
+extern "C" int vitae_block_colreduce(const vitae_col_job* jobs, int njobs, int rows, int accumulate, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+    VITAE_REQUIRE(jobs && njobs > 0 && njobs <= 6 && rows > 0 && workspace, "block_colreduce: bad arguments");
+    ColJobs js;
+    memset(&js, 0, sizeof(js));
+    int strips = 0;
+    for (int i = 0; i < njobs; ++i) {
+        const vitae_col_job& j = jobs[i];
+        VITAE_REQUIRE(j.a && j.out0 && j.cols > 0 && j.cols % 8 == 0 && j.ld % 8 == 0 && j.ld >= j.cols,
+                      "block_colreduce: job %d: cols / ld must be multiples of 8", i);
+        VITAE_REQUIRE(!j.x || (j.mean && j.rstd), "block_colreduce: job %d: LayerNorm job needs mean / rstd", i);
+        ColJob& d = js.j[i];
+        d.a = j.a; d.a2 = j.a2; d.x = j.x; d.mean = j.mean; d.rstd = j.rstd; d.out0 = j.out0; d.out1 = j.out1;
+        d.cols = j.cols; d.ld = j.ld; d.a_is_bf16 = j.a_is_bf16; d.strip0 = strips;
+        strips += ceil_div(j.cols, CS_COLS);
+    }
+    VITAE_REQUIRE(strips <= 1000, "block_colreduce: too many columns");
+    js.n = njobs; js.rows = rows; js.accumulate = accumulate; js.total_cols = strips * CS_COLS;
+    const int slices = bcr_slices(rows, strips);
+    js.rows_per_slice = ceil_div(rows, slices);
+    const int eff = ceil_div(rows, js.rows_per_slice);
+    VITAE_REQUIRE(workspace_bytes >= 4096 + static_cast<size_t>(2) * eff * js.total_cols * sizeof(float),
+                  "block_colreduce: workspace too small");
+    auto* counters = static_cast<unsigned int*>(workspace);
+    auto* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 4096);
+    launch_kernel(block_colreduce_kernel, dim3(strips, eff), dim3(256), 0, as_stream(stream), js, partials, counters);
+    VITAE_CHECK_LAUNCH("block_colreduce");
+    return 0;
+}
 
 static inline int ln_vec_class(int D) {
     const int v = ceil_div(D, 128);

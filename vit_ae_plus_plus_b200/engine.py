@@ -201,6 +201,7 @@ class _GraphSlot:
         self.calls = 0
 
 
+RING = 4                  # depth of the buffer rings shared between the two backward lanes (MAEPlan)
 MAX_INPUT_ADDRESSES = 4   # input-volume addresses that get their own (zero-copy) graphs; others are copied (below)
 
 
@@ -266,12 +267,18 @@ class MAEPlan:
         Hmax = max(eng.enc.hidden, eng.dec.hidden)
         self.dloss = a.new((1,), _F32)
         self.dpred = a.new((B, self.Nd, P), _BF16)
-        self.dres = [a.new((Mmax * Dmax,), _F32), a.new((Mmax * Dmax,), _F32)]
+        # rings of RING buffers: the side lane reads them (weight-gradient GEMMs, the per-block column reductions) after the
+        # main lane has moved on; with 4 the main lane only waits for side work issued two blocks earlier
+        self.dres = [a.new((Mmax * Dmax,), _F32) for _ in range(RING)]
         # buffers read by the side lane are double-buffered so that the main lane never waits for recent side work
-        self.dres16 = [a.new((Mmax * Dmax,), _BF16), a.new((Mmax * Dmax,), _BF16)]
+        self.dres16 = [a.new((Mmax * Dmax,), _BF16) for _ in range(RING)]
         self.d_d = a.new((Mmax * Dmax,), _BF16)
         # LayerNorm-backward inputs: read again by the side lane (affine-gradient reductions), so two alternate
-        self.d_ln = [a.new((Mmax * Dmax,), _BF16), a.new((Mmax * Dmax,), _BF16)]
+        self.d_ln = [a.new((Mmax * Dmax,), _BF16) for _ in range(RING)]
+        bcr = max(ops.block_colreduce_workspace_bytes(m, [st.hidden, 3 * st.dim, st.dim, st.dim, st.dim, st.dim])
+                  for m, st in ((self.Me, eng.enc), (self.Md, eng.dec)))
+        self.bcr_ws = torch.zeros(bcr, dtype=torch.uint8, device=dev)   # zero-filled: ticket counters (side lane only)
+        a.nbytes += bcr
         self.d_hid = [a.new((Mmax * Hmax,), _BF16), a.new((Mmax * Hmax,), _BF16)]
         self.dqkv = [a.new((Mmax * 3 * Dmax,), _BF16), a.new((Mmax * 3 * Dmax,), _BF16)]
         self.delta = a.new((B * max(eng.enc.heads * self.Ne, eng.dec.heads * self.Nd),), _F32)
@@ -807,16 +814,17 @@ class MAEEngine:
     def _ln_in(self, pl: MAEPlan, M: int, D: int) -> torch.Tensor:
         """Buffer for the input gradient (dy) of the NEXT _ln_bwd call; the side lane reads it after the main lane has
         moved on, so main waits here only for the side reader of two calls ago."""
-        k = pl.ln_calls & 1
+        k = pl.ln_calls % RING
         self.lanes.before_write(("d_ln", k))
         return pl.d_ln[k][:M * D].view(M, D)
 
     def _ln_bwd(self, pl: MAEPlan, dy: torch.Tensor, x: torch.Tensor, name: str, mean, rstd, dx_in_idx: Optional[int],
-                out_idx: int, M: int, D: int, acc: bool, bias_name: Optional[str], dy2: Optional[torch.Tensor] = None) -> int:
+                out_idx: int, M: int, D: int, acc: bool, bias_name: Optional[str], dy2: Optional[torch.Tensor] = None,
+                jobs: Optional[list] = None, reads: Optional[list] = None) -> int:
         """LayerNorm backward.  Main lane (critical path): dres[out_idx] = (dres[dx_in_idx] if given) + LN'(dy), plus its
         bf16 copy dres16[out_idx].  Side lane: the column reductions -- affine gradients and ``bias_name`` (the bias whose
         gradient is the column sum of the new residual gradient).  ``dy`` must come from _ln_in().  Returns out_idx."""
-        k = pl.ln_calls & 1
+        k = pl.ln_calls % RING
         pl.ln_calls += 1
         dx_in = None if dx_in_idx is None else pl.dres[dx_in_idx][:M * D].view(M, D)
         dx_out = pl.dres[out_idx][:M * D].view(M, D)
@@ -824,6 +832,13 @@ class MAEEngine:
         self.lanes.before_write(("dres", out_idx), ("dres16", out_idx))
         ops.layernorm_bwd(dy, x, self._p(f"{name}.weight"), mean, rstd, dx_in, dx_out, dx16, dy2=dy2)
         gb = self._g(bias_name) if bias_name is not None else None
+        if jobs is not None:       # deferred: the caller launches one column-reduction kernel for the whole block
+            jobs.append(ops.col_job(dy, self._g(f"{name}.weight"), x=x, mean=mean, rstd=rstd, a2=dy2,
+                                    out1=self._g(f"{name}.bias"), cols=D))
+            if gb is not None:
+                jobs.append(ops.col_job(dx_out, gb, cols=D))
+            reads.extend([("d_ln", k), ("dres", out_idx)])
+            return out_idx
 
         def side():
             ops.layernorm_param_grads(dy, x, mean, rstd, dx_out if gb is not None else None, pl.ln_ws,
@@ -858,16 +873,20 @@ class MAEEngine:
             ops.gemm(dres16, self._w(f"{pre}.mlp.fc2.weight"), M, hid, D, b_mn_major=True, dgelu_src=b.pre,
                      out_bf16=d_hid, workspace=wsm)
 
+            # the six column reductions of this block (two bias sums, two LayerNorm affine gradients, two residual sums)
+            # are collected and run as ONE side-lane kernel at the end of the block
+            jobs = [ops.col_job(d_hid, self._g(f"{pre}.mlp.fc1.bias"), cols=hid)]
+            job_reads = [("d_hid", hb), ("dqkv", hb)]
+
             def side_fc1(d_hid=d_hid, b=b, pre=pre):
                 ops.gemm(d_hid, b.ln2, hid, D, M, a_mn_major=True, b_mn_major=True,
                          out_f32=self._g(f"{pre}.mlp.fc1.weight"), accumulate=acc, workspace=wss)
-                ops.colsum(d_hid, M, hid, self._g(f"{pre}.mlp.fc1.bias"), cws, accumulate=acc)
             self._side(side_fc1, reads=(("d_hid", hb),))
             d_ln = self._ln_in(pl, M, D)
             ops.gemm(d_hid, self._w(f"{pre}.mlp.fc1.weight"), M, D, hid, b_mn_major=True, out_bf16=d_ln, workspace=wsm)
-            nxt = cur ^ 1
+            nxt = (cur + 1) % RING
             self._ln_bwd(pl, d_ln, b.xmid, f"{pre}.norm2", b.mean2, b.rstd2, cur, nxt, M, D, acc,
-                         f"{pre}.attn.proj.bias")
+                         f"{pre}.attn.proj.bias", jobs=jobs, reads=job_reads)
             cur = nxt
             dres16 = pl.dres16[cur][:M * D].view(M, D)
             # xmid = x_in + proj(attn(qkv(ln1))) + bp
@@ -878,17 +897,20 @@ class MAEEngine:
             lanes.before_write(("dqkv", hb))
             ops.attention_bwd(b.qkv, b.o, d_d, b.lse, delta, dqkv, B, N, H, hd, scale)
 
+            jobs.append(ops.col_job(dqkv, self._g(f"{pre}.attn.qkv.bias"), cols=3 * D))
+
             def side_qkv(dqkv=dqkv, b=b, pre=pre):
                 ops.gemm(dqkv, b.ln1, 3 * D, D, M, a_mn_major=True, b_mn_major=True,
                          out_f32=self._g(f"{pre}.attn.qkv.weight"), accumulate=acc, workspace=wss)
-                ops.colsum(dqkv, M, 3 * D, self._g(f"{pre}.attn.qkv.bias"), cws, accumulate=acc)
             self._side(side_qkv, reads=(("dqkv", hb),))
             d_ln = self._ln_in(pl, M, D)
             ops.gemm(dqkv, self._w(f"{pre}.attn.qkv.weight"), M, D, 3 * D, b_mn_major=True, out_bf16=d_ln, workspace=wsm)
-            nxt = cur ^ 1
+            nxt = (cur + 1) % RING
             below = f"{st.prefix}.{i - 1}.mlp.fc2.bias" if i > 0 else None
-            self._ln_bwd(pl, d_ln, x_in, f"{pre}.norm1", b.mean1, b.rstd1, cur, nxt, M, D, acc, below)
+            self._ln_bwd(pl, d_ln, x_in, f"{pre}.norm1", b.mean1, b.rstd1, cur, nxt, M, D, acc, below, jobs=jobs,
+                         reads=job_reads)
             cur = nxt
+            self._side(lambda jobs=jobs: ops.block_colreduce(jobs, M, pl.bcr_ws, accumulate=acc), reads=tuple(job_reads))
         return cur
 
     # ------------------------------------------------------------------------------------------------ data parallel

@@ -238,6 +238,27 @@ def layernorm_param_grads(dy, x, mean, rstd, dx_out, workspace, dgamma=None, dbe
                                           D, _stream()), "vitae_layernorm_param_grads")
 
 
+def col_job(a, out0, *, x=None, mean=None, rstd=None, a2=None, out1=None, cols: Optional[int] = None,
+            ld: Optional[int] = None):
+    """One job of block_colreduce: plain column sum of ``a`` [rows, cols] (bf16 / fp32) into out0, or, with x / mean / rstd,
+    the LayerNorm affine gradients (out0 = dgamma, out1 = dbeta) for the upstream gradient a (+ a2)."""
+    cols = a.shape[-1] if cols is None else cols
+    return _lib.ColJob(a.data_ptr(), _ptr(a2), _ptr(x), _ptr(mean), _ptr(rstd), out0.data_ptr(), _ptr(out1), cols,
+                       cols if ld is None else ld, int(a.dtype == _BF16), 0)
+
+
+def block_colreduce_workspace_bytes(rows: int, cols_list) -> int:
+    return _lib.load().vitae_block_colreduce_workspace_bytes(rows, sum((c + 255) // 256 * 256 for c in cols_list))
+
+
+def block_colreduce(jobs, rows: int, workspace, accumulate: bool = False) -> None:
+    """All column reductions of one block's backward in one launch (include/vitae_b200.h)."""
+    lib = _lib.load()
+    arr = (_lib.ColJob * len(jobs))(*jobs)
+    check(lib.vitae_block_colreduce(arr, len(jobs), rows, int(accumulate), workspace.data_ptr(),
+                                    workspace.numel() * workspace.element_size(), _stream()), "vitae_block_colreduce")
+
+
 def colsum(inp, rows: int, cols: int, out, workspace, accumulate: bool = False, ld: Optional[int] = None) -> None:
     """workspace: uint8 tensor of >= colsum_workspace_bytes(rows, cols) bytes, zero-filled at allocation (see header)."""
     lib = _lib.load()

@@ -308,8 +308,18 @@ def run_ours(a):
         torch.cuda.synchronize()
         gemm_ms = e0.elapsed_time(e1) / reps
         achieved = rec.flops / (gemm_ms / 1e3) / 1e12
+        # DRAM traffic of the same launch set from the committed ncu pass (profiles/): measured under ncu (cold caches per
+        # launch), only reported for the workload it was taken on
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01c_gemm_dram_traffic.json")))
+            if a.workload == "vit_base_128" and B == 4 and abs(a.mask_ratio - 0.75) < 1e-9 and tj["gemm_launches"] == len(rec.calls):
+                traffic = tj["gemm_dram_bytes"]
+        except (OSError, KeyError, ValueError):
+            pass
         roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": achieved, "peak": peak_tf,
-                    "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                    "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                    "traffic_note": "bytes per step over the same launches, ncu dram__bytes_read+write (profiles/r01c_gemm_dram_traffic.json)",
                     "launches_per_step": len(rec.calls), "avg_launch_us": 1e3 * gemm_ms / len(rec.calls),
                     "gemm_ms_per_step": gemm_ms, "gemm_flops_per_step": rec.flops, "peak_source": peak_src}
 

@@ -384,6 +384,53 @@ def contrastive_loss(p1, p2, z1, z2, contr_weight: float):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# Encoder-only feature extraction -- model/vit.py:265-284 (VisionTransformer3D.forward_features),
+# the model the k-fold scripts load the MAE checkpoint into (k_fold_cross_valid_combined_brats.py:219-245)
+# ----------------------------------------------------------------------------------------------------------------
+def vit_param_names(cfg, global_pool: bool):
+    """state_dict keys of VisionTransformer3D(embed_dim/depth/heads of cfg): the MAE encoder's keys + the head (+ fc_norm
+    instead of norm with global_pool, model/vit.py:219-222)."""
+    names = ["cls_token", "pos_embed", "patch_embed.proj.weight", "patch_embed.proj.bias"]
+    for i in range(cfg["depth"]):
+        for n in ("norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight", "attn.proj.bias",
+                  "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias"):
+            names.append(f"blocks.{i}.{n}")
+    names += ["fc_norm.weight", "fc_norm.bias"] if global_pool else ["norm.weight", "norm.bias"]
+    return names + ["head.weight", "head.bias"]
+
+
+def init_vit_params(cfg, num_classes: int, global_pool: bool, seed: int = 0, perturb: float = 0.02) -> Params:
+    """Encoder parameters as init_params() produces them (what a pre-trained MAE checkpoint carries) + head / fc_norm."""
+    P = init_params(cfg, seed)
+    gen = torch.Generator().manual_seed(seed + 4242)
+    D = cfg["embed_dim"]
+    out = {k: v for k, v in P.items() if k in set(vit_param_names(cfg, global_pool))}
+    if global_pool:
+        out["fc_norm.weight"] = 1.0 + perturb * torch.randn(D, generator=gen)
+        out["fc_norm.bias"] = perturb * torch.randn(D, generator=gen)
+    out["head.weight"] = 0.02 * torch.randn(num_classes, D, generator=gen)
+    out["head.bias"] = perturb * torch.randn(num_classes, generator=gen)
+    return out
+
+
+def vit_forward_features(x, P: Params, cfg, global_pool: bool):
+    # model/vit.py:265-284: all patches (no masking), cls + pos, blocks, then mean-pool + fc_norm or norm + cls row
+    t = patch_embed(x, P["patch_embed.proj.weight"], P["patch_embed.proj.bias"])
+    t = torch.cat([P["cls_token"].expand(t.shape[0], -1, -1), t], dim=1) + P["pos_embed"]
+    for i in range(cfg["depth"]):
+        t = block(t, P, f"blocks.{i}", cfg["num_heads"])
+    D = t.shape[-1]
+    if global_pool:
+        return F.layer_norm(t[:, 1:, :].mean(dim=1), (D,), P["fc_norm.weight"], P["fc_norm.bias"], LN_EPS)
+    return F.layer_norm(t, (D,), P["norm.weight"], P["norm.bias"], LN_EPS)[:, 0]
+
+
+def vit_forward(x, P: Params, cfg, global_pool: bool):
+    # model/vit.py:286-297 (no distillation head)
+    return F.linear(vit_forward_features(x, P, cfg, global_pool), P["head.weight"], P["head.bias"])
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # Optimizer grouping + AdamW as built at the call site (k_fold_cross_valid_combined_brats.py:168-169)
 # ----------------------------------------------------------------------------------------------------------------
 def weight_decay_groups(named_params, weight_decay: float):

@@ -121,3 +121,16 @@ def build_reference_model(cfg: dict, contrastive: bool = False):
     finally:
         torch.load = real
     return m
+
+
+def build_reference_vit(cfg: dict, num_classes: int, global_pool: bool):
+    """The reference's VisionTransformer3D as model_factory.get_models('vit', args) builds it (model/model_factory.py:19-22),
+    with the encoder geometry of ``cfg``."""
+    from functools import partial
+    load_reference()
+    import importlib
+    vit = importlib.import_module("model.vit")
+    return vit.VisionTransformer3D(volume_size=cfg["volume_size"], in_chans=cfg["in_chans"], num_classes=num_classes,
+                                   patch_size=cfg["patch_size"], embed_dim=cfg["embed_dim"], depth=cfg["depth"],
+                                   num_heads=cfg["num_heads"], mlp_ratio=cfg["mlp_ratio"], global_pool=global_pool,
+                                   norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), drop_path_rate=0.1)

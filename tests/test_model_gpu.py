@@ -346,3 +346,53 @@ def test_contrastive_model_through_the_training_loop_api():
             # elements whose true gradient is ~0 are moved by +-lr per step in a direction set by rounding noise (Adam
             # normalises it): allow the 3 steps x lr = 3e-4 such elements can drift apart, on top of 5e-3 relative
             assert d < 5e-3 * (pu[k].double().abs().max().item() + 1e-12) + 3.5e-4, k
+
+
+# ------------------------------------------------------------------------------------------------ encoder-only inference (f-3)
+@pytest.mark.parametrize("name,cfgname,gp", [("small_gp", "small", True), ("tiny_cls", "tiny", False)])
+def test_vit_feature_extractor_matches_oracle_and_reference_golden(name, cfgname, gp):
+    """VisionTransformer3D.forward_features / forward (model/vit.py:265-297) on the kernels, all patches, no masking."""
+    from vit_ae_plus_plus_b200.model.vit import VisionTransformer3D
+    g = np.load(os.path.join(GOLD, "vit_features.npz"))
+    cfg = O.CONFIGS[cfgname]
+    P = O.init_vit_params(cfg, 2, gp, seed=0)
+    m = VisionTransformer3D(volume_size=cfg["volume_size"], in_chans=cfg["in_chans"], num_classes=2, patch_size=cfg["patch_size"],
+                            embed_dim=cfg["embed_dim"], depth=cfg["depth"], num_heads=cfg["num_heads"], mlp_ratio=cfg["mlp_ratio"],
+                            global_pool=gp, norm_layer=partial(nn.LayerNorm, eps=1e-6), drop_path_rate=0.1)
+    assert sorted(m.state_dict()) == sorted(O.vit_param_names(cfg, gp))              # the reference's state_dict keys
+    m.load_state_dict(P, strict=True)
+    m = m.cuda().eval()
+    V, C = cfg["volume_size"], cfg["in_chans"]
+    x = torch.randn(3, C, V, V, V, generator=torch.Generator().manual_seed(1))
+    with pytest.raises(Exception):
+        m.forward_features(x.cuda())                 # autograd enabled: inference-only path says so
+    with torch.no_grad():
+        f = m.forward_features(x.cuda())
+        y = m(x.cuda())
+    ref = torch.from_numpy(g[f"feat/{name}"])
+    assert relmax(f, ref) < TOL, relmax(f, ref)
+    assert relmax(f, O.vit_forward_features(x, P, cfg, gp)) < TOL
+    assert relmax(y, torch.from_numpy(g[f"logits/{name}"])) < 2e-2
+
+
+def test_mae_checkpoint_hand_off_to_the_feature_extractor():
+    """The post-training flow of k_fold_cross_valid_combined_brats.py:219-253: get_models('vit'), load the MAE checkpoint's
+    'model' dict with strict=False, the asserted missing-key set, then forward_features under no_grad."""
+    from vit_ae_plus_plus_b200.model import model_factory
+    args = argparse.Namespace(model="mae_vit_base_patch16", volume_size=32, in_channels=1, patch_size=16, perceptual_weight=0,
+                              use_imagenet=False, nb_classes=2, global_pool=True, drop_path=0.1)
+    mae = model_factory.get_models("autoenc", args).cuda()
+    ckpt = {k: v.detach().cpu().clone() for k, v in mae.state_dict().items()}
+    vit = model_factory.get_models("vit", args)
+    msg = vit.load_state_dict(ckpt, strict=False)
+    assert set(msg.missing_keys) == {"head.weight", "head.bias", "fc_norm.weight", "fc_norm.bias"}
+    assert all(k.startswith(("decoder_", "mask_token", "norm.")) for k in msg.unexpected_keys)
+    vit = vit.cuda().eval()
+    x = torch.randn(2, 1, 32, 32, 32, generator=torch.Generator().manual_seed(2)).cuda()
+    with torch.no_grad():
+        f = vit.forward_features(x)
+    assert f.shape == (2, 768) and torch.isfinite(f).all()
+    # same encoder weights: the MAE's own encoder with nothing masked sees the same token stream
+    P = {k: v.detach().cpu() for k, v in vit.state_dict().items()}
+    cfg = dict(volume_size=32, patch_size=16, in_chans=1, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4)
+    assert relmax(f, O.vit_forward_features(x.cpu(), P, cfg, True)) < TOL

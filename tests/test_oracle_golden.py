@@ -108,6 +108,19 @@ def test_contrastive_wrapper_matches_reference():
         np.testing.assert_allclose(gr[:16].numpy(), g[f"ghead/{n}"], rtol=5e-3, atol=5e-5 * max(ref_norm, 1e-6), err_msg=n)
 
 
+@pytest.mark.parametrize("name,cfgname,gp", [("small_gp", "small", True), ("tiny_cls", "tiny", False)])
+def test_vit_feature_extraction_matches_reference(name, cfgname, gp):
+    """Encoder-only inference (VisionTransformer3D.forward_features, model/vit.py:265-284) against the reference golden."""
+    g = np.load(os.path.join(GOLD, "vit_features.npz"))
+    cfg = O.CONFIGS[cfgname]
+    P = O.init_vit_params(cfg, 2, gp, seed=0)
+    V, C = cfg["volume_size"], cfg["in_chans"]
+    x = torch.randn(3, C, V, V, V, generator=torch.Generator().manual_seed(1))
+    np.testing.assert_allclose(O.vit_forward_features(x, P, cfg, gp).numpy(), g[f"feat/{name}"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(O.vit_forward(x, P, cfg, gp).numpy(), g[f"logits/{name}"], rtol=1e-5, atol=1e-6)
+    assert sorted(P) == sorted(O.vit_param_names(cfg, gp))
+
+
 def test_pos_embed_matches_reference():
     g = np.load(os.path.join(GOLD, "pos_embed.npz"))
     for key in g.files:

@@ -198,7 +198,7 @@ def test_factory_and_named_ctors():
     assert set(m.state_dict()) == ref_keys
     assert sum(p.numel() for p in m.parameters() if p.requires_grad) > 100e6
     with pytest.raises(NotImplementedError):
-        model_factory.get_models("vit", args)
+        model_factory.get_models("contrastive", args)      # fine-tuning classifier: outside the B200 path, says so
 
 
 # ------------------------------------------------------------------------------------------------ contrastive wrapper

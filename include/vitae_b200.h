@@ -85,12 +85,13 @@ size_t vitae_gemm_workspace_bytes_for(const vitae_gemm_epilogue* ep, int a_mn_ma
                                       int split_k);
 
 /* Times the (tile_n, split_k) candidates of this GEMM on the device and returns the fastest (CUDA events; the GEMMs of
- * the step are short and latency bound, so the best tiling depends on the exact shape).  Re-runs the GEMM many times:
- * outputs are overwritten with identical values; not allowed for accumulate epilogues or on a capturing stream.
- * Candidates whose slabs exceed `workspace_bytes` are skipped.  Synchronises `stream`. */
+ * the step are short and latency bound, so the best tiling depends on the exact shape).  With flush_buf (>= 2x L2, e.g.
+ * 256 MB) every timed launch runs on a flushed L2 -- the state the step's weight matrices are in; NULL: back-to-back warm
+ * launches.  Re-runs the GEMM many times: outputs are overwritten with identical values; not allowed for accumulate
+ * epilogues or on a capturing stream.  Candidates whose slabs exceed `workspace_bytes` are skipped.  Synchronises `stream`. */
 int vitae_gemm_autotune(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M, int N,
-                        int K, const vitae_gemm_epilogue* ep, void* workspace, size_t workspace_bytes, void* stream,
-                        int* best_tile_n, int* best_split_k);
+                        int K, const vitae_gemm_epilogue* ep, void* workspace, size_t workspace_bytes, void* flush_buf,
+                        size_t flush_bytes, void* stream, int* best_tile_n, int* best_split_k);
 
 /* ------------------------------------------------------------------------------------------------------------
  * LayerNorm (biased variance, eps inside sqrt) -- nn.LayerNorm at model/vit.py:131,135,140-143 and

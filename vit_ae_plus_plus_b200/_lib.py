@@ -55,7 +55,8 @@ SIGNATURES = {
     "vitae_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vitae_gemm_workspace_bytes_for": (c_size_t, [POINTER(GemmEpilogue), c_int, c_int, c_int, c_int, c_int]),
     "vitae_gemm_autotune": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                    POINTER(GemmEpilogue), c_void_p, c_size_t, c_void_p, POINTER(c_int), POINTER(c_int)]),
+                                    POINTER(GemmEpilogue), c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, POINTER(c_int),
+                                    POINTER(c_int)]),
     "vitae_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                     c_float, c_void_p]),
     "vitae_layernorm_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_void_p]),

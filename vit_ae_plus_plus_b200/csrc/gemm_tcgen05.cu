@@ -727,14 +727,16 @@ extern "C" int vitae_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
     return 0;
 }
 
-// Times every (tile_n, split_k) candidate for this GEMM on the device (back-to-back launches from this loop: the host
-// enqueue cost of ~2 us per launch stays below the kernel time, so the stream is device-bound; CUDA events; best of two
-// trials) and returns the fastest.  The GEMMs of the training step are short and latency / ingest bound, which makes the
-// best tiling a property of the exact shape.  Candidates whose slabs do not fit into `workspace` are skipped.  The
-// outputs are overwritten repeatedly with the same values (do not use with accumulate).  Synchronises `stream`.
+// Times every (tile_n, split_k) candidate for this GEMM on the device and returns the fastest.  The GEMMs of the training
+// step are short and latency / ingest bound, which makes the best tiling a property of the exact shape -- and of the cache
+// state: in the step every weight matrix is read once per pass and comes from HBM, so a candidate is timed COLD when a
+// flush buffer is given (>= 2x L2, overwritten before every timed launch; CUDA events around each launch): a tiling with a
+// handful of CTAs looks best on L2-resident operands and is the worst one on cold weights.  Without a flush buffer the
+// launches run back to back (warm).  Candidates whose slabs do not fit into `workspace` are skipped.  The outputs are
+// overwritten repeatedly with the same values (do not use with accumulate).  Synchronises `stream`.
 extern "C" int vitae_gemm_autotune(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, int M,
                                    int N, int K, const vitae_gemm_epilogue* e, void* workspace, size_t workspace_bytes,
-                                   void* stream, int* best_tile_n, int* best_split_k) {
+                                   void* flush_buf, size_t flush_bytes, void* stream, int* best_tile_n, int* best_split_k) {
     VITAE_REQUIRE(e && best_tile_n && best_split_k, "gemm_autotune: null argument");
     VITAE_REQUIRE(!e->accumulate, "gemm_autotune: accumulate epilogues cannot be re-run");
     cudaStream_t st = as_stream(stream);
@@ -747,6 +749,7 @@ extern "C" int vitae_gemm_autotune(const void* A, int lda, int a_mn_major, const
     const int num_sub = ceil_div(K, BK), tiles_m = ceil_div(M, BM);
     const int tiles_n_opts[3] = {64, 128, 256};
     const int split_opts[6] = {1, 2, 3, 4, 6, 8};
+    const bool cold = flush_buf != nullptr && flush_bytes > 0;
     float best = 1e30f;
     int rc = 0;
     *best_tile_n = 0;
@@ -759,19 +762,35 @@ extern "C" int vitae_gemm_autotune(const void* A, int lda, int a_mn_major, const
             const int sk = split_opts[si];
             if (sk > 1 && (num_sub < 4 * sk || tiles * sk > 3 * 148)) continue;
             if (vitae_gemm_workspace_bytes_for(e, a_mn_major, b_mn_major, M, N, sk) > workspace_bytes) continue;
-            constexpr int REPS = 12;
             for (int w = 0; w < 2 && rc == 0; ++w)
                 rc = vitae_gemm_bf16(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, e, tn, sk, workspace, workspace_bytes, stream);
             float t = 1e30f;
-            for (int trial = 0; trial < 2 && rc == 0; ++trial) {
-                cudaEventRecord(e0, st);
-                for (int r = 0; r < REPS && rc == 0; ++r)
+            if (cold) {
+                constexpr int REPS = 6;
+                float sum = 0.f;
+                for (int r = 0; r < REPS && rc == 0; ++r) {
+                    cudaMemsetAsync(flush_buf, r & 0xff, flush_bytes, st);      // evicts operands and outputs from L2
+                    cudaEventRecord(e0, st);
                     rc = vitae_gemm_bf16(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, e, tn, sk, workspace, workspace_bytes, stream);
-                cudaEventRecord(e1, st);
-                if (cudaEventSynchronize(e1) != cudaSuccess) rc = set_error(-3, "gemm_autotune: %s", cudaGetErrorString(cudaGetLastError()));
-                float ms = 0.f;
-                cudaEventElapsedTime(&ms, e0, e1);
-                t = ms < t ? ms : t;
+                    cudaEventRecord(e1, st);
+                    if (cudaEventSynchronize(e1) != cudaSuccess) rc = set_error(-3, "gemm_autotune: %s", cudaGetErrorString(cudaGetLastError()));
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    if (r > 0) sum += ms;                                        // the first cold run also warms the instruction cache
+                }
+                t = sum / (REPS - 1);
+            } else {
+                constexpr int REPS = 12;
+                for (int trial = 0; trial < 2 && rc == 0; ++trial) {
+                    cudaEventRecord(e0, st);
+                    for (int r = 0; r < REPS && rc == 0; ++r)
+                        rc = vitae_gemm_bf16(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, e, tn, sk, workspace, workspace_bytes, stream);
+                    cudaEventRecord(e1, st);
+                    if (cudaEventSynchronize(e1) != cudaSuccess) rc = set_error(-3, "gemm_autotune: %s", cudaGetErrorString(cudaGetLastError()));
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    t = ms < t ? ms : t;
+                }
             }
             if (rc == 0 && t < best) {
                 best = t;

@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--workload", default="vit_base_128", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=4, help="volumes per GPU per step")
     ap.add_argument("--mask-ratio", type=float, default=0.75)
+    ap.add_argument("--edge-map-weight", type=float, default=0.0,
+                    help="weight of the Sobel edge-map term (model/vit_autoenc.py:221-224); 0 = the headline configuration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not use CUDA graphs for the step")
@@ -63,11 +65,13 @@ def model_args(w, a):
 
 def workload_name(w, a, n):
     return (f"{w['model']} {w['volume_size']}^3x{w['in_channels']} patch {w['patch_size']}, batch {a.batch}/GPU x {n} GPU, "
-            f"mask {a.mask_ratio}, fwd+bwd+AdamW(betas .9/.95, wd .05)+GradScaler")
+            f"mask {a.mask_ratio}, fwd+bwd+AdamW(betas .9/.95, wd .05)+GradScaler"
+            + (f", edge-map term weight {a.edge_map_weight}" if a.edge_map_weight else ""))
 
 
 # ---------------------------------------------------------------------------------------------------- CPU side
-def cpu_reference_rate(workload: dict, mask_ratio: float, batch: int, steps: int, warmup: int, threads: int):
+def cpu_reference_rate(workload: dict, mask_ratio: float, batch: int, steps: int, warmup: int, threads: int,
+                       edge_w: float = 0.0):
     """The reference algorithm (oracle/mae_oracle.py: functional restatement of model/vit_autoenc.py on torch CPU fp32,
     pinned to the unmodified reference by tests/golden) forward + backward + AdamW on the host cores."""
     from oracle import mae_oracle as O
@@ -84,7 +88,7 @@ def cpu_reference_rate(workload: dict, mask_ratio: float, batch: int, steps: int
     for it in range(warmup + steps):
         noise = torch.rand(batch, L, generator=gen)
         t0 = time.perf_counter()
-        losses, _, _, _ = O.forward(x, leaves, cfg, mask_ratio, noise, 0.0, with_edge=False)
+        losses, _, _, _ = O.forward(x, leaves, cfg, mask_ratio, noise, edge_w, with_edge=edge_w != 0)
         opt.zero_grad(set_to_none=True)
         losses[0].backward()
         opt.step()
@@ -101,7 +105,8 @@ def run_reference(a):
     w = WORKLOADS[a.workload]
     cores = os.cpu_count() or 1
     sample_batch = 1
-    rate, ms = cpu_reference_rate(w, a.mask_ratio, sample_batch, a.steps, max(1, min(a.warmup, 2)), cores)
+    rate, ms = cpu_reference_rate(w, a.mask_ratio, sample_batch, a.steps, max(1, min(a.warmup, 2)), cores,
+                                   a.edge_map_weight)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -198,7 +203,7 @@ def run_ours(a):
     pool = [torch.randn(B, C, V, V, V, device=dev) for _ in range(n_pool)]
 
     def step(x):
-        losses, _pred, _mask = model(x, mask_ratio=a.mask_ratio, edge_map_weight=0)
+        losses, _pred, _mask = model(x, mask_ratio=a.mask_ratio, edge_map_weight=a.edge_map_weight)
         scaler(losses[0], opt, parameters=model.parameters(), update_grad=True)
         opt.zero_grad()
         return losses[0]
@@ -327,7 +332,7 @@ def run_ours(a):
     cpu = None
     if rank == 0 and not a.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        rate, _ = cpu_reference_rate(w, a.mask_ratio, 1, a.cpu_sample_steps, 1, cores)
+        rate, _ = cpu_reference_rate(w, a.mask_ratio, 1, a.cpu_sample_steps, 1, cores, a.edge_map_weight)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{a.cpu_sample_steps} steps x 1 volume of the same workload (oracle: reference algorithm, torch CPU fp32)"}
 

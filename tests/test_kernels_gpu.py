@@ -289,7 +289,7 @@ def test_cast_params_and_adamw_match_torch():
     assert torch.equal(p, before)                                   # GradScaler semantics: skipped on inf (utils/misc.py:267)
 
 
-@pytest.mark.parametrize("B,C,V,p", [(2, 1, 32, 8), (1, 4, 32, 16), (2, 2, 48, 16)])
+@pytest.mark.parametrize("B,C,V,p", [(2, 1, 32, 8), (1, 4, 32, 16), (2, 2, 48, 16), (1, 1, 136, 8), (1, 2, 20, 4)])
 def test_edge_map_loss_kernels_match_oracle(B, C, V, p):
     """vitae_edge_target / vitae_edge_loss_fwd / vitae_edge_loss_bwd against the oracle's restatement of
     model/vit_autoenc.py:221-224 (Sobel of unpatchify(pred) vs Sobel of the Gaussian-blurred target) and its autograd."""

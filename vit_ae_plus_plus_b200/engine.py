@@ -364,6 +364,9 @@ class MAEEngine:
         self.dpos = decoder_pos_embed.detach().reshape(self.L + 1, Dd).contiguous()
         self.plans: Dict[Tuple[int, int], MAEPlan] = {}
         self.lanes = _Lanes(dev)
+        self.bg_stream: Optional[torch.cuda.Stream] = None     # edge-map target branch underneath the forward
+        self._bg_done: Optional[torch.cuda.Event] = None
+        self.cap_stream: Optional[torch.cuda.Stream] = None
         self.pf_stream = torch.cuda.Stream(device=dev)
         self.ws_main, self.ws_side = ops.GrowBuf(dev), ops.GrowBuf(dev)
         self.use_graphs = True
@@ -448,6 +451,37 @@ class MAEEngine:
                 ts += [b.pre, b.act, b.ln2, b.o, b.qkv, b.ln1, b.xmid, sb.x[i]]
             self._prefetch(ts)
 
+    def _capture_stream(self) -> Optional[torch.cuda.Stream]:
+        """Graphs are captured on a stream of priority VITAE_MAIN_PRIORITY (kernel nodes inherit it): above the
+        background stream (0, the lowest), below the side lane."""
+        prio = int(os.environ.get("VITAE_MAIN_PRIORITY", "0"))
+        if prio == 0:
+            return None
+        if self.cap_stream is None:
+            self.cap_stream = torch.cuda.Stream(device=self.device, priority=prio)
+        return self.cap_stream
+
+    def _background(self, fn) -> None:
+        """Forks ``fn`` onto the background stream (same priority as the main lane: it fills SMs the main chain leaves
+        idle); ``_background_join`` orders the main lane after it.  VITAE_EDGE_OVERLAP=0 runs it inline."""
+        if os.environ.get("VITAE_EDGE_OVERLAP", "1") == "0":
+            fn()
+            return
+        if self.bg_stream is None:
+            self.bg_stream = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.bg_stream.wait_event(ev)
+        with torch.cuda.stream(self.bg_stream):
+            fn()
+        self._bg_done = torch.cuda.Event()
+        self._bg_done.record(self.bg_stream)
+
+    def _background_join(self) -> None:
+        if self._bg_done is not None:
+            torch.cuda.current_stream().wait_event(self._bg_done)
+            self._bg_done = None
+
     def _need(self, name: str) -> None:
         """Orders the current stream after the optimizer's update of the group that holds parameter ``name`` (once per
         group and pass: an event-wait node in front of a kernel costs that kernel its programmatic launch edge)."""
@@ -506,7 +540,7 @@ class MAEEngine:
             lib = ops._lib.load()
             n0 = lib.vitae_launch_count()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self._capture_stream()):
                 fn()
             slot.launches = lib.vitae_launch_count() - n0
             self.graph_replayed_launches -= slot.launches    # the capture pass enqueued them without executing
@@ -560,12 +594,16 @@ class MAEEngine:
             pl.edge_buffers(self)
 
         def body():
+            if want_edge:
+                # the target branch (blur + Sobel of the input volume) depends on nothing the model computes: it runs on
+                # the background stream underneath the encoder / decoder, whose small GEMMs leave most SMs idle
+                self._background(lambda: ops.edge_target(vol, self.edge_taps, pl.edge_scratch, pl.edge_tgt))
             self.encode(pl, vol, pl.noise)
             self.decode(pl, pred_f32)
             if want_loss:
                 ops.masked_mse_fwd(pl.pred, vol, pl.mask, pl.patch_sums, pl.loss_out, self.p)
             if want_edge:
-                ops.edge_target(vol, self.edge_taps, pl.edge_scratch, pl.edge_tgt)
+                self._background_join()
                 ops.edge_loss_fwd(pl.pred, pl.edge_tgt, pl.edge_scratch, pl.edge_resid, pl.edge_out, pl.B, self.C, self.V,
                                   self.p)
             self.lanes.join()          # the side lane carries the L2 prefetches of the forward

@@ -217,9 +217,10 @@ int vitae_masked_mse_bwd(const void* pred, int pred_is_bf16, const float* vol, c
  * scratch: vitae_edge_scratch_floats(B, C, V) floats, shared by the three calls of one step (target, fwd, bwd).
  * vitae_edge_target: E_tgt fp32 [B, V^3] from the fp32 volume [B, C, V, V, V]; taps: HOST array of the ntaps (odd, <= 16)
  *   normalised 1-D Gaussian taps (the reference's dense ks^3 kernel is their outer product).
- * vitae_edge_loss_fwd: loss_out[0] = raw_edge for pred bf16 [B, L+1, P] (cls row first); keeps the residual in
- *   resid fp32 [B, V^3] and the normalised Sobel gradients in scratch for the backward.
- * vitae_edge_loss_bwd: dpred_bf16 [B, L+1, P] += (*upstream) * d raw_edge / d pred  (|grad| = 0 contributes 0). */
+ * vitae_edge_loss_fwd: loss_out[0] = raw_edge for pred bf16 [B, L+1, P] (cls row first); writes the residual
+ *   D = E_pred - E_tgt to resid fp32 [B, V^3] and keeps F = D * g / |g| (bf16, 3 per channel voxel) in scratch.
+ * vitae_edge_loss_bwd: dpred_bf16 [B, L+1, P] += (*upstream) * d raw_edge / d pred  (|grad| = 0 contributes 0); reads F
+ *   from scratch (resid is only checked for NULL).  V and p multiples of 4, C in {1, 2, 4}. */
 size_t vitae_edge_scratch_floats(int B, int C, int V);
 int vitae_edge_target(const float* vol, const float* taps, int ntaps, float* scratch, float* E_tgt, int B, int C, int V,
                       void* stream);

@@ -76,25 +76,30 @@ blur_axis_kernel(const float* __restrict__ in, float* __restrict__ out, int V, c
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * XT;
     if (x0 >= V) return;
     if constexpr (AXIS == 0) {
-        const int y = blockIdx.y * 4 + threadIdx.y, z = blockIdx.z % V, plane = blockIdx.z / V;
-        if (y >= V) return;
+        // BLUR_MT independent rows per thread (longer-lived blocks, BLUR_MT x the loads in flight)
+        const int yb = (blockIdx.y * 4 + threadIdx.y) * BLUR_MT, z = blockIdx.z % V, plane = blockIdx.z / V;
         constexpr int LQ = (H + 3) / 4;                        // aligned float4 chunks on each side of the own one
-        float w[(2 * LQ + 1) * 4];
-        const float* row = in + vox(V, plane, z, y, 0);
 #pragma unroll
-        for (int q = 0; q < 2 * LQ + 1; ++q) {
-            const int xs = x0 + 4 * (q - LQ);
-            const float4 v = (xs >= 0 && xs < V) ? *reinterpret_cast<const float4*>(row + xs) : make_float4(0.f, 0.f, 0.f, 0.f);
-            w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-        }
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < BLUR_MT; ++j) {
+            const int y = yb + j;
+            if (y >= V) break;
+            float w[(2 * LQ + 1) * 4];
+            const float* row = in + vox(V, plane, z, y, 0);
 #pragma unroll
-        for (int k = 0; k < NT; ++k) {
-            const float t = taps.t[k];
-            acc.x += t * w[4 * LQ + 0 + k - H]; acc.y += t * w[4 * LQ + 1 + k - H];
-            acc.z += t * w[4 * LQ + 2 + k - H]; acc.w += t * w[4 * LQ + 3 + k - H];
+            for (int q = 0; q < 2 * LQ + 1; ++q) {
+                const int xs = x0 + 4 * (q - LQ);
+                const float4 v = (xs >= 0 && xs < V) ? *reinterpret_cast<const float4*>(row + xs) : make_float4(0.f, 0.f, 0.f, 0.f);
+                w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+            }
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                const float t = taps.t[k];
+                acc.x += t * w[4 * LQ + 0 + k - H]; acc.y += t * w[4 * LQ + 1 + k - H];
+                acc.z += t * w[4 * LQ + 2 + k - H]; acc.w += t * w[4 * LQ + 3 + k - H];
+            }
+            *reinterpret_cast<float4*>(out + vox(V, plane, z, y, x0)) = acc;
         }
-        *reinterpret_cast<float4*>(out + vox(V, plane, z, y, x0)) = acc;
     } else {
         // first output coordinate along the axis (a0) and the fixed other one
         int y, z, plane;
@@ -510,7 +515,7 @@ template <int NT>
 static void launch_blur(const float* in, float* out, int V, int planes, int axis, const Taps& t, cudaStream_t st) {
     const dim3 blk(32, 4);
     if (axis == 0)
-        launch_kernel(blur_axis_kernel<NT, 0>, edge_grid(V, planes), blk, 0, st, in, out, V, t);
+        launch_kernel(blur_axis_kernel<NT, 0>, dim3(ceil_div(V, 128), ceil_div(V, 4 * BLUR_MT), planes * V), blk, 0, st, in, out, V, t);
     else if (axis == 1)
         launch_kernel(blur_axis_kernel<NT, 1>, dim3(ceil_div(V, 128), ceil_div(V, 4 * BLUR_MT), planes * V), blk, 0, st, in, out, V, t);
     else

@@ -152,7 +152,7 @@ class _Lanes:
     def __init__(self, device):
         # higher priority than the main lane: with programmatic dependent launch the main chain keeps the next kernels'
         # CTAs resident (waiting on their predecessor); side-lane CTAs must win the SM slots that free up
-        self.stream = torch.cuda.Stream(device=device, priority=int(os.environ.get("VITAE_SIDE_PRIORITY", "-1")))
+        self.stream = torch.cuda.Stream(device=device, priority=int(os.environ.get("VITAE_SIDE_PRIORITY", "-2")))
         self.readers: Dict[object, torch.cuda.Event] = {}
         self.dirty = False
         self.extra_dirty: Optional[torch.cuda.Stream] = None   # another forked stream to join (L2 prefetches)
@@ -454,7 +454,7 @@ class MAEEngine:
     def _capture_stream(self) -> Optional[torch.cuda.Stream]:
         """Graphs are captured on a stream of priority VITAE_MAIN_PRIORITY (kernel nodes inherit it): above the
         background stream (0, the lowest), below the side lane."""
-        prio = int(os.environ.get("VITAE_MAIN_PRIORITY", "0"))
+        prio = int(os.environ.get("VITAE_MAIN_PRIORITY", "-1"))
         if prio == 0:
             return None
         if self.cap_stream is None:
@@ -462,8 +462,8 @@ class MAEEngine:
         return self.cap_stream
 
     def _background(self, fn) -> None:
-        """Forks ``fn`` onto the background stream (same priority as the main lane: it fills SMs the main chain leaves
-        idle); ``_background_join`` orders the main lane after it.  VITAE_EDGE_OVERLAP=0 runs it inline."""
+        """Forks ``fn`` onto the background stream (priority 0, below the graph-captured main lane: it fills SMs the main
+        chain leaves idle); ``_background_join`` orders the main lane after it.  VITAE_EDGE_OVERLAP=0 runs it inline."""
         if os.environ.get("VITAE_EDGE_OVERLAP", "1") == "0":
             fn()
             return

@@ -396,7 +396,7 @@ block_colreduce_kernel(const ColJobs jobs, float* __restrict__ partials, unsigne
                 for (int i = 0; i < 8; ++i) acc0[i] += v0[i];
             }
         } else {
-#pragma unroll 2
+#pragma unroll 4
             for (int r = r0 + warp; r < r1; r += 8) {
                 float d[8], xv[8];
                 col_load8(jb, static_cast<size_t>(r) * jb.ld + c, d);
@@ -451,18 +451,16 @@ block_colreduce_kernel(const ColJobs jobs, float* __restrict__ partials, unsigne
         for (int o = 0; o < 2; ++o) {
             float* out = o == 0 ? jb.out0 : jb.out1;
             if ((o == 1 && !ln) || out == nullptr) continue;
-            float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;   // four loads in flight, fixed association
+            float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // eight loads in flight, fixed association
             const float* pp = partials + static_cast<size_t>(o) * nsl * jobs.total_cols + gcol;
             int y = 0;
-            for (; y + 4 <= nsl; y += 4) {
-                t0 += __ldcg(pp + static_cast<size_t>(y) * jobs.total_cols);
-                t1 += __ldcg(pp + static_cast<size_t>(y + 1) * jobs.total_cols);
-                t2 += __ldcg(pp + static_cast<size_t>(y + 2) * jobs.total_cols);
-                t3 += __ldcg(pp + static_cast<size_t>(y + 3) * jobs.total_cols);
+            for (; y + 8 <= nsl; y += 8) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) t[q] += __ldcg(pp + static_cast<size_t>(y + q) * jobs.total_cols);
             }
-            for (; y < nsl; ++y) t0 += __ldcg(pp + static_cast<size_t>(y) * jobs.total_cols);
-            const float t = (t0 + t1) + (t2 + t3);
-            out[col] = jobs.accumulate ? out[col] + t : t;
+            for (; y < nsl; ++y) t[0] += __ldcg(pp + static_cast<size_t>(y) * jobs.total_cols);
+            const float tt = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+            out[col] = jobs.accumulate ? out[col] + tt : tt;
         }
     }
     if (threadIdx.x == 0) counters[blockIdx.x] = 0u;
@@ -476,9 +474,9 @@ using namespace vitae;
 // jobs: HOST array of vitae_col_job, read during the call.  workspace: vitae_block_colreduce_workspace_bytes(...) bytes,
 // zero-filled before first use (ticket counters, self-resetting), not shared by concurrent calls.
 static inline int bcr_slices(int rows, int strips) {
-    int s = std::max(1, (3 * 148) / std::max(1, strips));
+    int s = std::max(1, (6 * 148) / std::max(1, strips));
     s = std::min(s, std::max(1, rows / 32));
-    return std::min(s, 16);
+    return std::min(s, 32);
 }
 
 extern "C" size_t vitae_block_colreduce_workspace_bytes(int rows, int total_cols_padded) {

@@ -145,36 +145,40 @@ class FlatParams:
 
 
 class _Lanes:
-    """Main lane = torch's current stream; side lane = work off the critical path (weight gradients, bias sums).
-    Hazards between the lanes are ordered with events: ``side()`` starts after everything enqueued on main so far and
-    remembers which buffers it reads; ``before_write()`` makes main wait for the last side reader of a buffer."""
+    """Main lane = torch's current stream; side lanes = work off the critical path: lane 0 the weight-gradient GEMMs, lane 1
+    the per-block column reductions (bias sums, LayerNorm affine gradients: latency-bound two-phase kernels that would
+    otherwise sit between the weight-gradient GEMMs).  Hazards between the lanes are ordered with events: ``side()``
+    starts after everything enqueued on main so far and remembers which buffers it reads; ``before_write()`` makes main
+    wait for the last side readers of a buffer."""
 
     def __init__(self, device):
         # higher priority than the main lane: with programmatic dependent launch the main chain keeps the next kernels'
         # CTAs resident (waiting on their predecessor); side-lane CTAs must win the SM slots that free up
-        self.stream = torch.cuda.Stream(device=device, priority=int(os.environ.get("VITAE_SIDE_PRIORITY", "-2")))
-        self.readers: Dict[object, torch.cuda.Event] = {}
-        self.dirty = False
+        self.streams = [torch.cuda.Stream(device=device, priority=int(os.environ.get("VITAE_SIDE_PRIORITY", "-2"))),
+                        torch.cuda.Stream(device=device, priority=int(os.environ.get("VITAE_REDUCE_PRIORITY", "-2")))]
+        self.stream = self.streams[0]
+        self.readers: Dict[object, Dict[int, torch.cuda.Event]] = {}
+        self.dirty = [False, False]
         self.extra_dirty: Optional[torch.cuda.Stream] = None   # another forked stream to join (L2 prefetches)
 
-    def side(self, fn, reads=()) -> None:
+    def side(self, fn, reads=(), lane: int = 0) -> None:
         main = torch.cuda.current_stream()
+        st = self.streams[lane]
         ev = torch.cuda.Event()
         ev.record(main)
-        self.stream.wait_event(ev)
-        with torch.cuda.stream(self.stream):
+        st.wait_event(ev)
+        with torch.cuda.stream(st):
             fn()
         done = torch.cuda.Event()
-        done.record(self.stream)
+        done.record(st)
         for k in reads:
-            self.readers[k] = done
-        self.dirty = True
+            self.readers.setdefault(k, {})[lane] = done
+        self.dirty[lane] = True
 
     def before_write(self, *keys) -> None:
         main = torch.cuda.current_stream()
         for k in keys:
-            ev = self.readers.pop(k, None)
-            if ev is not None:
+            for ev in self.readers.pop(k, {}).values():
                 main.wait_event(ev)
 
     def join(self) -> None:
@@ -183,12 +187,13 @@ class _Lanes:
             ev.record(self.extra_dirty)
             torch.cuda.current_stream().wait_event(ev)
             self.extra_dirty = None
-        if self.dirty:
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
-            torch.cuda.current_stream().wait_event(ev)
+        for lane, st in enumerate(self.streams):
+            if self.dirty[lane]:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                torch.cuda.current_stream().wait_event(ev)
+                self.dirty[lane] = False
         self.readers.clear()
-        self.dirty = False
 
 
 class _GraphSlot:
@@ -201,7 +206,15 @@ class _GraphSlot:
         self.calls = 0
 
 
-RING = 4                  # depth of the buffer rings shared between the two backward lanes (MAEPlan)
+# depth of the buffer rings shared between the backward lanes (MAEPlan): residual-stream gradients and LayerNorm inputs
+# (two per transformer block) / hidden and qkv gradients (one per block).  The main lane waits before it overwrites a
+# slot a side lane still reads, so the depth is how many blocks the side lanes may fall behind.
+# Default: one slot per use in the deepest stack (no slot is reused inside a backward stage; 0.6 GB at batch 4 for ViT-B:
+# measured 4.55 -> 4.39 ms per step against rings of 4 / 2).  VITAE_RING / VITAE_RING_BLOCK override (>= 4 / >= 2).
+def ring_depths(max_depth: int):
+    ring = int(os.environ.get("VITAE_RING", str(2 * max_depth + 2)))
+    ring_block = int(os.environ.get("VITAE_RING_BLOCK", str(max_depth)))
+    return max(4, ring), max(2, ring_block)
 MAX_INPUT_ADDRESSES = 4   # input-volume addresses that get their own (zero-copy) graphs; others are copied (below)
 
 
@@ -267,20 +280,19 @@ class MAEPlan:
         Hmax = max(eng.enc.hidden, eng.dec.hidden)
         self.dloss = a.new((1,), _F32)
         self.dpred = a.new((B, self.Nd, P), _BF16)
-        # rings of RING buffers: the side lane reads them (weight-gradient GEMMs, the per-block column reductions) after the
-        # main lane has moved on; with 4 the main lane only waits for side work issued two blocks earlier
-        self.dres = [a.new((Mmax * Dmax,), _F32) for _ in range(RING)]
-        # buffers read by the side lane are double-buffered so that the main lane never waits for recent side work
-        self.dres16 = [a.new((Mmax * Dmax,), _BF16) for _ in range(RING)]
+        # rings of eng.ring (two uses per block) / eng.ring_block (one use per block) buffers: the side lanes read them
+        # (weight-gradient GEMMs, the per-block column reductions) after the main lane has moved on (ring_depths above)
+        self.dres = [a.new((Mmax * Dmax,), _F32) for _ in range(eng.ring)]
+        self.dres16 = [a.new((Mmax * Dmax,), _BF16) for _ in range(eng.ring)]
         self.d_d = a.new((Mmax * Dmax,), _BF16)
-        # LayerNorm-backward inputs: read again by the side lane (affine-gradient reductions), so two alternate
-        self.d_ln = [a.new((Mmax * Dmax,), _BF16) for _ in range(RING)]
+        # LayerNorm-backward inputs: read again by the reduction lane (affine-gradient reductions)
+        self.d_ln = [a.new((Mmax * Dmax,), _BF16) for _ in range(eng.ring)]
         bcr = max(ops.block_colreduce_workspace_bytes(m, [st.hidden, 3 * st.dim, st.dim, st.dim, st.dim, st.dim])
                   for m, st in ((self.Me, eng.enc), (self.Md, eng.dec)))
         self.bcr_ws = torch.zeros(bcr, dtype=torch.uint8, device=dev)   # zero-filled: ticket counters (side lane only)
         a.nbytes += bcr
-        self.d_hid = [a.new((Mmax * Hmax,), _BF16), a.new((Mmax * Hmax,), _BF16)]
-        self.dqkv = [a.new((Mmax * 3 * Dmax,), _BF16), a.new((Mmax * 3 * Dmax,), _BF16)]
+        self.d_hid = [a.new((Mmax * Hmax,), _BF16) for _ in range(eng.ring_block)]
+        self.dqkv = [a.new((Mmax * 3 * Dmax,), _BF16) for _ in range(eng.ring_block)]
         self.delta = a.new((B * max(eng.enc.heads * self.Ne, eng.dec.heads * self.Nd),), _F32)
         ln_ws = ops.layernorm_param_grads_workspace_bytes(Mmax, Dmax)
         self.ln_ws = torch.zeros(ln_ws, dtype=torch.uint8, device=dev)   # zero-filled: ticket counters (side lane only)
@@ -352,6 +364,7 @@ class MAEEngine:
         self.enc = StackSpec("blocks", D, cfg["num_heads"], int(D * cfg["mlp_ratio"]), cfg["depth"])
         self.dec = StackSpec("decoder_blocks", Dd, cfg["decoder_num_heads"], int(Dd * cfg["mlp_ratio"]),
                              cfg["decoder_depth"])
+        self.ring, self.ring_block = ring_depths(max(self.enc.depth, self.dec.depth))
         for st in (self.enc, self.dec):
             if st.head_dim not in (16, 32, 64):
                 raise ops._lib.VitaeError(f"unsupported head_dim {st.head_dim} (kernels exist for 16/32/64)")
@@ -364,6 +377,7 @@ class MAEEngine:
         self.dpos = decoder_pos_embed.detach().reshape(self.L + 1, Dd).contiguous()
         self.plans: Dict[Tuple[int, int], MAEPlan] = {}
         self.lanes = _Lanes(dev)
+        self.reduce_lane = os.environ.get("VITAE_REDUCE_LANE", "1") != "0"   # column reductions on their own stream
         self.bg_stream: Optional[torch.cuda.Stream] = None     # edge-map target branch underneath the forward
         self._bg_done: Optional[torch.cuda.Event] = None
         self.cap_stream: Optional[torch.cuda.Stream] = None
@@ -517,9 +531,9 @@ class MAEEngine:
     def _g(self, name):   # fp32 gradient
         return self.flat.vg[name]
 
-    def _side(self, fn, reads=()):
+    def _side(self, fn, reads=(), lane: int = 0):
         if self.use_side_lane:
-            self.lanes.side(fn, reads)
+            self.lanes.side(fn, reads, lane if self.reduce_lane else 0)
         else:
             fn()
 
@@ -852,7 +866,7 @@ class MAEEngine:
     def _ln_in(self, pl: MAEPlan, M: int, D: int) -> torch.Tensor:
         """Buffer for the input gradient (dy) of the NEXT _ln_bwd call; the side lane reads it after the main lane has
         moved on, so main waits here only for the side reader of two calls ago."""
-        k = pl.ln_calls % RING
+        k = pl.ln_calls % self.ring
         self.lanes.before_write(("d_ln", k))
         return pl.d_ln[k][:M * D].view(M, D)
 
@@ -862,7 +876,7 @@ class MAEEngine:
         """LayerNorm backward.  Main lane (critical path): dres[out_idx] = (dres[dx_in_idx] if given) + LN'(dy), plus its
         bf16 copy dres16[out_idx].  Side lane: the column reductions -- affine gradients and ``bias_name`` (the bias whose
         gradient is the column sum of the new residual gradient).  ``dy`` must come from _ln_in().  Returns out_idx."""
-        k = pl.ln_calls % RING
+        k = pl.ln_calls % self.ring
         pl.ln_calls += 1
         dx_in = None if dx_in_idx is None else pl.dres[dx_in_idx][:M * D].view(M, D)
         dx_out = pl.dres[out_idx][:M * D].view(M, D)
@@ -898,7 +912,7 @@ class MAEEngine:
         for i in layers:
             pre = f"{st.prefix}.{i}"
             b, x_in = sb.blocks[i], sb.x[i]
-            hb = i & 1
+            hb = i % self.ring_block
             self._prefetch_block(st, sb, i - 1, with_acts=True)
             d_hid = pl.d_hid[hb][:M * hid].view(M, hid)
             dqkv = pl.dqkv[hb][:M * 3 * D].view(M, 3 * D)
@@ -922,7 +936,7 @@ class MAEEngine:
             self._side(side_fc1, reads=(("d_hid", hb),))
             d_ln = self._ln_in(pl, M, D)
             ops.gemm(d_hid, self._w(f"{pre}.mlp.fc1.weight"), M, D, hid, b_mn_major=True, out_bf16=d_ln, workspace=wsm)
-            nxt = (cur + 1) % RING
+            nxt = (cur + 1) % self.ring
             self._ln_bwd(pl, d_ln, b.xmid, f"{pre}.norm2", b.mean2, b.rstd2, cur, nxt, M, D, acc,
                          f"{pre}.attn.proj.bias", jobs=jobs, reads=job_reads)
             cur = nxt
@@ -943,12 +957,13 @@ class MAEEngine:
             self._side(side_qkv, reads=(("dqkv", hb),))
             d_ln = self._ln_in(pl, M, D)
             ops.gemm(dqkv, self._w(f"{pre}.attn.qkv.weight"), M, D, 3 * D, b_mn_major=True, out_bf16=d_ln, workspace=wsm)
-            nxt = (cur + 1) % RING
+            nxt = (cur + 1) % self.ring
             below = f"{st.prefix}.{i - 1}.mlp.fc2.bias" if i > 0 else None
             self._ln_bwd(pl, d_ln, x_in, f"{pre}.norm1", b.mean1, b.rstd1, cur, nxt, M, D, acc, below, jobs=jobs,
                          reads=job_reads)
             cur = nxt
-            self._side(lambda jobs=jobs: ops.block_colreduce(jobs, M, pl.bcr_ws, accumulate=acc), reads=tuple(job_reads))
+            self._side(lambda jobs=jobs: ops.block_colreduce(jobs, M, pl.bcr_ws, accumulate=acc), reads=tuple(job_reads),
+                       lane=1)
         return cur
 
     # ------------------------------------------------------------------------------------------------ data parallel

@@ -9,7 +9,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_longlong, c_size_t, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libvitae_b200.so")
+LIB_PATH = os.environ.get("VITAE_LIB") or os.path.join(PKG_DIR, "libvitae_b200.so")   # VITAE_LIB: an experiment build
 
 
 class VitaeError(RuntimeError):

@@ -37,6 +37,26 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def _build_variant(flags, variant: str, verbose: bool) -> str:
+    out_dir = os.path.join(BUILD_DIR, variant)
+    os.makedirs(out_dir, exist_ok=True)
+    out = LIB_PATH.replace(".so", f"_{variant}.so")
+    nvcc = _nvcc()
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(out_dir, src.replace(".cu", ".o"))
+        r = subprocess.run([nvcc, *flags, "-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        objs.append(obj)
+    r = subprocess.run([nvcc, "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        print(f"built {out}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = True) -> str:
     os.makedirs(BUILD_DIR, exist_ok=True)
     stamp = os.path.join(BUILD_DIR, "digest.txt")
@@ -47,6 +67,11 @@ def build(force: bool = False, verbose: bool = True) -> str:
         flags.append("-DVITAE_EPI_WARPS=" + os.environ["VITAE_EPI_WARPS"])
     if os.environ.get("VITAE_EPI_NOGELU") == "1":  # experiment only: GELU code compiled out of the GEMM epilogue
         flags.append("-DVITAE_EPI_NOGELU")
+    if os.environ.get("VITAE_PDL_EARLY") == "1":   # experiment: GEMM / attention let their dependents launch at their start
+        flags.append("-DVITAE_PDL_EARLY")
+    variant = os.environ.get("VITAE_BUILD_VARIANT")     # experiment builds go to libvitae_b200_<variant>.so (VITAE_LIB selects)
+    if variant:
+        return _build_variant(flags, variant, verbose)
     digest = _digest() + "".join(f for f in flags if f.startswith("-DVITAE"))
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB_PATH

@@ -101,7 +101,7 @@ template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N, int H,
                 float scale_log2) {
-    pdl_trigger();
+    PDL_TRIGGER_EARLY();
     pdl_wait();
     constexpr int LD = HD + 8;
     __shared__ __align__(16) __nv_bfloat16 sQ[TILE * LD];
@@ -176,6 +176,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
         mma_p_tile<HD>(o, s, sV[buf], lane);
         __syncthreads();
     }
+    PDL_TRIGGER_LATE();
     l0 = quad_sum(l0); l1 = quad_sum(l1);
     const float i0 = 1.f / l0, i1 = 1.f / l1;
     const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int N, int H,
                    float scale, float scale_log2) {
-    pdl_trigger();
+    PDL_TRIGGER_EARLY();
     pdl_wait();
     constexpr int LD = HD + 8;
     __shared__ __align__(16) __nv_bfloat16 sQ[TILE * LD];
@@ -283,6 +284,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
             cp_async_commit();
         }
     }
+    PDL_TRIGGER_LATE();
 #pragma unroll
     for (int j = 0; j < HD / 8; ++j) {
         const int d = 8 * j + 2 * (lane & 3);
@@ -295,7 +297,7 @@ template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
                     const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale, float scale_log2) {
-    pdl_trigger();
+    PDL_TRIGGER_EARLY();
     pdl_wait();
     constexpr int LD = HD + 8;
     __shared__ __align__(16) __nv_bfloat16 sQ[TILE * LD];
@@ -362,6 +364,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
             cp_async_commit();
         }
     }
+    PDL_TRIGGER_LATE();
     const int r0 = kv0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
 #pragma unroll
     for (int j = 0; j < HD / 8; ++j) {

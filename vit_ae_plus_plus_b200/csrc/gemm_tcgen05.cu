@@ -177,10 +177,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // PDL: this CTA now holds everything it will ever acquire (smem, TMEM columns), so the next kernel in the stream may
-    // start its own prologue; our first global access (TMA loads, epilogue operands) waits for the predecessor grid.
+    // PDL: our first global access (TMA loads, epilogue operands) waits for the predecessor grid; the next kernel in the
+    // stream may start its prologue once every CTA has issued its last MMA (PDL_TRIGGER_LATE below; ptx.cuh).
     if (threadIdx.x == 0) GEMM_TRACE(1);
-    pdl_trigger();
+    PDL_TRIGGER_EARLY();
     pdl_wait();
     if (threadIdx.x == 0) GEMM_TRACE(2);
 
@@ -250,6 +250,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 umma_commit(empty_bar + s * 8);  // frees the smem stage once these MMAs retire
             }
             umma_commit(tmem_full_bar);
+            PDL_TRIGGER_LATE();
             GEMM_TRACE(6);
         }
         __syncwarp();

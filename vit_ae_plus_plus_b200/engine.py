@@ -18,9 +18,11 @@ Data layout in HBM
 Execution
   one CUDA graph per (shape, input address) for the forward kernels and one for the backward kernels: ~500 kernel
   nodes are replayed with a single launch each (a ViT-B step is ~2 ms of device time; launching its kernels one by one
-  from Python costs ~12 ms).  Inside the backward graph the weight-gradient GEMMs, bias column sums and LayerNorm
-  partial reductions run on a side stream (they are not on the dgrad critical path), with per-buffer events
-  guarding every read-after-write / write-after-read pair between the two lanes.
+  from Python costs ~12 ms).  Inside the backward graph the weight-gradient GEMMs run on a side stream and the per-block
+  column reductions (bias sums, LayerNorm affine gradients) on a third (they are not on the dgrad critical path, which
+  is captured at a higher stream priority), with per-buffer events guarding every read-after-write / write-after-read
+  pair between the lanes and gradient rings deep enough that the chain never waits for a lane (_Lanes, ring_depths).
+  The edge-map target branch (input only) runs on a background stream underneath the forward.
 
 Mixed precision: bf16 tensor-core operands, fp32 accumulation, fp32 residual stream / LayerNorm statistics /
 loss / gradients of parameters (BASELINE.json north_star tolerance for this mode: 1e-2 relative).

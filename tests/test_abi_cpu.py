@@ -76,3 +76,15 @@ def test_model_refuses_cpu():
                              args=argparse.Namespace(perceptual_weight=0))
     with pytest.raises(VitaeError):
         m(torch.zeros(1, 1, 32, 32, 32))
+
+
+def test_ring_depths_defaults_and_overrides(monkeypatch):
+    """Gradient rings of the backward lanes: one slot per use in the whole backward by default, env overrides with floors."""
+    from vit_ae_plus_plus_b200 import engine
+    monkeypatch.delenv("VITAE_RING", raising=False)
+    monkeypatch.delenv("VITAE_RING_BLOCK", raising=False)
+    assert engine.ring_depths(12, 8) == (42, 12)
+    assert engine.ring_depths(24, 8) == (66, 24)
+    monkeypatch.setenv("VITAE_RING", "2")
+    monkeypatch.setenv("VITAE_RING_BLOCK", "1")
+    assert engine.ring_depths(12, 8) == (4, 2)

@@ -213,12 +213,16 @@ class _GraphSlot:
 # depth of the buffer rings shared between the backward lanes (MAEPlan): residual-stream gradients and LayerNorm inputs
 # (two per transformer block) / hidden and qkv gradients (one per block).  The main lane waits before it overwrites a
 # slot a side lane still reads, so the depth is how many blocks the side lanes may fall behind.
-# Default: one slot per use in the deepest stack (no slot is reused inside a backward stage; 0.6 GB at batch 4 for ViT-B:
-# measured 4.55 -> 4.39 ms per step against rings of 4 / 2).  VITAE_RING / VITAE_RING_BLOCK override (>= 4 / >= 2).
-def ring_depths(max_depth: int):
-    ring = int(os.environ.get("VITAE_RING", str(2 * max_depth + 2)))
-    ring_block = int(os.environ.get("VITAE_RING_BLOCK", str(max_depth)))
+# Default: one slot per use in the whole backward for the two-per-block rings (their index runs on across the decoder and
+# the encoder) and one per block of the deepest stack for the others: no slot is reused while a lane may still read it
+# (1 GB at batch 4 for ViT-B; measured 4.55 -> 4.39 ms per step against rings of 4 / 2 and another 0.03 ms for the
+# whole-backward depth).  VITAE_RING / VITAE_RING_BLOCK override (>= 4 / >= 2) when memory matters more.
+def ring_depths(enc_depth: int, dec_depth: int):
+    ring = int(os.environ.get("VITAE_RING", str(2 * (enc_depth + dec_depth) + 2)))
+    ring_block = int(os.environ.get("VITAE_RING_BLOCK", str(max(enc_depth, dec_depth))))
     return max(4, ring), max(2, ring_block)
+
+
 MAX_INPUT_ADDRESSES = 4   # input-volume addresses that get their own (zero-copy) graphs; others are copied (below)
 
 
@@ -368,7 +372,7 @@ class MAEEngine:
         self.enc = StackSpec("blocks", D, cfg["num_heads"], int(D * cfg["mlp_ratio"]), cfg["depth"])
         self.dec = StackSpec("decoder_blocks", Dd, cfg["decoder_num_heads"], int(Dd * cfg["mlp_ratio"]),
                              cfg["decoder_depth"])
-        self.ring, self.ring_block = ring_depths(max(self.enc.depth, self.dec.depth))
+        self.ring, self.ring_block = ring_depths(self.enc.depth, self.dec.depth)
         for st in (self.enc, self.dec):
             if st.head_dim not in (16, 32, 64):
                 raise ops._lib.VitaeError(f"unsupported head_dim {st.head_dim} (kernels exist for 16/32/64)")

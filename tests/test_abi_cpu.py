@@ -88,3 +88,25 @@ def test_ring_depths_defaults_and_overrides(monkeypatch):
     monkeypatch.setenv("VITAE_RING", "2")
     monkeypatch.setenv("VITAE_RING_BLOCK", "1")
     assert engine.ring_depths(12, 8) == (4, 2)
+
+
+def test_block_colreduce_workspace_covers_every_subset_of_the_jobs():
+    """The plan sizes ONE workspace for the six column-reduction jobs of a block; launches with fewer jobs (first / last
+    block, encoder-only backward) use more row slices and must still fit.  Host-side check only: without a GPU the call
+    gets past the workspace check and fails at the launch (regression: batch 16 failed with 'workspace too small')."""
+    import ctypes
+    import itertools
+    from vit_ae_plus_plus_b200 import _lib, ops
+    lib = _lib.load()
+    for D, hid in ((768, 3072), (512, 2048), (1024, 4096), (128, 512)):
+        cols = [hid, 3 * D, D, D, D, D]
+        for rows in (34, 516, 2052, 2064, 8208, 16416, 65664):
+            ws_bytes = ops.block_colreduce_workspace_bytes(rows, cols)
+            for n in range(1, 7):
+                for sub in itertools.combinations(cols, n):
+                    jobs = (_lib.ColJob * n)()
+                    for j, c in zip(jobs, sub):
+                        j.a, j.out0, j.cols, j.ld, j.a_is_bf16 = 0x1000, 0x2000, c, c, 1
+                    rc = lib.vitae_block_colreduce(jobs, n, rows, 0, ctypes.c_void_p(0x3000), ws_bytes, None)
+                    msg = lib.vitae_last_error().decode() if rc else ""
+                    assert "workspace too small" not in msg, (D, rows, sub, msg)

@@ -473,15 +473,18 @@ using namespace vitae;
 // One launch for up to 6 column-reduction jobs over matrices with the same number of rows (see block_colreduce_kernel).
 // jobs: HOST array of vitae_col_job, read during the call.  workspace: vitae_block_colreduce_workspace_bytes(...) bytes,
 // zero-filled before first use (ticket counters, self-resetting), not shared by concurrent calls.
+constexpr int BCR_MAX_SLICES = 32;
 static inline int bcr_slices(int rows, int strips) {
     int s = std::max(1, (6 * 148) / std::max(1, strips));
     s = std::min(s, std::max(1, rows / 32));
-    return std::min(s, 32);
+    return std::min(s, BCR_MAX_SLICES);
 }
 
+// Sized for the largest number of row slices any launch over `rows` rows can use: a launch with FEWER jobs than the set
+// the workspace was sized for has fewer strips and therefore more slices, so the bound must not depend on the strips.
 extern "C" size_t vitae_block_colreduce_workspace_bytes(int rows, int total_cols_padded) {
-    const int strips = total_cols_padded / CS_COLS;
-    return 4096 + static_cast<size_t>(2) * bcr_slices(rows, strips) * total_cols_padded * sizeof(float);
+    const int slices = std::min(BCR_MAX_SLICES, std::max(1, rows / 32));
+    return 4096 + static_cast<size_t>(2) * slices * total_cols_padded * sizeof(float);
 }
 
 extern "C" int vitae_block_colreduce(const vitae_col_job* jobs, int njobs, int rows, int accumulate, void* workspace,

@@ -20,7 +20,6 @@ import subprocess
 import sys
 import tempfile
 import time
-from functools import partial
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:

@@ -69,6 +69,8 @@ def build(force: bool = False, verbose: bool = True) -> str:
         flags.append("-DVITAE_EPI_NOGELU")
     if os.environ.get("VITAE_PDL_EARLY") == "1":   # experiment: GEMM / attention let their dependents launch at their start
         flags.append("-DVITAE_PDL_EARLY")
+    if os.environ.get("VITAE_ATTN_TAIL") == "1":   # experiment: attention loops bounded by the valid part of ragged tail tiles
+        flags.append("-DVITAE_ATTN_TAIL")
     variant = os.environ.get("VITAE_BUILD_VARIANT")     # experiment builds go to libvitae_b200_<variant>.so (VITAE_LIB selects)
     if variant:
         return _build_variant(flags, variant, verbose)

@@ -45,8 +45,11 @@ __device__ __forceinline__ void load_a_frags(const __nv_bfloat16* s, int warp, i
 }
 
 // acc[8][4] (16 x 64) = A(16 x HD, frags) * T^T where T is a padded smem tile [64][HD] (rows = output columns)
+// jpn: how many 16-column pairs of T hold valid rows (4 = all; VITAE_ATTN_TAIL passes fewer for a ragged tail tile: the
+// skipped accumulators stay 0)
 template <int HD>
-__device__ __forceinline__ void mma_a_tileT(float (&acc)[8][4], const uint32_t (&a)[HD / 16][4], const __nv_bfloat16* t, int lane) {
+__device__ __forceinline__ void mma_a_tileT(float (&acc)[8][4], const uint32_t (&a)[HD / 16][4], const __nv_bfloat16* t, int lane,
+                                            const int jpn = 4) {
     constexpr int LD = HD + 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -56,6 +59,7 @@ __device__ __forceinline__ void mma_a_tileT(float (&acc)[8][4], const uint32_t (
     for (int ks = 0; ks < HD / 16; ++ks) {
 #pragma unroll
         for (int jp = 0; jp < 4; ++jp) {
+            if (jp >= jpn) continue;
             uint32_t b0, b1, b2, b3;
             const uint32_t addr = smem_u32(t + (jp * 16 + (lane & 7) + 8 * (lane >> 4)) * LD + ks * 16 + 8 * ((lane >> 3) & 1));
             ldmatrix_x4(addr, b0, b1, b2, b3);
@@ -66,11 +70,14 @@ __device__ __forceinline__ void mma_a_tileT(float (&acc)[8][4], const uint32_t (
 }
 
 // acc[HD/8][4] (16 x HD) += P(16 x 64, fp32 in accumulator layout, rounded to bf16) * T, T = padded smem tile [64][HD]
+// ksn: how many 16-row steps of T (= 16-column pairs of P) are non-zero (4 = all)
 template <int HD>
-__device__ __forceinline__ void mma_p_tile(float (&acc)[HD / 8][4], const float (&p)[8][4], const __nv_bfloat16* t, int lane) {
+__device__ __forceinline__ void mma_p_tile(float (&acc)[HD / 8][4], const float (&p)[8][4], const __nv_bfloat16* t, int lane,
+                                           const int ksn = 4) {
     constexpr int LD = HD + 8;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
+        if (ks >= ksn) continue;
         uint32_t a[4];
         a[0] = pack_bf16(p[2 * ks][0], p[2 * ks][1]);
         a[1] = pack_bf16(p[2 * ks][2], p[2 * ks][3]);
@@ -95,6 +102,19 @@ __device__ __forceinline__ float quad_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
+
+// Ragged tails (opt-in build -DVITAE_ATTN_TAIL, not yet measured): the decoder's N = 513 = 8 * 64 + 1 leaves ONE valid
+// row / column in the 9th tile of every head, i.e. 81 tile pairs are computed where 64.3 are needed.  With the flag the
+// loops of a tail tile are bounded by its valid 16-column pairs and warps without a valid row skip the math (they still
+// take part in the cooperative loads and barriers).  Without it TAIL_PAIRS is the constant 4 and WARP_HAS_ROWS true: the
+// generated code is the unbounded one.
+#ifdef VITAE_ATTN_TAIL
+#define TAIL_PAIRS(first, n) min(4, (min(TILE, (n) - (first)) + 15) >> 4)
+#define WARP_HAS_ROWS(first, n) ((first) < (n))
+#else
+#define TAIL_PAIRS(first, n) 4
+#define WARP_HAS_ROWS(first, n) true
+#endif
 
 // ------------------------------------------------------------------------------------------------------ forward
 template <int HD>
@@ -142,13 +162,19 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
         }
         __syncthreads();
         if (t == 0) load_a_frags<HD>(sQ, warp, lane, qf);
+        if (!WARP_HAS_ROWS(q0 + warp * 16, N)) {       // no valid query row in this warp: barriers and loads only
+            __syncthreads();
+            continue;
+        }
 
         float s[8][4];
-        mma_a_tileT<HD>(s, qf, sK[buf], lane);
+        const int jpn = TAIL_PAIRS(t * TILE, N);
+        mma_a_tileT<HD>(s, qf, sK[buf], lane, jpn);
         const int kv0 = t * TILE;
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+            if (j >= 2 * jpn) continue;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int col = kv0 + 8 * j + 2 * (lane & 3) + (e & 1);
@@ -162,6 +188,10 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
         float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+            if (j >= 2 * jpn) {
+                s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+                continue;
+            }
             s[j][0] = exp2f(s[j][0] - mn0); s[j][1] = exp2f(s[j][1] - mn0);
             s[j][2] = exp2f(s[j][2] - mn1); s[j][3] = exp2f(s[j][3] - mn1);
             rs0 += s[j][0] + s[j][1];
@@ -173,7 +203,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
         for (int j = 0; j < HD / 8; ++j) {
             o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1;
         }
-        mma_p_tile<HD>(o, s, sV[buf], lane);
+        mma_p_tile<HD>(o, s, sV[buf], lane, jpn);
         __syncthreads();
     }
     PDL_TRIGGER_LATE();
@@ -263,20 +293,27 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
                 if (r1 < N) drow[r1] = dl1;
             }
         }
-        float s[8][4], dp[8][4];
-        mma_a_tileT<HD>(s, qf, sK, lane);
-        mma_a_tileT<HD>(dp, dof, sV, lane);
-        const int kv0 = t * TILE;
+        if (WARP_HAS_ROWS(q0 + warp * 16, N)) {        // (always true without VITAE_ATTN_TAIL)
+            float s[8][4], dp[8][4];
+            const int jpn = TAIL_PAIRS(t * TILE, N);
+            mma_a_tileT<HD>(s, qf, sK, lane, jpn);
+            mma_a_tileT<HD>(dp, dof, sV, lane, jpn);
+            const int kv0 = t * TILE;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 8; ++j) {
+                if (j >= 2 * jpn) {
+                    s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+                    continue;
+                }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int col = kv0 + 8 * j + 2 * (lane & 3) + (e & 1);
-                const float p = col < N ? exp2f(s[j][e] * scale_log2 - (e < 2 ? lse0 : lse1)) : 0.f;
-                s[j][e] = p * (dp[j][e] - (e < 2 ? dl0 : dl1));
+                for (int e = 0; e < 4; ++e) {
+                    const int col = kv0 + 8 * j + 2 * (lane & 3) + (e & 1);
+                    const float p = col < N ? exp2f(s[j][e] * scale_log2 - (e < 2 ? lse0 : lse1)) : 0.f;
+                    s[j][e] = p * (dp[j][e] - (e < 2 ? dl0 : dl1));
+                }
             }
+            mma_p_tile<HD>(dq, s, sK, lane, jpn);
         }
-        mma_p_tile<HD>(dq, s, sK, lane);
         __syncthreads();
         if (t + 1 < ntiles) {
             load_tile_async<HD>(sK, gk, pitch, (t + 1) * TILE, N);
@@ -342,21 +379,29 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
             load_a_frags<HD>(sK, warp, lane, kf);
             load_a_frags<HD>(sV, warp, lane, vf);
         }
-        float pt[8][4], dpt[8][4];
-        mma_a_tileT<HD>(pt, kf, sQ, lane);     // S^T  (kv rows x q cols)
-        mma_a_tileT<HD>(dpt, vf, sdO, lane);   // dP^T
+        if (WARP_HAS_ROWS(kv0 + warp * 16, N)) {       // (always true without VITAE_ATTN_TAIL)
+            float pt[8][4], dpt[8][4];
+            const int jpn = TAIL_PAIRS(t * TILE, N);   // valid query columns of this Q tile
+            mma_a_tileT<HD>(pt, kf, sQ, lane, jpn);     // S^T  (kv rows x q cols)
+            mma_a_tileT<HD>(dpt, vf, sdO, lane, jpn);   // dP^T
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 8; ++j) {
+                if (j >= 2 * jpn) {
+                    pt[j][0] = pt[j][1] = pt[j][2] = pt[j][3] = 0.f;
+                    dpt[j][0] = dpt[j][1] = dpt[j][2] = dpt[j][3] = 0.f;
+                    continue;
+                }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int qc = 8 * j + 2 * (lane & 3) + (e & 1);
-                const float p = exp2f(pt[j][e] * scale_log2 - sLse[qc]);
-                pt[j][e] = p;
-                dpt[j][e] = p * (dpt[j][e] - sDelta[qc]);
+                for (int e = 0; e < 4; ++e) {
+                    const int qc = 8 * j + 2 * (lane & 3) + (e & 1);
+                    const float p = exp2f(pt[j][e] * scale_log2 - sLse[qc]);
+                    pt[j][e] = p;
+                    dpt[j][e] = p * (dpt[j][e] - sDelta[qc]);
+                }
             }
+            mma_p_tile<HD>(dv, pt, sdO, lane, jpn);
+            mma_p_tile<HD>(dk, dpt, sQ, lane, jpn);
         }
-        mma_p_tile<HD>(dv, pt, sdO, lane);
-        mma_p_tile<HD>(dk, dpt, sQ, lane);
         __syncthreads();
         if (t + 1 < ntiles) {
             load_tile_async<HD>(sQ, gq, pitch, (t + 1) * TILE, N);

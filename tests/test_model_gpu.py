@@ -47,7 +47,34 @@ def run_ours(cfg, P, x, noise, mask_ratio, edge_w=0.0):
     return [l.detach().cpu() for l in losses], pred.detach().float().cpu(), mask.cpu(), grads, m
 
 
-def check_against_oracle(cfg, seed, B, mask_ratio, edge_w=0.0, grad_tol=2e-2):
+def _record(tag, per_param, extra=None):
+    """Per-parameter gradient errors of the BASELINE-sized runs go to gpurun_out/ (merged back from the GPU box; the
+    summaries under profiles/ are made from these files)."""
+    import json
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        rows = sorted(((e, n) for n, e in per_param.items()), reverse=True)
+        with open(os.path.join(out_dir, f"grad_errors_{tag}.json"), "w") as f:
+            json.dump({"tag": tag, "metric": "||g - g_oracle||_2 / ||g_oracle||_2 per parameter tensor", "worst": rows[:12],
+                       "n_params": len(rows), "n_above_1e-2": sum(e > 1e-2 for e, _ in rows),
+                       "median": rows[len(rows) // 2][0], **(extra or {})}, f, indent=1)
+    except OSError:
+        pass
+
+
+# North-star tolerance for the bf16 path: 1e-2.  Tensors allowed more, and why:
+#   * ``attn.qkv.bias``: its K third has an exactly-zero true gradient (softmax is invariant to a per-query shift of the
+#     scores, model/vit.py:117-119), so what any implementation produces there is rounding noise; it is compared on the
+#     Q and V thirds only (``_signal``).
+def _signal(name, t):
+    if name.endswith("attn.qkv.bias"):
+        d = t.shape[0] // 3
+        return torch.cat([t[:d], t[2 * d:]])
+    return t
+
+
+def check_against_oracle(cfg, seed, B, mask_ratio, edge_w=0.0, grad_tol=1e-2, tag=None):
     P = O.init_params(cfg, seed)
     V, C = cfg["volume_size"], cfg["in_chans"]
     x = torch.randn(B, C, V, V, V, generator=torch.Generator().manual_seed(seed + 1))
@@ -61,8 +88,12 @@ def check_against_oracle(cfg, seed, B, mask_ratio, edge_w=0.0, grad_tol=2e-2):
     assert abs(l[0].item() - l_ref[0].item()) <= TOL * abs(l_ref[0].item())
     assert relmax(pred, pred_ref) < TOL, relmax(pred, pred_ref)
     assert sorted(g) == sorted(g_ref)                                    # every trainable parameter gets a gradient
-    worst = max((relnorm(g[n], g_ref[n]), n) for n in g)
-    assert worst[0] < grad_tol, worst
+    per_param = {n: relnorm(_signal(n, g[n]), _signal(n, g_ref[n])) for n in g}
+    if tag:
+        _record(tag, per_param, {"batch": B, "mask_ratio": mask_ratio, "recon_rel_err": abs(l[2].item() - l_ref[2].item()) / abs(l_ref[2].item()),
+                                 "pred_relmax": relmax(pred, pred_ref)})
+    worst = max((e, n) for n, e in per_param.items())
+    assert worst[0] < grad_tol, (worst, sorted(((e, n) for n, e in per_param.items()), reverse=True)[:6])
     return worst
 
 
@@ -73,7 +104,7 @@ def test_small_configs_match_oracle(name, B, ratio):
 
 def test_tiny_with_edge_map_term_matches_oracle():
     # SURVEY row f-1 (interim torch ops on the kernels' pred): loss[0] = w*edge + recon, gradient flows through pred
-    check_against_oracle(O.CONFIGS["tiny"], 5, 2, 0.75, edge_w=0.05, grad_tol=3e-2)
+    check_against_oracle(O.CONFIGS["tiny"], 5, 2, 0.75, edge_w=0.05, grad_tol=1.5e-2)
 
 
 @pytest.mark.parametrize("name", ["tiny", "tiny_r50", "small"])
@@ -99,33 +130,21 @@ def test_matches_reference_golden(name):
 
 def test_vit_base_one_volume_matches_oracle():
     """configs[1] geometry (ViT-B/16, 128^3 x 4) at batch 1: the oracle's fp32 CPU forward+backward takes seconds."""
-    worst = check_against_oracle(O.CONFIGS["vit_base_128"], 3, 1, 0.75, grad_tol=3e-2)
+    worst = check_against_oracle(O.CONFIGS["vit_base_128"], 3, 1, 0.75, tag="vit_base_128_r75")
     print("worst grad rel err", worst)
 
 
 def test_vit_large_96_one_volume_matches_oracle():
     """configs[3] geometry (ViT-L/16, 96^3 x 4: D = 1024, 24 blocks, L = 216, keep = 54) at batch 1."""
-    worst = check_against_oracle(O.CONFIGS["vit_large_96"], 4, 1, 0.75, grad_tol=3e-2)
+    worst = check_against_oracle(O.CONFIGS["vit_large_96"], 4, 1, 0.75, tag="vit_large_96_r75")
     print("worst grad rel err", worst)
 
 
 @pytest.mark.parametrize("ratio", [0.25, 0.50])
-def test_vit_base_mask_ratio_sweep_forward_matches_oracle(ratio):
+def test_vit_base_mask_ratio_sweep_matches_oracle(ratio):
     """configs[4]: mask-ratio sweep on ViT-B 128^3 (keep = 384 / 256 kept patches, ragged encoder lengths 385 / 257):
-    loss, pred and mask of one volume against the oracle's forward (backward at these ratios is covered on the small
-    configurations by test_small_configs_match_oracle)."""
-    cfg = O.CONFIGS["vit_base_128"]
-    P = O.init_params(cfg, 6)
-    x = torch.randn(1, 4, 128, 128, 128, generator=torch.Generator().manual_seed(7))
-    torch.manual_seed(8)
-    noise = torch.rand(1, 512)
-    with torch.no_grad():
-        l_ref, pred_ref, mask_ref, _ = O.forward(x, P, cfg, ratio, noise, 0.0, with_edge=False)
-        m = build(cfg, P)
-        losses, pred, mask = m(x.cuda(), mask_ratio=ratio, noise=noise)
-    assert torch.equal(mask.cpu(), mask_ref) and int(mask.sum()) == 512 - int(512 * (1 - ratio))
-    assert abs(losses[2].item() - l_ref[2].item()) <= TOL * abs(l_ref[2].item())
-    assert relmax(pred.float(), pred_ref) < TOL
+    loss, pred, mask AND every parameter gradient of one volume against the oracle."""
+    check_against_oracle(O.CONFIGS["vit_base_128"], 6, 1, ratio, tag=f"vit_base_128_r{int(ratio * 100)}")
 
 
 def test_gradient_accumulation_and_zero_grad():

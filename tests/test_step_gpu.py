@@ -269,6 +269,42 @@ def test_loss_curve_100_steps_matches_oracle():
     assert curve[-1] < 0.9 * curve[0]                     # and it actually trains
 
 
+def test_loss_curve_vit_base_128_matches_oracle():
+    """The north star quotes the loss curve beside ViT-B 128^3: 30 AdamW steps of configs[1]'s model at batch 1 (the CPU
+    oracle needs ~1.5 s per step on the box's cores), same parameters / volumes / per-step mask noise on both sides, 1e-2
+    per step.  The curve is written to gpurun_out/loss_curve_vit_base_128.json (summarised under profiles/)."""
+    import json
+    import os
+    cfg = O.CONFIGS["vit_base_128"]
+    steps, lr = 30, 1.5e-4
+    P = O.init_params(cfg, 41)
+    g = torch.Generator().manual_seed(42)
+    xs = [torch.randn(1, 4, 128, 128, 128, generator=g) for _ in range(3)]
+    noises = [torch.rand(1, 512, generator=g) for _ in range(steps)]
+    leaves = {k: v.clone().requires_grad_(k not in O.FROZEN) for k, v in P.items()}
+    opt = torch.optim.AdamW(O.weight_decay_groups(list(leaves.items()), 0.05), lr=lr, betas=(0.9, 0.95))
+    ref = []
+    for i in range(steps):
+        losses, _, _, _ = O.forward(xs[i % 3], leaves, cfg, 0.75, noises[i], 0.0, with_edge=False)
+        opt.zero_grad(set_to_none=True)
+        losses[0].backward()
+        opt.step()
+        ref.append(float(losses[0].detach()))
+    _, _, _, curve, _ = _train(cfg, P, [x.cuda() for x in xs], noises, fused=True, graphs=True, steps=steps, lr=lr)
+    ref = torch.tensor(ref)
+    rel = ((curve - ref).abs() / ref.abs())
+    try:
+        out = os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        json.dump({"config": "vit_base_128 batch 1, AdamW lr 1.5e-4 wd 0.05 betas .9/.95, mask 0.75", "steps": steps,
+                   "b200": curve.tolist(), "oracle": ref.tolist(), "max_rel_err": rel.max().item()},
+                  open(os.path.join(out, "loss_curve_vit_base_128.json"), "w"), indent=1)
+    except OSError:
+        pass
+    assert rel.max().item() < 1e-2, rel
+    assert curve[-1] < curve[0]
+
+
 def test_device_prefetcher_delivers_batches_in_order_through_rotating_buffers():
     """utils.misc.DevicePrefetcher: batch k+1 is copied on a side stream while batch k is consumed; two device buffers
     per tensor slot are reused, so a wrong event ordering shows up as a batch overwritten before it was read."""

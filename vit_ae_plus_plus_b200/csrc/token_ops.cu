@@ -459,7 +459,16 @@ extern "C" int vitae_random_masking(const float* noise, int32_t* ids_shuffle, in
     int lp = 2;
     while (lp < L) lp <<= 1;
     const int threads = std::min(1024, std::max(32, lp / 2));
-    launch_kernel(random_masking_kernel, dim3(B), dim3(threads), lp * sizeof(unsigned long long), as_stream(stream), noise, ids_shuffle, ids_restore, mask, L, lp, len_keep);
+    const size_t key_bytes = lp * sizeof(unsigned long long);
+    if (key_bytes > 48 * 1024) {      // L > 4096 (keys padded to 8192): past the default 48 KB dynamic shared-memory limit
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(random_masking_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            if (e != cudaSuccess) return set_error(-3, "random_masking: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            attr_set = true;
+        }
+    }
+    launch_kernel(random_masking_kernel, dim3(B), dim3(threads), key_bytes, as_stream(stream), noise, ids_shuffle, ids_restore, mask, L, lp, len_keep);
     VITAE_CHECK_LAUNCH("random_masking");
     return 0;
 }

@@ -31,6 +31,7 @@ from __future__ import annotations
 
 import math
 import os
+import weakref
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -127,6 +128,11 @@ class FlatParams:
 
     def stamp_shadow(self) -> None:
         self.shadow_version = self._version()
+
+    def invalidate_shadow(self) -> None:
+        """Forces the next forward to re-cast the bf16 shadow.  Needed after writes that bump no version counter:
+        ``param.data.copy_()/mul_()`` (EMA, manual re-initialisation) go around autograd's bookkeeping."""
+        self.shadow_version = -1
 
     def grads_alias(self, thorough: bool = False) -> Optional[bool]:
         """True: every .grad is our view (accumulate in place); False: every .grad is None; None: mixed / foreign.
@@ -1034,7 +1040,7 @@ class FusedAdamW:
         flat = self.eng.flat
         by_ptr = {flat.v32[n].data_ptr(): n for n in flat.order}
         sig = tuple(tuple(p.data_ptr() for p in g["params"]) for g in optimizer.param_groups)
-        if self.bound == id(optimizer) and self.bound_sig == sig:
+        if self.bound == id(optimizer) and self.bound_sig == sig and self._state_aliased(optimizer):
             return True
         if len(optimizer.param_groups) > 8:
             return False
@@ -1067,9 +1073,25 @@ class FusedAdamW:
         for group in optimizer.param_groups:
             for p in group["params"]:
                 optimizer.state[p]["step"].fill_(float(self.host_steps))
+        if self.bound != id(optimizer):
+            # optimizer.state_dict() (misc.save_model, reference misc.py:302) must see the device-side step count
+            optimizer.register_state_dict_pre_hook(lambda opt, fo=weakref.ref(self): fo() and fo()._pre_state_dict(opt))
         self.bound = id(optimizer)
         self.bound_sig = tuple(tuple(p.data_ptr() for p in g["params"]) for g in optimizer.param_groups)
         return True
+
+    def _state_aliased(self, optimizer) -> bool:
+        """False once the optimizer's moments stopped being views of the flat buffers (``optimizer.load_state_dict``
+        installs fresh tensors): bind() then adopts the loaded state."""
+        flat = self.eng.flat
+        n = flat.order[0]
+        st = optimizer.state.get(flat.params[n])
+        o = flat.offsets[n][0]
+        return bool(st) and "exp_avg" in st and st["exp_avg"].data_ptr() == self.m[o:].data_ptr()
+
+    def _pre_state_dict(self, optimizer) -> None:
+        if self.bound == id(optimizer) and self._state_aliased(optimizer):
+            self.sync_state(optimizer)
 
     def _build_extras(self, optimizer, by_ptr) -> None:
         """(Re)builds the extras flat buffers from every optimizer parameter that is not an engine view."""

@@ -287,6 +287,21 @@ class MaskedAutoencoderViT(nn.Module):
             self._engine.wait_params()       # an overlapped optimizer step may still be writing the parameters
         return super().state_dict(*args, **kwargs)
 
+    # frozen helper modules of the reference model whose buffers / weights ride along in its checkpoints
+    # (model/vit_autoenc.py:54-57: SobelFilter3d, PerceptualLoss); here they are constants inside the kernels
+    REFERENCE_ONLY_PREFIXES = ("sobel_filter3D.", "perceptual_loss.")
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        """Accepts this module's own checkpoints and the reference's (``misc.load_model``, reference misc.py:320): keys of
+        the reference's frozen Sobel / VGG helpers are dropped before the (strict) match."""
+        sd = {k: v for k, v in state_dict.items() if not k.startswith(self.REFERENCE_ONLY_PREFIXES)}
+        if self._engine is not None:
+            self._engine.wait_params()
+        out = super().load_state_dict(sd, strict=strict, assign=assign)
+        if self._engine is not None:
+            self._engine.flat.invalidate_shadow()
+        return out
+
     # ------------------------------------------------------------------------------------------------ reference API
     def patchify(self, volume):
         """model/vit_autoenc.py:100-113: (N, C, V, V, V) -> (N, L, p^3*C), within-patch order (pz, py, px, c).

@@ -74,16 +74,22 @@ def release_autotune_scratch() -> None:
 
 
 class GrowBuf:
-    """A device byte buffer that grows on demand (never inside a CUDA-graph capture: the eager warm-up sizes it)."""
+    """A device byte buffer that grows on demand (never inside a CUDA-graph capture: the eager warm-up sizes it).
+    Superseded allocations are kept alive: CUDA graphs captured against the smaller buffer have its address baked in
+    and keep replaying into it (split-K slabs are scratch that lives from a GEMM to its finalize kernel, so the old and
+    the new buffer never need to agree), and freeing it would hand that memory to the caching allocator."""
 
     def __init__(self, device):
         self.device = device
         self.buf: Optional[torch.Tensor] = None
+        self.retired: list = []
 
     def get(self, nbytes: int) -> torch.Tensor:
         if self.buf is None or self.buf.numel() < nbytes:
             if torch.cuda.is_current_stream_capturing():
                 raise _lib.VitaeError("workspace would have to grow during CUDA-graph capture")
+            if self.buf is not None:
+                self.retired.append(self.buf)
             self.buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=self.device)
         return self.buf
 

@@ -7,8 +7,9 @@ import math
 def lr_at(epoch: float, lr: float, min_lr: float, warmup_epochs: float, epochs: float) -> float:
     if epoch < warmup_epochs:
         return lr * epoch / warmup_epochs
-    progress = (epoch - warmup_epochs) / (epochs - warmup_epochs)
-    return min_lr + (lr - min_lr) * 0.5 * (1.0 + math.cos(math.pi * progress))
+    # operation order as in the reference (pi * elapsed, then / span): the schedule is bit-identical, not 1 ulp off
+    phase = math.pi * (epoch - warmup_epochs) / (epochs - warmup_epochs)
+    return min_lr + (lr - min_lr) * 0.5 * (1.0 + math.cos(phase))
 
 
 def adjust_learning_rate(optimizer, epoch, args):

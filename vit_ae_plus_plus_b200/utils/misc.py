@@ -2,13 +2,18 @@
 not synchronise the device every step: windowed meters (misc.py:24-100), the iteration logger (:102-167), the
 GradScaler wrapper the k-fold scripts construct (:251-277), the gradient norm (:280-292), the scalar all-reduce
 (:332-340) and the timm-0.5.4 weight-decay grouping used at the optimizer call site
-(k_fold_cross_valid_combined_brats.py:168).  Checkpoint helpers, SLURM / OpenMPI launch parsing and the print patch are
-glue outside this package's path: use the reference's own ``utils.misc`` for those."""
+(k_fold_cross_valid_combined_brats.py:168), plus the launch / checkpoint glue the k-fold scripts call on this module
+(``init_distributed_mode`` :216-248 at brats.py:78, ``load_model`` :313-329 at :173, ``save_model`` :295-310 at :198,
+``setup_for_distributed`` :170-184, ``save_on_master`` :211-213), so that an overlay which shadows ``utils.misc`` with
+this module (overlay/utils/__init__.py) leaves no name of the reference's module unresolved."""
 from __future__ import annotations
 
+import builtins
 import datetime
+import os
 import time
 from collections import defaultdict, deque
+from pathlib import Path
 
 import torch
 import torch.distributed as dist
@@ -28,6 +33,64 @@ def get_rank() -> int:
 
 def is_main_process() -> bool:
     return get_rank() == 0
+
+
+def setup_for_distributed(is_master: bool) -> None:
+    """Silences ``print`` on non-master ranks (reference misc.py:170-184): ``print(..., force=True)`` always prints, and
+    so does every rank of a job with more than 8 ranks; printed lines carry a wall-clock stamp."""
+    plain = getattr(builtins.print, "_vitae_plain", builtins.print)     # re-patching must not stack time stamps
+
+    def print(*args, **kwargs):
+        force = kwargs.pop("force", False) or get_world_size() > 8
+        if is_master or force:
+            plain("[{}] ".format(datetime.datetime.now().time()), end="")
+            plain(*args, **kwargs)
+
+    print._vitae_plain = plain
+    builtins.print = print
+
+
+def save_on_master(*args, **kwargs) -> None:
+    if is_main_process():
+        torch.save(*args, **kwargs)
+
+
+def init_distributed_mode(args) -> None:
+    """Reads the launcher's environment into ``args`` and brings up the NCCL process group (reference misc.py:216-248).
+    Launch styles, in the reference's order: OpenMPI (``args.dist_on_itp``), torchrun (RANK / WORLD_SIZE / LOCAL_RANK),
+    SLURM (SLURM_PROCID); none of them -> ``args.distributed = False`` and printing stays on.  One process drives one
+    GPU; this package's models broadcast their parameters and average their gradients themselves once the group exists
+    (vit_ae_plus_plus_b200/dp.py), so no DistributedDataParallel wrapper follows."""
+    env = os.environ
+    if getattr(args, "dist_on_itp", False):
+        args.rank, args.world_size = int(env["OMPI_COMM_WORLD_RANK"]), int(env["OMPI_COMM_WORLD_SIZE"])
+        args.gpu = int(env["OMPI_COMM_WORLD_LOCAL_RANK"])
+        args.dist_url = "tcp://%s:%s" % (env["MASTER_ADDR"], env["MASTER_PORT"])
+        env["LOCAL_RANK"], env["RANK"], env["WORLD_SIZE"] = str(args.gpu), str(args.rank), str(args.world_size)
+    elif "RANK" in env and "WORLD_SIZE" in env:
+        args.rank, args.world_size, args.gpu = int(env["RANK"]), int(env["WORLD_SIZE"]), int(env["LOCAL_RANK"])
+    elif "SLURM_PROCID" in env:
+        args.rank = int(env["SLURM_PROCID"])
+        args.gpu = args.rank % torch.cuda.device_count()
+    else:
+        print("Not using distributed mode")
+        setup_for_distributed(is_master=True)
+        args.distributed = False
+        return
+    args.distributed = True
+    if not hasattr(args, "dist_url"):
+        args.dist_url = "env://"
+    if not hasattr(args, "world_size"):
+        args.world_size = int(env.get("WORLD_SIZE", env.get("SLURM_NTASKS", "1")))
+    # the reference always asks for NCCL; VITAE_DIST_BACKEND=gloo lets the CPU tests exercise the same code
+    args.dist_backend = env.get("VITAE_DIST_BACKEND", "nccl")
+    if args.dist_backend == "nccl":
+        torch.cuda.set_device(args.gpu)
+    print("| distributed init (rank {}): {}, gpu {}".format(args.rank, args.dist_url, args.gpu), flush=True)
+    dist.init_process_group(backend=args.dist_backend, init_method=args.dist_url, world_size=args.world_size,
+                            rank=args.rank)
+    dist.barrier()
+    setup_for_distributed(args.rank == 0)
 
 
 class SmoothedValue:
@@ -292,6 +355,38 @@ class NativeScalerWithGradNormCount:
         if self._fused is not None and state_dict:
             self._fused.ctl[0] = float(state_dict["scale"])
             self._fused.ctl[1] = float(state_dict["_growth_tracker"])
+
+
+def save_model(args, epoch, model, model_without_ddp, optimizer, loss_scaler):
+    """``<args.output_dir>/checkpoint-<epoch>.pth`` = {model, optimizer, epoch, scaler, args}, written by rank 0
+    (reference misc.py:295-310).  ``optimizer.state_dict()`` is complete at any time: the fused AdamW keeps its moments
+    in views the optimizer's state already points at and refreshes the per-parameter ``step`` through a state-dict
+    pre-hook (engine.FusedAdamW.bind).  ``loss_scaler=None`` is the reference's DeepSpeed branch."""
+    if loss_scaler is None:
+        model.save_checkpoint(save_dir=args.output_dir, tag="checkpoint-%s" % str(epoch), client_state={"epoch": epoch})
+        return
+    path = Path(args.output_dir) / ("checkpoint-%s.pth" % str(epoch))
+    save_on_master({"model": model_without_ddp.state_dict(), "optimizer": optimizer.state_dict(), "epoch": epoch,
+                    "scaler": loss_scaler.state_dict(), "args": args}, path)
+
+
+def load_model(args, model_without_ddp, optimizer, loss_scaler):
+    """Resumes model (+ optimizer and loss scale unless ``args.eval``) from ``args.resume`` (path or https URL); a falsy
+    ``args.resume`` is a no-op (reference misc.py:313-329).  Checkpoints hold an ``argparse.Namespace`` (``args``), hence
+    ``weights_only=False`` -- the reference's plain ``torch.load`` predates that default."""
+    if not getattr(args, "resume", None):
+        return
+    if args.resume.startswith("https"):
+        checkpoint = torch.hub.load_state_dict_from_url(args.resume, map_location="cpu", check_hash=True)
+    else:
+        checkpoint = torch.load(args.resume, map_location="cpu", weights_only=False)
+    model_without_ddp.load_state_dict(checkpoint["model"])
+    print("Resume checkpoint %s" % args.resume)
+    if "optimizer" in checkpoint and "epoch" in checkpoint and not getattr(args, "eval", False):
+        optimizer.load_state_dict(checkpoint["optimizer"])
+        if "scaler" in checkpoint:
+            loss_scaler.load_state_dict(checkpoint["scaler"])
+        print("With optim & sched!")
 
 
 def all_reduce_mean(x):

@@ -53,7 +53,7 @@ class _DeferredScalars:
         block = torch.stack(self.rows)
         local = block.tolist()                                    # the one device sync
         reduced = local
-        if self.writer is not None and misc.get_world_size() > 1:
+        if misc.get_world_size() > 1:      # every rank takes part (the reference all-reduces unconditionally, :78-81)
             torch.distributed.all_reduce(block)
             reduced = (block / misc.get_world_size()).tolist()
         for vals, red, (lr, x_axis, log_step) in zip(local, reduced, self.meta):
@@ -152,7 +152,7 @@ def train_one_epoch(model, criterion, data_loader, optimizer, device, epoch, los
         block = torch.stack([p[0] for p in pending])
         local = block.tolist()
         reduced = local
-        if log_writer is not None and misc.get_world_size() > 1:
+        if misc.get_world_size() > 1:      # every rank takes part, whether or not it owns a SummaryWriter
             torch.distributed.all_reduce(block)
             reduced = (block / misc.get_world_size()).tolist()
         for v, r, (_, lr, x_axis, log_step) in zip(local, reduced, pending):

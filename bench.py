@@ -51,6 +51,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not use CUDA graphs for the step")
+    ap.add_argument("--ingest", default="f16", choices=["f16", "bf16", "u16", "f32"],
+                    help="storage type of the host volumes of the e2e leg: raw intensities in f16 / bf16 / u16 are normalised "
+                         "on the device (misc.DevicePrefetcher(normalize=...), SURVEY row f-4); f32 = already normalised on the "
+                         "host, as the reference's Dataset does")
     ap.add_argument("--cpu-sample-steps", type=int, default=4)
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
@@ -311,55 +315,72 @@ def run_ours(a):
     # a copy stream by the package's DevicePrefetcher, the same wrapper train_one_stage_epoch puts around the DataLoader)
     # and every step's loss is read back to the host
     e2e = None
+    e2e_f32 = None
     if not a.no_e2e:
-        host = [torch.randn(B, C, V, V, V).pin_memory() for _ in range(2)]
+        def run_e2e(ingest):
+            """K steps through the public API with every batch crossing PCIe from pinned host memory.  ingest 'f32': the
+            host holds normalised fp32 volumes (what the reference's Dataset yields); otherwise raw intensities in the
+            storage type, z-scored per channel on the device right after the copy (dataset/egd_dataset/egd.py:45-47)."""
+            if ingest == "f32":
+                host = [torch.randn(B, C, V, V, V).pin_memory() for _ in range(2)]
+                norm = None
+            else:
+                raw = [(torch.randn(B, C, V, V, V) * 180.0 + 600.0).clamp_(0, 4000) for _ in range(2)]
+                dt = {"f16": torch.float16, "bf16": torch.bfloat16}.get(ingest)
+                host = [(r.to(dt) if dt is not None else r.round().to(torch.int32).to(torch.uint16)).pin_memory() for r in raw]
+                norm = "z_score_channel"
 
-        class _Batches:
-            def __init__(self, n):
-                self.n = n
+            class _Batches:
+                def __init__(self, n):
+                    self.n = n
 
-            def __len__(self):
-                return self.n
+                def __len__(self):
+                    return self.n
 
-            def __iter__(self):
-                for i in range(self.n):
-                    yield (host[i % 2],)
+                def __iter__(self):
+                    for i in range(self.n):
+                        yield (host[i % 2],)
 
-        for (x,) in misc.DevicePrefetcher(_Batches(6), dev):     # 2 device buffers x (eager, capture, replay)
-            step(x).item()
-        # every step's loss is read on the host inside the timed region, one step behind: a non-blocking D2H copy into
-        # pinned memory + an event, waited for while the next step is already enqueued (a blocking .item() per step
-        # exposes the host's launch time of the next step: 849 vs 9xx volumes/s)
-        losses_host = torch.empty(a.steps, dtype=torch.float32).pin_memory()
+            for (x,) in misc.DevicePrefetcher(_Batches(6), dev, normalize=norm):     # 2 device buffers x (eager, capture, replay)
+                step(x).item()
+            # every step's loss is read on the host inside the timed region, one step behind: a non-blocking D2H copy into
+            # pinned memory + an event, waited for while the next step is already enqueued (a blocking .item() per step
+            # exposes the host's launch time of the next step: 849 vs 9xx volumes/s)
+            losses_host = torch.empty(a.steps, dtype=torch.float32).pin_memory()
 
-        def timed_e2e():
-            evs, seen = [], []
-            barrier()
-            e0.record()
-            for k, (x,) in enumerate(misc.DevicePrefetcher(_Batches(a.steps), dev)):
-                losses_host[k:k + 1].copy_(step(x).detach().reshape(1), non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record()
-                evs.append(ev)
-                if k >= 1:
-                    evs[k - 1].synchronize()
-                    seen.append(float(losses_host[k - 1]))
-            evs[-1].synchronize()
-            seen.append(float(losses_host[a.steps - 1]))
-            e1.record()
-            barrier()
-            assert len(seen) == a.steps and all(math.isfinite(v) for v in seen), "e2e: a step's loss did not reach the host"
-            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return t.item()
-        # K steps are ~0.1 s: three repeats of exactly K steps each, the median is reported (all three are listed)
-        e2e_ms = sorted(timed_e2e() for _ in range(3))
-        e2e = {"value": eff_batch * a.steps / (e2e_ms[1] / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": host[0].numel() * host[0].element_size(), "d2h_bytes_per_step": 4,
-               "ms_per_step_repeats": [m / a.steps for m in e2e_ms],
-               "note": "median of 3 repeats of K steps; H2D of step k+1 overlaps step k (copy stream, 2 rotating device "
-                       "buffers); each step's loss is read on the host one step behind (non-blocking D2H into pinned memory + event)"}
+            def timed():
+                evs, seen = [], []
+                barrier()
+                e0.record()
+                for k, (x,) in enumerate(misc.DevicePrefetcher(_Batches(a.steps), dev, normalize=norm)):
+                    losses_host[k:k + 1].copy_(step(x).detach().reshape(1), non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    evs.append(ev)
+                    if k >= 1:
+                        evs[k - 1].synchronize()
+                        seen.append(float(losses_host[k - 1]))
+                evs[-1].synchronize()
+                seen.append(float(losses_host[a.steps - 1]))
+                e1.record()
+                barrier()
+                assert len(seen) == a.steps and all(math.isfinite(v) for v in seen), "e2e: a step's loss did not reach the host"
+                t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                return t.item()
+            # K steps are ~0.1 s: three repeats of exactly K steps each, the median is reported (all three are listed)
+            ms3 = sorted(timed() for _ in range(3))
+            return {"value": eff_batch * a.steps / (ms3[1] / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": host[0].numel() * host[0].element_size(), "d2h_bytes_per_step": 4,
+                    "host_dtype": str(host[0].dtype).replace("torch.", ""),
+                    "device_normalize": norm, "ms_per_step_repeats": [m / a.steps for m in ms3],
+                    "note": "median of 3 repeats of K steps; H2D of step k+1 (and its on-device normalisation) overlaps step k "
+                            "(copy stream, 2 rotating device buffers); each step's loss is read on the host one step behind "
+                            "(non-blocking D2H into pinned memory + event)"}
+        e2e = run_e2e(a.ingest)
+        if a.ingest != "f32":
+            e2e_f32 = run_e2e("f32")       # the reference's host-normalised fp32 batches, for comparison
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM): replay the step's GEMM launches alone, CUDA events
     roofline = None
@@ -430,7 +451,7 @@ def run_ours(a):
                        "parallelism": f"dp{world}", "cuda_graph": bool(model.use_cuda_graph),
                        "algorithmic_gflop_per_volume": f_step / 1e9,
                        "step_tflops": value * f_step / 1e12},
-            "final_loss": final_loss, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "final_loss": final_loss, "e2e": e2e, "e2e_f32_ingest": e2e_f32, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu, "dp_check": dp_check,
         }
         print(json.dumps(line), flush=True)

@@ -268,6 +268,25 @@ int vitae_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp
                      long long n, const unsigned char* group_of_chunk, const float* hyper, int ngroups,
                      const float* ctl, int max_blocks, void* stream);
 
+/* fp32 <-> bf16 copies of a flat gradient slice: the data-parallel exchange (one all-reduce of the trainable parameters'
+ * gradients per optimizer step; the reference scripts never wrap the model in DDP,
+ * k_fold_cross_valid_combined_brats.py:154) moves bf16 over NVLink and the slice is widened again afterwards.
+ * max_blocks > 0 caps the grid (the copies run beside the backward); 0 = default. */
+int vitae_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, int max_blocks, void* stream);
+int vitae_cast_bf16_to_f32(const void* src_bf16, float* dst, long long n, int max_blocks, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * On-device intensity normalisation of raw volumes, replacing Dataset._normalize_data
+ * (dataset/egd_dataset/egd.py:44-50, dataset/brats_dataset/brats.py:26-32), so that the host ships the storage type.
+ * raw: [B, C, voxels] of raw_type (0 f32, 1 f16, 2 bf16, 3 u16, 4 i16, 5 u8); out: fp32, same shape.
+ * mode 0: z-score per channel with the unbiased variance (egd.py:45-47); 1: z-score per sample (brats.py:27-29);
+ * 2: min-max of the sample to [-1, 1] (egd.py:48-50).  stats (optional): fp32 [groups][2] = {offset a, scale s} of
+ * out = (x - a) * s per group (B*C groups in mode 0, B otherwise).  voxels % 8 == 0.
+ * workspace: vitae_ingest_workspace_bytes(B, C) bytes.  Deterministic (fixed reduction order). */
+size_t vitae_ingest_workspace_bytes(int B, int C);
+int vitae_ingest_normalize(const void* raw, int raw_type, float* out, int B, int C, long long voxels, int mode,
+                           void* workspace, float* stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -431,6 +431,21 @@ def vit_forward(x, P: Params, cfg, global_pool: bool):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# Intensity normalisation of an incoming volume [C, V, V, V] -- Dataset._normalize_data
+# ----------------------------------------------------------------------------------------------------------------
+def normalize_volume(volume: torch.Tensor, mode: str) -> torch.Tensor:
+    volume = volume.float()
+    if mode == "z_score_channel":      # dataset/egd_dataset/egd.py:45-47 (torch.var: unbiased)
+        return (volume - torch.mean(volume, dim=[1, 2, 3], keepdim=True)) / torch.sqrt(torch.var(volume, dim=[1, 2, 3], keepdim=True))
+    if mode == "z_score_sample":       # dataset/brats_dataset/brats.py:27-29
+        return (volume - volume.mean()) / torch.sqrt(volume.var())
+    if mode == "min_max":              # egd.py:48-50, brats.py:30-32
+        max_val, min_val = volume.max(), volume.min()
+        return 2 * ((volume - min_val) / (max_val - min_val)) - 1
+    raise ValueError(mode)
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # Optimizer grouping + AdamW as built at the call site (k_fold_cross_valid_combined_brats.py:168-169)
 # ----------------------------------------------------------------------------------------------------------------
 def weight_decay_groups(named_params, weight_decay: float):

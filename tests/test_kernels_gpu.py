@@ -324,3 +324,47 @@ def test_edge_map_loss_kernels_match_oracle(B, C, V, p):
     want = 3.0 * pr.grad
     err = (got[:, 1:] - want).abs().max().item() / want.abs().max().item()
     assert err < 2e-2, err                                             # bf16 accumulation target
+
+
+# ------------------------------------------------------------------------------------------------ ingest (row f-4)
+@pytest.mark.parametrize("dtype", [torch.uint16, torch.int16, torch.uint8, torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("mode", ["z_score_channel", "z_score_sample", "min_max"])
+def test_ingest_normalize_matches_oracle(dtype, mode):
+    """On-device Dataset._normalize_data (egd.py:44-50, brats.py:26-32) for every storage dtype against the oracle applied
+    to the same raw values; fp32 tolerance 1e-5 of the value range (north star: 1e-3 rel fp32)."""
+    from vit_ae_plus_plus_b200.utils import misc
+    g = torch.Generator().manual_seed(11)
+    B, C, V = 3, 4, 32
+    base = torch.rand(B, C, V, V, V, generator=g)
+    if dtype == torch.uint8:
+        raw = (base * 255).round().to(torch.uint8)
+    elif dtype == torch.uint16:
+        raw = (base * 60000).round().to(torch.int32).to(torch.uint16)
+    elif dtype == torch.int16:
+        raw = (base * 4000 - 1000).round().to(torch.int16)
+    else:
+        raw = (base * 900 + 37).to(dtype)
+    if raw.dtype.is_floating_point:                        # channels differ in scale
+        raw[1, 2] = raw[1, 2] * 0.3
+    else:
+        raw[1, 2] = (raw[1, 2].to(torch.int32) // 3).to(dtype)
+    as_f32 = raw.to(torch.int32).float() if dtype == torch.uint16 else raw.float()
+    want = torch.stack([O.normalize_volume(as_f32[b], mode) for b in range(B)])
+    got = misc.normalize_volumes(raw.to(DEV), mode)
+    assert got.dtype == torch.float32 and got.shape == want.shape
+    assert (got.cpu() - want).abs().max().item() < 1e-5 * want.abs().max().item() + 1e-6
+    # deterministic: fixed reduction order
+    assert torch.equal(got, misc.normalize_volumes(raw.to(DEV), mode))
+
+
+def test_flat_casts_roundtrip():
+    from vit_ae_plus_plus_b200 import ops
+    x = torch.randn(1000003, device=DEV)
+    x[:4096] = x[:4096].bfloat16().float()
+    x[0] = float("inf")
+    h = torch.empty_like(x, dtype=torch.bfloat16)
+    ops.cast_f32_to_bf16(x, h)
+    assert torch.equal(h, x.bfloat16())
+    y = torch.empty_like(x)
+    ops.cast_bf16_to_f32(h, y)
+    assert torch.equal(y, h.float())

@@ -164,3 +164,30 @@ def test_live_reference_small_batch3():
     torch.testing.assert_close(pred, pred_ref, rtol=1e-5, atol=1e-5)
     for a, b in zip(losses, losses_ref):
         torch.testing.assert_close(a, b.detach().reshape(()), rtol=1e-5, atol=1e-6)
+
+
+def _reference_method(path, name):
+    """Compiles ONE method of a reference file without importing the module (its imports need torchio / the datasets):
+    the function's own source lines run unmodified in a namespace that holds what the file imports for it."""
+    import ast
+    src = open(path).read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"torch": torch, "sqrt": torch.sqrt, "np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference only exists in the build container")
+@pytest.mark.parametrize("dataset,z,mode", [("egd_dataset/egd.py", True, "z_score_channel"), ("egd_dataset/egd.py", False, "min_max"),
+                                            ("brats_dataset/brats.py", True, "z_score_sample"),
+                                            ("brats_dataset/brats.py", False, "min_max")])
+def test_normalize_volume_matches_reference_dataset_code(dataset, z, mode):
+    """oracle.normalize_volume against Dataset._normalize_data of the unmodified reference (egd.py:44-50, brats.py:26-32)."""
+    import types
+    ref = _reference_method(os.path.join("/root/reference/dataset", dataset), "_normalize_data")
+    g = torch.Generator().manual_seed(3)
+    vol = (torch.rand(4, 16, 16, 16, generator=g) * 4000).round()          # scanner-like intensities
+    vol[1] = vol[1] * 0.25 + 100
+    want = ref(types.SimpleNamespace(use_z_score=z), vol.clone())
+    got = O.normalize_volume(vol, mode)
+    torch.testing.assert_close(got, want, rtol=0, atol=0)

@@ -93,6 +93,11 @@ SIGNATURES = {
     "vitae_optim_workspace_bytes": (c_size_t, []),
     "vitae_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_int,
                                  c_void_p, c_int, c_void_p]),
+    "vitae_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
+    "vitae_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
+    "vitae_ingest_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "vitae_ingest_normalize": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p, c_void_p,
+                                       c_void_p]),
 }
 
 _lib = None

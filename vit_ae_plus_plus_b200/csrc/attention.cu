@@ -429,9 +429,10 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 
 }  // namespace vitae
 
-using namespace vitae;
+namespace vitae {
 
-extern "C" int vitae_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int hd, float scale, void* stream) {
+// Round-1 kernels, reachable through VITAE_ATTN_LEGACY=1 only (A/B timing against attention_tc.cu); not part of the C ABI.
+int attention_fwd_legacy(const void* qkv, void* out, float* lse, int B, int N, int H, int hd, float scale, void* stream) {
     VITAE_REQUIRE(qkv && out && lse, "attention_fwd: null pointer");
     VITAE_REQUIRE(B > 0 && N > 0 && H > 0 && (hd == 16 || hd == 32 || hd == 64), "attention_fwd: unsupported shape B=%d N=%d H=%d hd=%d", B, N, H, hd);
     dim3 grid(ceil_div(N, TILE), H, B);
@@ -446,8 +447,8 @@ extern "C" int vitae_attention_fwd(const void* qkv, void* out, float* lse, int B
     return 0;
 }
 
-extern "C" int vitae_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
-                                   void* dqkv, int B, int N, int H, int hd, float scale, void* stream) {
+int attention_bwd_legacy(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
+                         void* dqkv, int B, int N, int H, int hd, float scale, void* stream) {
     VITAE_REQUIRE(qkv && out && dout && lse && delta && dqkv, "attention_bwd: null pointer");
     VITAE_REQUIRE(B > 0 && N > 0 && H > 0 && (hd == 16 || hd == 32 || hd == 64), "attention_bwd: unsupported shape B=%d N=%d H=%d hd=%d", B, N, H, hd);
     cudaStream_t st = as_stream(stream);
@@ -473,3 +474,5 @@ extern "C" int vitae_attention_bwd(const void* qkv, const void* out, const void*
     VITAE_CHECK_LAUNCH("attention_bwd_dkv");
     return 0;
 }
+
+}  // namespace vitae

@@ -1,0 +1,861 @@
+// Fused multi-head self-attention on the Blackwell tensor cores: softmax(q k^T * scale) v and its backward with the
+// score tiles in tensor memory (model/vit.py:112-121 materialises a [B,H,N,N] fp32 score tensor).
+//
+// Layouts (unchanged C ABI, include/vitae_b200.h): qkv bf16 [B, N, 3, H, hd] = the qkv Linear's output as is,
+// out / dout bf16 [B, N, H*hd], lse / delta fp32 [B, H, N].  hd in {16, 32, 64}; N ragged.
+//
+// One CTA = one 128-row tile of one (batch, head): 6 warps.
+//   warp 0     TMA producer.  Operand tiles are 64-row x 128-byte boxes of a 3-D tensor map (columns, tokens, batch) in
+//              SWIZZLE_128B form; rows past a sample's N read as zero.  A head narrower than 64 columns shares its box
+//              with its neighbours: the MMA descriptors start (h*hd % 64) * 2 bytes into the swizzled row (K-major
+//              operands), or the MMA runs over all 64 columns and the epilogue keeps this head's (MN-major operands).
+//   warp 1     one thread issues tcgen05.mma (M = 128, N = 64 -- or the valid part of the last tile rounded up to 16 --,
+//              K = 16 per instruction), accumulators in TMEM, completion through tcgen05.commit -> mbarrier.
+//   warps 2-5  softmax: each thread owns one row (TMEM lane), reads its scores with tcgen05.ld -- no shuffles --, and
+//              writes P (bf16) into a swizzled shared-memory tile that is the A operand of the next MMA.
+//
+// forward   two passes over the kv tiles (the scores of a 128 x 513 tile do not fit the 256 TMEM columns a CTA gets when
+//           two CTAs share an SM, and recomputing q k^T costs ~2 % of the softmax time): pass 1 row maxima (FMNMX3),
+//           pass 2 p = ex2(s * scale*log2e - m) (one FFMA + one MUFU per score), row sums, O += P V accumulated in TMEM
+//           with no rescaling.  The column mask exists on the last kv tile only.
+// backward  dQ kernel (CTA per query tile: S and dP = dO V^T in TMEM, dS -> shared memory, dQ += dS K accumulated in
+//           TMEM; also writes delta = rowsum(dO * O)) and dK/dV kernel (CTA per kv tile: S^T and dP^T in TMEM,
+//           P^T / dS^T -> shared memory, dV += P^T dO and dK += dS^T Q in TMEM).  No atomics: deterministic.
+#include <stdlib.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vitae {
+
+constexpr float LOG2E_F = 1.4426950408889634f;
+constexpr float LN2_F = 0.6931471805599453f;
+constexpr int AT_THREADS = 192;
+constexpr int QT = 128;                 // rows per CTA (UMMA M)
+constexpr int KT = 64;                  // columns per score tile
+constexpr uint32_t BOX_BYTES = 64 * 128;   // one 64-row x 64-column bf16 box
+constexpr uint32_t ROWT_BYTES = 2 * BOX_BYTES;   // a 128-row operand tile = two boxes
+
+__device__ __forceinline__ uint32_t at_swz(int r, int j) { return static_cast<uint32_t>(r * 128 + ((j ^ (r & 7)) << 4)); }
+__device__ __forceinline__ void at_sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// K-major operand (rows x 64 bf16 in 128-byte swizzled rows), 16-element K step kk, starting sub_bytes into the row
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, uint32_t sub_bytes, int kk) {
+    return umma_smem_desc_sw128(tile + sub_bytes + kk * 32, 16, 1024);
+}
+// MN-major operand (K rows x 64 contiguous bf16): K step kk = 16 rows of 128 bytes
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kk) {
+    return umma_smem_desc_sw128(tile + kk * 2048, BOX_BYTES, 1024);
+}
+
+// ------------------------------------------------------------------------------------------------------ forward
+struct FwdSmem {
+    static constexpr int NSLOT = 6;     // ring of kv boxes
+    static constexpr int NS = 2;        // score tiles in TMEM
+    static constexpr uint32_t Q = 0;
+    static constexpr uint32_t KV = Q + ROWT_BYTES;
+    static constexpr uint32_t P = KV + NSLOT * BOX_BYTES;
+    static constexpr uint32_t BAR = P + 2 * ROWT_BYTES;
+    // barriers: q_full, kv_full[NSLOT], kv_empty[NSLOT], s_full[NS], s_free[NS], p_full[2], p_free[2], o_full
+    static constexpr int NBAR = 1 + 2 * NSLOT + 2 * NS + 4 + 1;
+    static constexpr uint32_t TOTAL = BAR + NBAR * 8 + 16 + 1024;
+    static constexpr uint32_t TMEM_COLS = 256;      // S tiles at 0 / 64, O at 128
+};
+
+template <int HD>
+__global__ void __launch_bounds__(AT_THREADS)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N,
+                   int H, float scale_log2) {
+    using S = FwdSmem;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw_u32);
+    const uint32_t q_full = base + S::BAR;
+    const uint32_t kv_full = q_full + 8, kv_empty = kv_full + S::NSLOT * 8;
+    const uint32_t s_full = kv_empty + S::NSLOT * 8, s_free = s_full + S::NS * 8;
+    const uint32_t p_full = s_free + S::NS * 8, p_free = p_full + 16, o_full = p_free + 16;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + S::BAR + S::NBAR * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * QT;
+    const int D = H * HD;
+    const int T = ceil_div(N, KT);
+    const int nv_last = N - (T - 1) * KT;                   // valid columns of the last kv tile
+    const int n16_last = (nv_last + 15) & ~15;
+    const int qcol = h * HD, kcol = D + h * HD, vcol = 2 * D + h * HD;
+
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmQKV);
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < S::NSLOT; ++i) { mbar_init(kv_full + i * 8, 1); mbar_init(kv_empty + i * 8, 1); }
+        for (int i = 0; i < S::NS; ++i) { mbar_init(s_full + i * 8, 1); mbar_init(s_free + i * 8, 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(p_full + i * 8, 128); mbar_init(p_free + i * 8, 1); }
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), S::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    PDL_TRIGGER_EARLY();
+    pdl_wait();
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- TMA producer
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, ROWT_BYTES);
+            tma_load_3d(base + S::Q, &tmQKV, q_full, qcol & ~63, q0, b);
+            tma_load_3d(base + S::Q + BOX_BYTES, &tmQKV, q_full, qcol & ~63, q0 + 64, b);
+            uint32_t seq = 0;
+            auto load = [&](int col, int t) {
+                const uint32_t slot = seq % S::NSLOT;
+                mbar_wait(kv_empty + slot * 8, ((seq / S::NSLOT) & 1) ^ 1);
+                mbar_arrive_expect_tx(kv_full + slot * 8, BOX_BYTES);
+                tma_load_3d(base + S::KV + slot * BOX_BYTES, &tmQKV, kv_full + slot * 8, col & ~63, t * KT, b);
+                ++seq;
+            };
+            // the order the MMA warp consumes them in: K tiles of pass 1, then K_t / V_(t-1) interleaved
+            for (int t = 0; t < T; ++t) load(kcol, t);
+            for (int t = 0; t < T; ++t) {
+                load(kcol, t);
+                if (t >= 1) load(vcol, t - 1);
+            }
+            load(vcol, T - 1);
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            const uint32_t subq = (qcol & 63) * 2, subk = (kcol & 63) * 2;
+            constexpr uint32_t idesc_pv = umma_idesc_bf16(QT, 64, 0u, 1u);
+            uint32_t seq = 0;
+            auto kv_wait = [&]() -> uint32_t {
+                const uint32_t slot = seq % S::NSLOT;
+                mbar_wait(kv_full + slot * 8, (seq / S::NSLOT) & 1);
+                ++seq;
+                return slot;
+            };
+            auto issue_s = [&](int it, int t) {          // S tile number `it` (both passes counted) = Q K_t^T
+                const uint32_t slot = kv_wait();
+                const int sb = it % S::NS;
+                mbar_wait(s_free + sb * 8, ((it / S::NS) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t idesc = umma_idesc_bf16(QT, t == T - 1 ? n16_last : KT, 0u, 0u);
+                const uint32_t sk = base + S::KV + slot * BOX_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < HD / 16; ++kk)
+                    umma_bf16(tmem_base + sb * KT, desc_kmajor(base + S::Q, subq, kk), desc_kmajor(sk, subk, kk), idesc, kk != 0);
+                umma_commit(kv_empty + slot * 8);
+                umma_commit(s_full + sb * 8);
+            };
+            auto issue_pv = [&](int u) {                 // O += P_u V_u
+                const uint32_t slot = kv_wait();
+                const int pb = u & 1;
+                mbar_wait(p_full + pb * 8, (u >> 1) & 1);
+                tc_fence_after();
+                const int nk = (u == T - 1 ? n16_last : KT) / 16;
+                const uint32_t sv = base + S::KV + slot * BOX_BYTES, sp = base + S::P + pb * ROWT_BYTES;
+#pragma unroll 1
+                for (int kk = 0; kk < nk; ++kk)
+                    umma_bf16(tmem_base + 128, desc_kmajor(sp, 0, kk), desc_mnmajor(sv, kk), idesc_pv, (u | kk) != 0);
+                umma_commit(kv_empty + slot * 8);
+                umma_commit(p_free + pb * 8);
+            };
+            mbar_wait(q_full, 0);
+            for (int t = 0; t < T; ++t) issue_s(t, t);
+            for (int t = 0; t < T; ++t) {
+                issue_s(T + t, t);
+                if (t >= 1) issue_pv(t - 1);
+            }
+            issue_pv(T - 1);
+            umma_commit(o_full);
+            PDL_TRIGGER_LATE();
+        }
+        __syncwarp();
+    } else {
+        // ---------------------------------------------------------------- softmax warps: one row per thread
+        const int q = warp & 3;                              // TMEM lane quadrant of this warp
+        const int row = q * 32 + lane;
+        const int grow = q0 + row;
+        const bool warp_valid = q0 + q * 32 < N;             // warps without a valid row only keep the barriers going
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        float mraw = -INFINITY;
+        for (int t = 0; t < T; ++t) {                        // pass 1: row maxima of the raw scores
+            const int sb = t % S::NS;
+            mbar_wait(s_full + sb * 8, (t / S::NS) & 1);
+            tc_fence_after();
+            if (warp_valid) {
+                const bool last = t == T - 1;
+                const int nch = last ? n16_last / 16 : 4;
+                uint32_t v[4][16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < nch) tmem_ld_32x16(t_lane + sb * KT + c * 16, v[c]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c >= nch) continue;
+                    if (last && (c + 1) * 16 > nv_last) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c * 16 + j < nv_last) mraw = fmaxf(mraw, __uint_as_float(v[c][j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2)
+                            mraw = fmax3(mraw, __uint_as_float(v[c][j]), __uint_as_float(v[c][j + 1]));
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(s_free + sb * 8);
+        }
+        const float msc = mraw * scale_log2;
+        float l = 0.f;
+        for (int t = 0; t < T; ++t) {                        // pass 2: p = 2^(s * scale_log2 - msc), row sums, P -> smem
+            const int it = T + t, sb = it % S::NS, pb = t & 1;
+            const bool last = t == T - 1;
+            const int nch = last ? n16_last / 16 : 4;
+            mbar_wait(s_full + sb * 8, (it / S::NS) & 1);
+            tc_fence_after();
+            uint32_t v[4][16];
+            if (warp_valid) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < nch) tmem_ld_32x16(t_lane + sb * KT + c * 16, v[c]);
+                tmem_ld_wait();
+            }
+            tc_fence_before();
+            mbar_arrive(s_free + sb * 8);                    // the scores are in registers: the MMA warp may reuse the tile
+            mbar_wait(p_free + pb * 8, ((t >> 1) & 1) ^ 1);  // P V of two tiles ago has read this P buffer
+            if (warp_valid) {
+                const uint32_t sp = base + S::P + pb * ROWT_BYTES;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c >= nch) continue;
+                    float p[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        p[j] = ex2_approx(fmaf(__uint_as_float(v[c][j]), scale_log2, -msc));
+                        if (last && c * 16 + j >= nv_last) p[j] = 0.f;
+                        l += p[j];
+                    }
+                    at_sts128(sp + at_swz(row, 2 * c), pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]),
+                              pack_bf16(p[6], p[7]));
+                    at_sts128(sp + at_swz(row, 2 * c + 1), pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]),
+                              pack_bf16(p[12], p[13]), pack_bf16(p[14], p[15]));
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(p_full + pb * 8);
+        }
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        if (warp_valid) {
+            const int subv = vcol & 63;
+            uint32_t o[HD / 16][16];
+#pragma unroll
+            for (int c = 0; c < HD / 16; ++c) tmem_ld_32x16(t_lane + 128 + subv + c * 16, o[c]);
+            tmem_ld_wait();
+            if (grow < N) {
+                const float inv = 1.f / l;
+                __nv_bfloat16* orow = out + (static_cast<size_t>(b) * N + grow) * D + h * HD;
+#pragma unroll
+                for (int c = 0; c < HD / 16; ++c) {
+                    uint4 lo, hi;
+                    lo.x = pack_bf16(__uint_as_float(o[c][0]) * inv, __uint_as_float(o[c][1]) * inv);
+                    lo.y = pack_bf16(__uint_as_float(o[c][2]) * inv, __uint_as_float(o[c][3]) * inv);
+                    lo.z = pack_bf16(__uint_as_float(o[c][4]) * inv, __uint_as_float(o[c][5]) * inv);
+                    lo.w = pack_bf16(__uint_as_float(o[c][6]) * inv, __uint_as_float(o[c][7]) * inv);
+                    hi.x = pack_bf16(__uint_as_float(o[c][8]) * inv, __uint_as_float(o[c][9]) * inv);
+                    hi.y = pack_bf16(__uint_as_float(o[c][10]) * inv, __uint_as_float(o[c][11]) * inv);
+                    hi.z = pack_bf16(__uint_as_float(o[c][12]) * inv, __uint_as_float(o[c][13]) * inv);
+                    hi.w = pack_bf16(__uint_as_float(o[c][14]) * inv, __uint_as_float(o[c][15]) * inv);
+                    *reinterpret_cast<uint4*>(orow + c * 16) = lo;
+                    *reinterpret_cast<uint4*>(orow + c * 16 + 8) = hi;
+                }
+                lse[(static_cast<size_t>(b) * H + h) * N + grow] = (msc + log2f(l)) * LN2_F;
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------------ backward: dQ
+struct DqSmem {
+    static constexpr int NSLOT = 4;
+    static constexpr uint32_t Q = 0;
+    static constexpr uint32_t DO = Q + ROWT_BYTES;
+    static constexpr uint32_t KV = DO + ROWT_BYTES;
+    static constexpr uint32_t DS = KV + NSLOT * BOX_BYTES;
+    static constexpr uint32_t BAR = DS + ROWT_BYTES;
+    // barriers: qdo_full, kv_full[NSLOT], kv_empty[NSLOT], sdp_full, sdp_free, ds_full, ds_free, dq_full
+    static constexpr int NBAR = 1 + 2 * NSLOT + 5;
+    static constexpr uint32_t TOTAL = BAR + NBAR * 8 + 16 + 1024;
+    static constexpr uint32_t TMEM_COLS = 256;      // S at 0, dP at 64, dQ at 128
+};
+
+template <int HD>
+__global__ void __launch_bounds__(AT_THREADS)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                      const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                      const float* __restrict__ lse, float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int N, int H,
+                      float scale, float scale_log2) {
+    using S = DqSmem;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw_u32);
+    const uint32_t qdo_full = base + S::BAR;
+    const uint32_t kv_full = qdo_full + 8, kv_empty = kv_full + S::NSLOT * 8;
+    const uint32_t sdp_full = kv_empty + S::NSLOT * 8, sdp_free = sdp_full + 8, ds_full = sdp_free + 8, ds_free = ds_full + 8,
+                   dq_full = ds_free + 8;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + S::BAR + S::NBAR * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * QT;
+    const int D = H * HD;
+    const int T = ceil_div(N, KT);
+    const int nv_last = N - (T - 1) * KT;
+    const int n16_last = (nv_last + 15) & ~15;
+    const int qcol = h * HD, kcol = D + h * HD, vcol = 2 * D + h * HD;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQKV);
+        tma_prefetch_desc(&tmDO);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(qdo_full, 1);
+        for (int i = 0; i < S::NSLOT; ++i) { mbar_init(kv_full + i * 8, 1); mbar_init(kv_empty + i * 8, 1); }
+        mbar_init(sdp_full, 1);
+        mbar_init(sdp_free, 128);
+        mbar_init(ds_full, 128);
+        mbar_init(ds_free, 1);
+        mbar_init(dq_full, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), S::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    PDL_TRIGGER_EARLY();
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(qdo_full, 2 * ROWT_BYTES);
+            tma_load_3d(base + S::Q, &tmQKV, qdo_full, qcol & ~63, q0, b);
+            tma_load_3d(base + S::Q + BOX_BYTES, &tmQKV, qdo_full, qcol & ~63, q0 + 64, b);
+            tma_load_3d(base + S::DO, &tmDO, qdo_full, qcol & ~63, q0, b);
+            tma_load_3d(base + S::DO + BOX_BYTES, &tmDO, qdo_full, qcol & ~63, q0 + 64, b);
+            uint32_t seq = 0;
+            for (int t = 0; t < T; ++t) {
+#pragma unroll
+                for (int which = 0; which < 2; ++which) {
+                    const uint32_t slot = seq % S::NSLOT;
+                    mbar_wait(kv_empty + slot * 8, ((seq / S::NSLOT) & 1) ^ 1);
+                    mbar_arrive_expect_tx(kv_full + slot * 8, BOX_BYTES);
+                    tma_load_3d(base + S::KV + slot * BOX_BYTES, &tmQKV, kv_full + slot * 8, (which ? vcol : kcol) & ~63, t * KT, b);
+                    ++seq;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t subq = (qcol & 63) * 2, subk = (kcol & 63) * 2, subv = (vcol & 63) * 2;
+            constexpr uint32_t idesc_dq = umma_idesc_bf16(QT, 64, 0u, 1u);
+            uint32_t seq = 0;
+            auto kv_wait = [&]() -> uint32_t {
+                const uint32_t slot = seq % S::NSLOT;
+                mbar_wait(kv_full + slot * 8, (seq / S::NSLOT) & 1);
+                ++seq;
+                return slot;
+            };
+            auto issue_dq = [&](int u, uint32_t slot_k) {            // dQ += dS_u K_u
+                mbar_wait(ds_full, u & 1);
+                tc_fence_after();
+                const int nk = (u == T - 1 ? n16_last : KT) / 16;
+                const uint32_t sk = base + S::KV + slot_k * BOX_BYTES;
+#pragma unroll 1
+                for (int kk = 0; kk < nk; ++kk)
+                    umma_bf16(tmem_base + 128, desc_kmajor(base + S::DS, 0, kk), desc_mnmajor(sk, kk), idesc_dq, (u | kk) != 0);
+                umma_commit(kv_empty + slot_k * 8);
+                umma_commit(ds_free);
+            };
+            mbar_wait(qdo_full, 0);
+            uint32_t prev_k = 0;
+            for (int t = 0; t < T; ++t) {
+                const uint32_t slot_k = kv_wait();
+                const uint32_t slot_v = kv_wait();
+                mbar_wait(sdp_free, (t & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t idesc = umma_idesc_bf16(QT, t == T - 1 ? n16_last : KT, 0u, 0u);
+                const uint32_t sk = base + S::KV + slot_k * BOX_BYTES, sv = base + S::KV + slot_v * BOX_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < HD / 16; ++kk)     // S = Q K^T
+                    umma_bf16(tmem_base, desc_kmajor(base + S::Q, subq, kk), desc_kmajor(sk, subk, kk), idesc, kk != 0);
+#pragma unroll
+                for (int kk = 0; kk < HD / 16; ++kk)     // dP = dO V^T
+                    umma_bf16(tmem_base + 64, desc_kmajor(base + S::DO, subq, kk), desc_kmajor(sv, subv, kk), idesc, kk != 0);
+                umma_commit(kv_empty + slot_v * 8);
+                umma_commit(sdp_full);
+                if (t >= 1) issue_dq(t - 1, prev_k);
+                prev_k = slot_k;
+            }
+            issue_dq(T - 1, prev_k);
+            umma_commit(dq_full);
+            PDL_TRIGGER_LATE();
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int grow = q0 + row;
+        const bool warp_valid = q0 + q * 32 < N;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        // this row's log-sum-exp (base 2) and delta = rowsum(dO * O); delta also goes to global memory for the dK/dV kernel
+        float lse2 = 0.f, dl = 0.f;
+        if (grow < N) {
+            lse2 = lse[(static_cast<size_t>(b) * H + h) * N + grow] * LOG2E_F;
+            const uint4* po = reinterpret_cast<const uint4*>(out + (static_cast<size_t>(b) * N + grow) * D + h * HD);
+            const uint4* pg = reinterpret_cast<const uint4*>(dout + (static_cast<size_t>(b) * N + grow) * D + h * HD);
+#pragma unroll
+            for (int i = 0; i < HD / 8; ++i) {
+                const uint4 a = po[i], g = pg[i];
+                const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+                const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&g);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 af = __bfloat1622float2(ah[j]), gf = __bfloat1622float2(gh[j]);
+                    dl = fmaf(af.x, gf.x, dl);
+                    dl = fmaf(af.y, gf.y, dl);
+                }
+            }
+            delta[(static_cast<size_t>(b) * H + h) * N + grow] = dl;
+        }
+        for (int t = 0; t < T; ++t) {
+            const bool last = t == T - 1;
+            const int nch = last ? n16_last / 16 : 4;
+            mbar_wait(sdp_full, t & 1);
+            tc_fence_after();
+            mbar_wait(ds_free, (t & 1) ^ 1);                 // dQ MMA of the previous tile has read the dS buffer
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t sv[2][16], dv[2][16];
+                if (warp_valid) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        if (2 * half + c < nch) {
+                            tmem_ld_32x16(t_lane + (2 * half + c) * 16, sv[c]);
+                            tmem_ld_32x16(t_lane + 64 + (2 * half + c) * 16, dv[c]);
+                        }
+                    tmem_ld_wait();
+                }
+                if (half == 1) {
+                    tc_fence_before();
+                    mbar_arrive(sdp_free);                   // both score tiles are in registers
+                }
+                if (warp_valid) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int cc = 2 * half + c;
+                        if (cc >= nch) continue;
+                        float ds[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float p = ex2_approx(fmaf(__uint_as_float(sv[c][j]), scale_log2, -lse2));
+                            if (last && cc * 16 + j >= nv_last) p = 0.f;
+                            ds[j] = p * (__uint_as_float(dv[c][j]) - dl);
+                        }
+                        at_sts128(base + S::DS + at_swz(row, 2 * cc), pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]),
+                                  pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
+                        at_sts128(base + S::DS + at_swz(row, 2 * cc + 1), pack_bf16(ds[8], ds[9]), pack_bf16(ds[10], ds[11]),
+                                  pack_bf16(ds[12], ds[13]), pack_bf16(ds[14], ds[15]));
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(ds_full);
+        }
+        mbar_wait(dq_full, 0);
+        tc_fence_after();
+        if (warp_valid) {
+            const int subk = kcol & 63;          // dQ = dS K: the MMA ran over the 64 columns of K's box
+            uint32_t o[HD / 16][16];
+#pragma unroll
+            for (int c = 0; c < HD / 16; ++c) tmem_ld_32x16(t_lane + 128 + subk + c * 16, o[c]);
+            tmem_ld_wait();
+            if (grow < N) {
+                __nv_bfloat16* drow = dqkv + (static_cast<size_t>(b) * N + grow) * (3 * D) + h * HD;
+#pragma unroll
+                for (int c = 0; c < HD / 16; ++c) {
+                    uint4 lo, hi;
+                    lo.x = pack_bf16(__uint_as_float(o[c][0]) * scale, __uint_as_float(o[c][1]) * scale);
+                    lo.y = pack_bf16(__uint_as_float(o[c][2]) * scale, __uint_as_float(o[c][3]) * scale);
+                    lo.z = pack_bf16(__uint_as_float(o[c][4]) * scale, __uint_as_float(o[c][5]) * scale);
+                    lo.w = pack_bf16(__uint_as_float(o[c][6]) * scale, __uint_as_float(o[c][7]) * scale);
+                    hi.x = pack_bf16(__uint_as_float(o[c][8]) * scale, __uint_as_float(o[c][9]) * scale);
+                    hi.y = pack_bf16(__uint_as_float(o[c][10]) * scale, __uint_as_float(o[c][11]) * scale);
+                    hi.z = pack_bf16(__uint_as_float(o[c][12]) * scale, __uint_as_float(o[c][13]) * scale);
+                    hi.w = pack_bf16(__uint_as_float(o[c][14]) * scale, __uint_as_float(o[c][15]) * scale);
+                    *reinterpret_cast<uint4*>(drow + c * 16) = lo;
+                    *reinterpret_cast<uint4*>(drow + c * 16 + 8) = hi;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------------ backward: dK / dV
+struct DkvSmem {
+    static constexpr int NSLOT = 4;
+    static constexpr uint32_t K = 0;
+    static constexpr uint32_t V = K + ROWT_BYTES;
+    static constexpr uint32_t RING = V + ROWT_BYTES;             // Q_t / dO_t boxes
+    static constexpr uint32_t PT = RING + NSLOT * BOX_BYTES;
+    static constexpr uint32_t DST = PT + ROWT_BYTES;
+    static constexpr uint32_t STATS = DST + ROWT_BYTES;          // lse2[2][64], delta[2][64]
+    static constexpr uint32_t BAR = STATS + 4 * 64 * 4;
+    // barriers: kv_full, r_full[NSLOT], r_empty[NSLOT], sdp_full, sdp_free, pds_full, pds_free, dkv_full
+    static constexpr int NBAR = 1 + 2 * NSLOT + 5;
+    static constexpr uint32_t TOTAL = BAR + NBAR * 8 + 16 + 1024;
+    static constexpr uint32_t TMEM_COLS = 256;      // S^T at 0, dP^T at 64, dK at 128, dV at 192
+};
+
+template <int HD>
+__global__ void __launch_bounds__(AT_THREADS)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                       const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int N,
+                       int H, float scale, float scale_log2) {
+    using S = DkvSmem;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw_u32);
+    const uint32_t kv_full = base + S::BAR;
+    const uint32_t r_full = kv_full + 8, r_empty = r_full + S::NSLOT * 8;
+    const uint32_t sdp_full = r_empty + S::NSLOT * 8, sdp_free = sdp_full + 8, pds_full = sdp_free + 8, pds_free = pds_full + 8,
+                   dkv_full = pds_free + 8;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + S::BAR + S::NBAR * 8);
+    float* s_lse = reinterpret_cast<float*>(sm + S::STATS);      // [2][64]
+    float* s_del = s_lse + 128;                                  // [2][64]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.y, b = blockIdx.z, kv0 = blockIdx.x * QT;
+    const int D = H * HD;
+    const int T = ceil_div(N, KT);                   // query tiles of 64 rows
+    const int nv_last = N - (T - 1) * KT;
+    const int n16_last = (nv_last + 15) & ~15;
+    const int qcol = h * HD, kcol = D + h * HD, vcol = 2 * D + h * HD;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQKV);
+        tma_prefetch_desc(&tmDO);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < S::NSLOT; ++i) { mbar_init(r_full + i * 8, 1); mbar_init(r_empty + i * 8, 1); }
+        mbar_init(sdp_full, 1);
+        mbar_init(sdp_free, 128);
+        mbar_init(pds_full, 128);
+        mbar_init(pds_free, 1);
+        mbar_init(dkv_full, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), S::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    PDL_TRIGGER_EARLY();
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(kv_full, 2 * ROWT_BYTES);
+            tma_load_3d(base + S::K, &tmQKV, kv_full, kcol & ~63, kv0, b);
+            tma_load_3d(base + S::K + BOX_BYTES, &tmQKV, kv_full, kcol & ~63, kv0 + 64, b);
+            tma_load_3d(base + S::V, &tmQKV, kv_full, vcol & ~63, kv0, b);
+            tma_load_3d(base + S::V + BOX_BYTES, &tmQKV, kv_full, vcol & ~63, kv0 + 64, b);
+            uint32_t seq = 0;
+            for (int t = 0; t < T; ++t) {
+#pragma unroll
+                for (int which = 0; which < 2; ++which) {     // Q_t, then dO_t
+                    const uint32_t slot = seq % S::NSLOT;
+                    mbar_wait(r_empty + slot * 8, ((seq / S::NSLOT) & 1) ^ 1);
+                    mbar_arrive_expect_tx(r_full + slot * 8, BOX_BYTES);
+                    tma_load_3d(base + S::RING + slot * BOX_BYTES, which ? &tmDO : &tmQKV, r_full + slot * 8, qcol & ~63, t * KT, b);
+                    ++seq;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t subq = (qcol & 63) * 2, subk = (kcol & 63) * 2, subv = (vcol & 63) * 2;
+            constexpr uint32_t idesc_acc = umma_idesc_bf16(QT, 64, 0u, 1u);
+            uint32_t seq = 0;
+            auto r_wait = [&]() -> uint32_t {
+                const uint32_t slot = seq % S::NSLOT;
+                mbar_wait(r_full + slot * 8, (seq / S::NSLOT) & 1);
+                ++seq;
+                return slot;
+            };
+            auto issue_dkv = [&](int u, uint32_t slot_q, uint32_t slot_do) {     // dV += P_u^T dO_u, dK += dS_u^T Q_u
+                mbar_wait(pds_full, u & 1);
+                tc_fence_after();
+                const int nk = (u == T - 1 ? n16_last : KT) / 16;
+                const uint32_t sq = base + S::RING + slot_q * BOX_BYTES, sdo = base + S::RING + slot_do * BOX_BYTES;
+#pragma unroll 1
+                for (int kk = 0; kk < nk; ++kk)
+                    umma_bf16(tmem_base + 192, desc_kmajor(base + S::PT, 0, kk), desc_mnmajor(sdo, kk), idesc_acc, (u | kk) != 0);
+#pragma unroll 1
+                for (int kk = 0; kk < nk; ++kk)
+                    umma_bf16(tmem_base + 128, desc_kmajor(base + S::DST, 0, kk), desc_mnmajor(sq, kk), idesc_acc, (u | kk) != 0);
+                umma_commit(r_empty + slot_q * 8);
+                umma_commit(r_empty + slot_do * 8);
+                umma_commit(pds_free);
+            };
+            mbar_wait(kv_full, 0);
+            uint32_t prev_q = 0, prev_do = 0;
+            for (int t = 0; t < T; ++t) {
+                const uint32_t slot_q = r_wait();
+                const uint32_t slot_do = r_wait();
+                mbar_wait(sdp_free, (t & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t idesc = umma_idesc_bf16(QT, t == T - 1 ? n16_last : KT, 0u, 0u);
+                const uint32_t sq = base + S::RING + slot_q * BOX_BYTES, sdo = base + S::RING + slot_do * BOX_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < HD / 16; ++kk)     // S^T = K Q_t^T
+                    umma_bf16(tmem_base, desc_kmajor(base + S::K, subk, kk), desc_kmajor(sq, subq, kk), idesc, kk != 0);
+#pragma unroll
+                for (int kk = 0; kk < HD / 16; ++kk)     // dP^T = V dO_t^T
+                    umma_bf16(tmem_base + 64, desc_kmajor(base + S::V, subv, kk), desc_kmajor(sdo, subq, kk), idesc, kk != 0);
+                umma_commit(sdp_full);
+                if (t >= 1) issue_dkv(t - 1, prev_q, prev_do);
+                prev_q = slot_q;
+                prev_do = slot_do;
+            }
+            issue_dkv(T - 1, prev_q, prev_do);
+            umma_commit(dkv_full);
+            PDL_TRIGGER_LATE();
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                   // kv row of this thread
+        const int grow = kv0 + row;
+        const bool warp_valid = kv0 + q * 32 < N;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const int st = threadIdx.x - 64;                 // 0..127 among the softmax threads
+        const float* lrow = lse + (static_cast<size_t>(b) * H + h) * N;
+        const float* drow = delta + (static_cast<size_t>(b) * H + h) * N;
+        auto stage = [&](int t) {                        // statistics of query tile t -> shared memory (buffer t & 1)
+            const int c = st & 63, qi = t * KT + c;
+            if (st < 64) s_lse[(t & 1) * 64 + c] = qi < N ? lrow[qi] * LOG2E_F : INFINITY;   // padded query rows: p = 0
+            else s_del[(t & 1) * 64 + c] = qi < N ? drow[qi] : 0.f;
+        };
+        stage(0);
+        named_bar_sync(1, 128);
+        for (int t = 0; t < T; ++t) {
+            const bool last = t == T - 1;
+            const int nch = last ? n16_last / 16 : 4;
+            if (t + 1 < T) stage(t + 1);
+            const float* sl = s_lse + (t & 1) * 64;
+            const float* sd = s_del + (t & 1) * 64;
+            mbar_wait(sdp_full, t & 1);
+            tc_fence_after();
+            mbar_wait(pds_free, (t & 1) ^ 1);            // the dK / dV MMAs of the previous tile have read P^T / dS^T
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t sv[2][16], dv[2][16];
+                if (warp_valid) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        if (2 * half + c < nch) {
+                            tmem_ld_32x16(t_lane + (2 * half + c) * 16, sv[c]);
+                            tmem_ld_32x16(t_lane + 64 + (2 * half + c) * 16, dv[c]);
+                        }
+                    tmem_ld_wait();
+                }
+                if (half == 1) {
+                    tc_fence_before();
+                    mbar_arrive(sdp_free);
+                }
+                if (warp_valid) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int cc = 2 * half + c;
+                        if (cc >= nch) continue;
+                        float p[16], ds[16];
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 l4 = *reinterpret_cast<const float4*>(sl + cc * 16 + 4 * j4);
+                            const float4 d4 = *reinterpret_cast<const float4*>(sd + cc * 16 + 4 * j4);
+                            const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int j = 4 * j4 + e;
+                                p[j] = ex2_approx(fmaf(__uint_as_float(sv[c][j]), scale_log2, -lv[e]));
+                                ds[j] = p[j] * (__uint_as_float(dv[c][j]) - dd[e]);
+                            }
+                        }
+                        at_sts128(base + S::PT + at_swz(row, 2 * cc), pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]),
+                                  pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+                        at_sts128(base + S::PT + at_swz(row, 2 * cc + 1), pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]),
+                                  pack_bf16(p[12], p[13]), pack_bf16(p[14], p[15]));
+                        at_sts128(base + S::DST + at_swz(row, 2 * cc), pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]),
+                                  pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
+                        at_sts128(base + S::DST + at_swz(row, 2 * cc + 1), pack_bf16(ds[8], ds[9]), pack_bf16(ds[10], ds[11]),
+                                  pack_bf16(ds[12], ds[13]), pack_bf16(ds[14], ds[15]));
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(pds_full);
+            named_bar_sync(1, 128);      // next tile's statistics are staged; this tile's are no longer read
+        }
+        mbar_wait(dkv_full, 0);
+        tc_fence_after();
+        if (warp_valid) {
+            const int subq = qcol & 63;      // both accumulators span the 64 columns of the Q / dO boxes
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {        // 0: dK (x scale) -> k section, 1: dV -> v section
+                uint32_t o[HD / 16][16];
+#pragma unroll
+                for (int c = 0; c < HD / 16; ++c) tmem_ld_32x16(t_lane + 128 + which * 64 + subq + c * 16, o[c]);
+                tmem_ld_wait();
+                if (grow < N) {
+                    const float f = which ? 1.0f : scale;
+                    __nv_bfloat16* orow = dqkv + (static_cast<size_t>(b) * N + grow) * (3 * D) + (which ? vcol : kcol);
+#pragma unroll
+                    for (int c = 0; c < HD / 16; ++c) {
+                        uint4 lo, hi;
+                        lo.x = pack_bf16(__uint_as_float(o[c][0]) * f, __uint_as_float(o[c][1]) * f);
+                        lo.y = pack_bf16(__uint_as_float(o[c][2]) * f, __uint_as_float(o[c][3]) * f);
+                        lo.z = pack_bf16(__uint_as_float(o[c][4]) * f, __uint_as_float(o[c][5]) * f);
+                        lo.w = pack_bf16(__uint_as_float(o[c][6]) * f, __uint_as_float(o[c][7]) * f);
+                        hi.x = pack_bf16(__uint_as_float(o[c][8]) * f, __uint_as_float(o[c][9]) * f);
+                        hi.y = pack_bf16(__uint_as_float(o[c][10]) * f, __uint_as_float(o[c][11]) * f);
+                        hi.z = pack_bf16(__uint_as_float(o[c][12]) * f, __uint_as_float(o[c][13]) * f);
+                        hi.w = pack_bf16(__uint_as_float(o[c][14]) * f, __uint_as_float(o[c][15]) * f);
+                        *reinterpret_cast<uint4*>(orow + c * 16) = lo;
+                        *reinterpret_cast<uint4*>(orow + c * 16 + 8) = hi;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
+template <typename Kern>
+static int set_smem(Kern kern, uint32_t bytes, bool& done) {
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+        if (e != cudaSuccess) return set_error(-3, "attention: cudaFuncSetAttribute(smem=%u): %s", bytes, cudaGetErrorString(e));
+        done = true;
+    }
+    return 0;
+}
+
+template <int HD>
+static int launch_fwd(const CUtensorMap& tq, void* out, float* lse, int B, int N, int H, float sl2, cudaStream_t st) {
+    static bool attr = false;
+    if (int rc = set_smem(attn_fwd_tc_kernel<HD>, FwdSmem::TOTAL, attr)) return rc;
+    launch_kernel(attn_fwd_tc_kernel<HD>, dim3(ceil_div(N, QT), H, B), dim3(AT_THREADS), FwdSmem::TOTAL, st, tq,
+                  static_cast<__nv_bfloat16*>(out), lse, N, H, sl2);
+    VITAE_CHECK_LAUNCH("attention_fwd");
+    return 0;
+}
+
+template <int HD>
+static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const void* out, const void* dout, const float* lse,
+                      float* delta, void* dqkv, int B, int N, int H, float scale, float sl2, cudaStream_t st) {
+    static bool attr_dq = false, attr_dkv = false;
+    if (int rc = set_smem(attn_bwd_dq_tc_kernel<HD>, DqSmem::TOTAL, attr_dq)) return rc;
+    if (int rc = set_smem(attn_bwd_dkv_tc_kernel<HD>, DkvSmem::TOTAL, attr_dkv)) return rc;
+    const dim3 grid(ceil_div(N, QT), H, B);
+    launch_kernel(attn_bwd_dq_tc_kernel<HD>, grid, dim3(AT_THREADS), DqSmem::TOTAL, st, tq, tdo,
+                  static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), lse, delta,
+                  static_cast<__nv_bfloat16*>(dqkv), N, H, scale, sl2);
+    VITAE_CHECK_LAUNCH("attention_bwd_dq");
+    launch_kernel(attn_bwd_dkv_tc_kernel<HD>, grid, dim3(AT_THREADS), DkvSmem::TOTAL, st, tq, tdo, lse,
+                  static_cast<const float*>(delta), static_cast<__nv_bfloat16*>(dqkv), N, H, scale, sl2);
+    VITAE_CHECK_LAUNCH("attention_bwd_dkv");
+    return 0;
+}
+
+}  // namespace vitae
+
+using namespace vitae;
+
+// the round-1 mma.sync kernels (attention.cu), kept for A/B timing: VITAE_ATTN_LEGACY=1
+namespace vitae {
+int attention_fwd_legacy(const void* qkv, void* out, float* lse, int B, int N, int H, int hd, float scale, void* stream);
+int attention_bwd_legacy(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv, int B,
+                         int N, int H, int hd, float scale, void* stream);
+}  // namespace vitae
+
+static bool use_legacy() {
+    static const bool on = [] { const char* e = getenv("VITAE_ATTN_LEGACY"); return e && e[0] == '1'; }();
+    return on;
+}
+
+extern "C" int vitae_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int hd, float scale, void* stream) {
+    if (use_legacy()) return attention_fwd_legacy(qkv, out, lse, B, N, H, hd, scale, stream);
+    VITAE_REQUIRE(qkv && out && lse, "attention_fwd: null pointer");
+    VITAE_REQUIRE(B > 0 && N > 0 && H > 0 && (hd == 16 || hd == 32 || hd == 64), "attention_fwd: unsupported shape B=%d N=%d H=%d hd=%d", B, N, H, hd);
+    VITAE_REQUIRE((H * hd) % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                  "attention_fwd: qkv / out must be 16-byte aligned and H*hd a multiple of 8");
+    const int D = H * hd;
+    CUtensorMap tq;
+    if (int rc = make_tmap(&tq, qkv, 2, 3ull * D, (uint64_t)N, (uint64_t)B, 3ull * D, 64, 64)) return rc;
+    const float sl2 = scale * LOG2E_F;
+    cudaStream_t st = as_stream(stream);
+    if (hd == 64) return launch_fwd<64>(tq, out, lse, B, N, H, sl2, st);
+    if (hd == 32) return launch_fwd<32>(tq, out, lse, B, N, H, sl2, st);
+    return launch_fwd<16>(tq, out, lse, B, N, H, sl2, st);
+}
+
+extern "C" int vitae_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
+                                   void* dqkv, int B, int N, int H, int hd, float scale, void* stream) {
+    if (use_legacy()) return attention_bwd_legacy(qkv, out, dout, lse, delta, dqkv, B, N, H, hd, scale, stream);
+    VITAE_REQUIRE(qkv && out && dout && lse && delta && dqkv, "attention_bwd: null pointer");
+    VITAE_REQUIRE(B > 0 && N > 0 && H > 0 && (hd == 16 || hd == 32 || hd == 64), "attention_bwd: unsupported shape B=%d N=%d H=%d hd=%d", B, N, H, hd);
+    VITAE_REQUIRE((H * hd) % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(dout) & 15) == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0,
+                  "attention_bwd: tensors must be 16-byte aligned and H*hd a multiple of 8");
+    const int D = H * hd;
+    CUtensorMap tq, tdo;
+    if (int rc = make_tmap(&tq, qkv, 2, 3ull * D, (uint64_t)N, (uint64_t)B, 3ull * D, 64, 64)) return rc;
+    if (int rc = make_tmap(&tdo, dout, 2, (uint64_t)D, (uint64_t)N, (uint64_t)B, (uint64_t)D, 64, 64)) return rc;
+    const float sl2 = scale * LOG2E_F;
+    cudaStream_t st = as_stream(stream);
+    if (hd == 64) return launch_bwd<64>(tq, tdo, out, dout, lse, delta, dqkv, B, N, H, scale, sl2, st);
+    if (hd == 32) return launch_bwd<32>(tq, tdo, out, dout, lse, delta, dqkv, B, N, H, scale, sl2, st);
+    return launch_bwd<16>(tq, tdo, out, dout, lse, delta, dqkv, B, N, H, scale, sl2, st);
+}

@@ -1,6 +1,8 @@
 // Shared host-side helpers for libvitae_b200.so: error reporting, launch checks.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdint.h>
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -55,5 +57,9 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
+
+// Tensor map over a row-major matrix, or (d2 > 0) a stack of d2 matrices of d1 rows (gemm_tcgen05.cu); cached per key.
+int make_tmap(CUtensorMap* out, const void* ptr, uint32_t esize, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld,
+              uint32_t b0, uint32_t b1);
 
 }  // namespace vitae

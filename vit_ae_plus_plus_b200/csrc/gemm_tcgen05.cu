@@ -489,8 +489,8 @@ struct TmapKeyHash {
 // Tensor map over a row-major matrix, or (d2 > 0) a stack of d2 matrices of d1 rows (pitch ld elements, matrix pitch
 // d1*ld): inner dim d0 (contiguous), box b0 x b1 (x 1), 128B swizzle, element size 2 (bf16) or 4 (fp32).
 // Out-of-bounds elements read as zero and are clipped on stores, so ragged M / N / K need no special casing.
-static int make_tmap(CUtensorMap* out, const void* ptr, uint32_t esize, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld,
-                     uint32_t b0, uint32_t b1) {
+int make_tmap(CUtensorMap* out, const void* ptr, uint32_t esize, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld,
+              uint32_t b0, uint32_t b1) {
     static std::mutex mu;
     static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
     const TmapKey key{ptr, d0, d1, d2, ld, b0, b1, esize};

@@ -572,6 +572,54 @@ extern "C" int vitae_adamw_step(float* param, const float* grad, float* exp_avg,
 
 constexpr int OPT_NORM_BLOCKS = 148 * 4;
 
+// fp32 <-> bf16 copies of a flat gradient slice (the data-parallel gradient exchange moves bf16, dp.py)
+template <bool TO_BF16>
+__global__ void __launch_bounds__(256) cast_flat_kernel(const void* __restrict__ src, void* __restrict__ dst, long long n) {
+    pdl_trigger();
+    pdl_wait();
+    const long long n4 = n >> 2;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += gridDim.x * 256ll) {
+        if (TO_BF16) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + i);
+            uint2 pk;
+            pk.x = pack_bf16(v.x, v.y);
+            pk.y = pack_bf16(v.z, v.w);
+            reinterpret_cast<uint2*>(dst)[i] = pk;
+        } else {
+            const uint2 pk = __ldcs(reinterpret_cast<const uint2*>(src) + i);
+            float4 v;
+            v.x = __uint_as_float(pk.x << 16); v.y = __uint_as_float(pk.x & 0xffff0000u);
+            v.z = __uint_as_float(pk.y << 16); v.w = __uint_as_float(pk.y & 0xffff0000u);
+            reinterpret_cast<float4*>(dst)[i] = v;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (long long k = n4 << 2; k < n; ++k) {
+            if (TO_BF16) static_cast<__nv_bfloat16*>(dst)[k] = __float2bfloat16(static_cast<const float*>(src)[k]);
+            else static_cast<float*>(dst)[k] = __bfloat162float(static_cast<const __nv_bfloat16*>(src)[k]);
+        }
+}
+
+extern "C" int vitae_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, int max_blocks, void* stream) {
+    VITAE_REQUIRE(src && dst_bf16 && n > 0, "cast_f32_to_bf16: bad arguments");
+    VITAE_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst_bf16) & 7) == 0, "cast_f32_to_bf16: alignment");
+    const int cap = max_blocks > 0 ? max_blocks : 148 * 4;
+    const int blocks = static_cast<int>(std::min<long long>(ceil_div<long long>(n, 1024), cap));
+    launch_kernel(cast_flat_kernel<true>, dim3(blocks), dim3(256), 0, as_stream(stream), static_cast<const void*>(src), dst_bf16, n);
+    VITAE_CHECK_LAUNCH("cast_f32_to_bf16");
+    return 0;
+}
+
+extern "C" int vitae_cast_bf16_to_f32(const void* src_bf16, float* dst, long long n, int max_blocks, void* stream) {
+    VITAE_REQUIRE(src_bf16 && dst && n > 0, "cast_bf16_to_f32: bad arguments");
+    VITAE_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(src_bf16) & 7) == 0, "cast_bf16_to_f32: alignment");
+    const int cap = max_blocks > 0 ? max_blocks : 148 * 4;
+    const int blocks = static_cast<int>(std::min<long long>(ceil_div<long long>(n, 1024), cap));
+    launch_kernel(cast_flat_kernel<false>, dim3(blocks), dim3(256), 0, as_stream(stream), src_bf16, static_cast<void*>(dst), n);
+    VITAE_CHECK_LAUNCH("cast_bf16_to_f32");
+    return 0;
+}
+
 extern "C" size_t vitae_optim_workspace_bytes(void) { return 2 * OPT_NORM_BLOCKS * sizeof(float); }
 
 extern "C" int vitae_optim_prepare(const float* grad, long long n, const float* grad2, long long n2, float* ctl,

@@ -418,6 +418,8 @@ class MAEEngine:
         self._waited = set()               # groups the pass being enqueued has already waited for
         self.grad_buckets = None
         self.bucket_elems = 32 << 20       # 128 MB of fp32 gradients per all-reduce bucket
+        self.g16: Optional[torch.Tensor] = None            # bf16 staging of the gradient exchange (allocated for N > 1)
+        self.comm_stream: Optional[torch.cuda.Stream] = None
 
     # ------------------------------------------------------------------------------------------------ helpers
     def _make_param_groups(self):
@@ -747,7 +749,7 @@ class MAEEngine:
         staged = sync_grads and dp.world_size() > 1
         stages = self._backward_stages(pl, dpred_extra, accumulate, split=staged, with_dlatent=dlatent is not None,
                                        encoder_only=encoder_only, with_edge=dedge is not None)
-        reducer = dp.GradReducer() if staged else None
+        reducer = self._grad_reducer() if staged else None
         for i, (fn, (a, b)) in enumerate(stages):
             if dpred_extra is not None and i == 0:   # auxiliary torch-side terms that consume ``pred``: not graphed
                 fn()
@@ -981,6 +983,16 @@ class MAEEngine:
         return cur
 
     # ------------------------------------------------------------------------------------------------ data parallel
+    def _grad_reducer(self) -> "dp.GradReducer":
+        """Reducer of the staged backward: bf16 exchange through a staging buffer on a communication stream of its own
+        (dp.exchange_dtype), else plain fp32 all-reduces on the process group's stream."""
+        if dp.exchange_dtype() != "bf16":
+            return dp.GradReducer()
+        if self.g16 is None:
+            self.g16 = torch.empty(self.flat.total, dtype=_BF16, device=self.device)
+            self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        return dp.GradReducer(self.flat.g32, self.g16, self.comm_stream)
+
     def broadcast_parameters(self) -> None:
         """One broadcast of the flat parameter buffer (+ the frozen position tables) from rank 0 (dp.py)."""
         dp.broadcast_flat(self.flat.p32)

@@ -470,3 +470,40 @@ def adamw_flat(param, grad, exp_avg, exp_avg_sq, param_bf16, n: int, group_of_ch
                                exp_avg_sq.data_ptr() + 4 * start, p16, n, group_of_chunk.data_ptr() + start // 64,
                                ctypes.cast(host, ctypes.c_void_p), ng, ctl.data_ptr(), max_blocks, _stream()),
           "vitae_adamw_flat")
+
+
+def cast_f32_to_bf16(src, dst, max_blocks: int = 0) -> None:
+    _req(src, _F32, "cast src"); _req(dst, _BF16, "cast dst")
+    check(_lib.load().vitae_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), max_blocks, _stream()),
+          "vitae_cast_f32_to_bf16")
+
+
+def cast_bf16_to_f32(src, dst, max_blocks: int = 0) -> None:
+    _req(src, _BF16, "cast src"); _req(dst, _F32, "cast dst")
+    check(_lib.load().vitae_cast_bf16_to_f32(src.data_ptr(), dst.data_ptr(), src.numel(), max_blocks, _stream()),
+          "vitae_cast_bf16_to_f32")
+
+
+RAW_TYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2, torch.uint16: 3, torch.int16: 4, torch.uint8: 5}
+INGEST_MODES = {"z_score_channel": 0, "z_score_sample": 1, "min_max": 2}
+
+
+def ingest_workspace_bytes(B: int, C: int) -> int:
+    return _lib.load().vitae_ingest_workspace_bytes(B, C)
+
+
+def ingest_normalize(raw, out, mode: str, workspace, stats=None) -> None:
+    """raw [B, C, ...] in its storage dtype (RAW_TYPES) -> out fp32, normalised per ``mode`` (INGEST_MODES; the reference's
+    Dataset._normalize_data, dataset/egd_dataset/egd.py:44-50 / dataset/brats_dataset/brats.py:26-32)."""
+    if raw.dtype not in RAW_TYPES:
+        raise _lib.VitaeError(f"ingest_normalize: unsupported raw dtype {raw.dtype}")
+    if mode not in INGEST_MODES:
+        raise _lib.VitaeError(f"ingest_normalize: mode {mode!r} not in {sorted(INGEST_MODES)}")
+    if not (raw.is_cuda and raw.is_contiguous()):
+        raise _lib.VitaeError("ingest_normalize: raw volume must be a contiguous CUDA tensor")
+    _req(out, _F32, "ingest out")
+    B, C = raw.shape[0], raw.shape[1]
+    vox = raw[0, 0].numel()
+    check(_lib.load().vitae_ingest_normalize(raw.data_ptr(), RAW_TYPES[raw.dtype], out.data_ptr(), B, C, vox,
+                                             INGEST_MODES[mode], workspace.data_ptr(), _ptr(stats), _stream()),
+          "vitae_ingest_normalize")

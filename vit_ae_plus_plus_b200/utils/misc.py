@@ -197,23 +197,45 @@ class MetricLogger:
         print(f"{header} Total time: {datetime.timedelta(seconds=int(total))} ({total / max(n, 1):.4f} s / it)")
 
 
+def normalize_volumes(raw: torch.Tensor, mode: str = "z_score_channel", out: torch.Tensor = None) -> torch.Tensor:
+    """The reference's ``Dataset._normalize_data`` on the device: ``raw`` [B, C, V, V, V] CUDA tensor in its
+    storage dtype (uint16 / int16 / uint8 / float16 / bfloat16 / float32) -> fp32 of the same shape.  ``mode``:
+    "z_score_channel" (dataset/egd_dataset/egd.py:45-47: per channel, unbiased variance), "z_score_sample"
+    (dataset/brats_dataset/brats.py:27-29: over the whole sample), "min_max" (:30-32 / egd.py:48-50: to [-1, 1])."""
+    from .. import ops
+    raw = raw.contiguous()
+    if out is None:
+        out = torch.empty(raw.shape, dtype=torch.float32, device=raw.device)
+    ws = torch.empty(ops.ingest_workspace_bytes(raw.shape[0], raw.shape[1]), dtype=torch.uint8, device=raw.device)
+    ops.ingest_normalize(raw, out, mode, ws)
+    return out
+
+
 class DevicePrefetcher:
     """Wraps a batch iterable (the k-fold scripts' DataLoader, k_fold_cross_valid_combined_brats.py:131-148): batch k+1 is
     copied host -> device on a dedicated copy stream while step k computes, into ``depth`` rotating device buffers per
     tensor slot (stable addresses: the step's CUDA graphs read the volume in place).  The reference loop's
     ``sample.to(device, non_blocking=True)`` (utils/train_one_epoch.py:47-48) then finds the tensors already resident.
     A 4 x 4 x 128^3 fp32 batch is 134 MB = ~2.6 ms of PCIe time per step, more than half a B200 training step; host
-    tensors should be pinned (DataLoader(pin_memory=True), the scripts' default) or the copy cannot overlap."""
+    tensors should be pinned (DataLoader(pin_memory=True), the scripts' default) or the copy cannot overlap.
 
-    def __init__(self, loader, device, depth: int = 2):
+    ``normalize`` (None | "z_score_channel" | "z_score_sample" | "min_max"): the loader yields RAW volumes in their storage
+    dtype (uint16 / float16 ...: half the PCIe bytes of fp32, or fewer) and every 5-D tensor of a batch is normalised on the
+    device right after its copy, on the copy stream (``normalize_volumes``: the reference does this on the host inside
+    ``Dataset.__getitem__``); the consumer sees fp32 volumes as before."""
+
+    def __init__(self, loader, device, depth: int = 2, normalize: str = None):
         self.loader, self.device, self.depth = loader, torch.device(device), max(2, int(depth))
         self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         self.bufs = [dict() for _ in range(self.depth)]
+        self.normalize = normalize
+        self.h2d_bytes = 0          # bytes copied host -> device so far (bench.py reports them)
 
     def __len__(self):
         return len(self.loader)
 
     def _issue(self, slot: int, batch, free_event):
+        from .. import ops
         items = list(batch) if isinstance(batch, (tuple, list)) else [batch]
         with torch.cuda.stream(self.stream):
             if free_event is not None:
@@ -227,6 +249,16 @@ class DevicePrefetcher:
                 if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
                     buf = self.bufs[slot][j] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
                 buf.copy_(t, non_blocking=True)
+                self.h2d_bytes += t.numel() * t.element_size()
+                if self.normalize is not None and t.dim() == 5:
+                    key = ("norm", j)
+                    nb = self.bufs[slot].get(key)
+                    if nb is None or nb[0].shape != t.shape:
+                        nb = self.bufs[slot][key] = (
+                            torch.empty(t.shape, dtype=torch.float32, device=self.device),
+                            torch.empty(ops.ingest_workspace_bytes(t.shape[0], t.shape[1]), dtype=torch.uint8, device=self.device))
+                    ops.ingest_normalize(buf, nb[0], self.normalize, nb[1])
+                    buf = nb[0]
                 out.append(buf)
             ready = torch.cuda.Event()
             ready.record(self.stream)

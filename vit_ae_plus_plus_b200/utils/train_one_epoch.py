@@ -96,7 +96,10 @@ def train_one_stage_epoch(model: torch.nn.Module, data_loader: Iterable, optimiz
     optimizer.zero_grad()
     if log_writer is not None:
         print("log_dir: {}".format(log_writer.log_dir))
-    batches = misc.DevicePrefetcher(data_loader, device) if torch.device(device).type == "cuda" else data_loader
+    # args.device_normalize (optional, not in the reference's argument set): the loader yields raw volumes in their storage
+    # dtype and the normalisation of Dataset._normalize_data runs on the device (misc.DevicePrefetcher)
+    batches = (misc.DevicePrefetcher(data_loader, device, normalize=getattr(args, "device_normalize", None))
+               if torch.device(device).type == "cuda" else data_loader)
     for step, (sample, original_volume, _) in enumerate(
             metric_logger.log_every(batches, PRINT_FREQ, header, before_print=deferred.flush)):
         if step % accum_iter == 0:

@@ -287,6 +287,28 @@ size_t vitae_ingest_workspace_bytes(int B, int C);
 int vitae_ingest_normalize(const void* raw, int raw_type, float* out, int B, int C, long long voxels, int mode,
                            void* workspace, float* stats, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Contrastive head: predictor = Linear(no bias) -> BatchNorm1d -> ReLU -> Linear
+ * (model/vit_autoenc.py:263-268) and the loop's cosine loss (utils/train_one_epoch.py:32,113-114).  The Linear layers
+ * are vitae_gemm_bf16 calls.
+ * vitae_bn_relu_fwd: h fp32 [M, D] (output of the first Linear) -> act bf16 = relu(batchnorm(h)) with the batch
+ *   statistics of the M rows (training mode, biased variance, eps); mean / rstd fp32 [D] are kept for the backward;
+ *   running_mean / running_var (both or neither) are updated with `momentum` and the unbiased variance, like torch.
+ * vitae_bn_relu_bwd: dact bf16 (gradient w.r.t. act) -> dh bf16 (gradient w.r.t. h); dgamma / dbeta fp32 [D] (+)=.
+ * vitae_cosine_loss_fwd: loss[0] = -weight * (mean_i cos(p1_i, z2_i) + mean_i cos(p2_i, z1_i)) / 2 over fp32 [M, D]
+ *   rows, cos with torch.nn.CosineSimilarity's eps = 1e-8; workspace: vitae_cosine_loss_workspace_floats(M) floats,
+ *   kept for the backward.  vitae_cosine_loss_bwd: dp1 / dp2 fp32 [M, D] = upstream[0] * d loss / d p (z detached). */
+int vitae_bn_relu_fwd(const float* h, const float* gamma, const float* beta, float eps, void* act_bf16, float* mean,
+                      float* rstd, float* running_mean, float* running_var, float momentum, int M, int D, void* stream);
+int vitae_bn_relu_bwd(const void* dact_bf16, const float* h, const float* gamma, const float* beta, const float* mean,
+                      const float* rstd, void* dh_bf16, float* dgamma, float* dbeta, int accumulate, int M, int D,
+                      void* stream);
+size_t vitae_cosine_loss_workspace_floats(int M);
+int vitae_cosine_loss_fwd(const float* p1, const float* z2, const float* p2, const float* z1, int M, int D, float weight,
+                          float* workspace, float* loss, void* stream);
+int vitae_cosine_loss_bwd(const float* p1, const float* z2, const float* p2, const float* z1, int M, int D, float weight,
+                          const float* workspace, const float* upstream, float* dp1, float* dp2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

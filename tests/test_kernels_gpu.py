@@ -368,3 +368,54 @@ def test_flat_casts_roundtrip():
     y = torch.empty_like(x)
     ops.cast_bf16_to_f32(h, y)
     assert torch.equal(y, h.float())
+
+
+# ------------------------------------------------------------------------------------------------ contrastive head (row f-2)
+@pytest.mark.parametrize("M,D", [(14, 128), (516, 768), (70, 96)])
+def test_bn_relu_fwd_bwd_match_torch(M, D):
+    """BatchNorm1d (training mode) + ReLU of the predictor (model/vit_autoenc.py:264-266) against torch fp32, including the
+    running statistics."""
+    from vit_ae_plus_plus_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(M + D)
+    h = torch.randn(M, D, generator=g, device=DEV) * 1.7 + 0.3
+    gamma = 1 + 0.1 * torch.randn(D, generator=g, device=DEV)
+    beta = 0.1 * torch.randn(D, generator=g, device=DEV)
+    bn = torch.nn.BatchNorm1d(D).to(DEV).train()
+    with torch.no_grad():
+        bn.weight.copy_(gamma); bn.bias.copy_(beta)
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    hr = h.clone().requires_grad_(True)
+    y = torch.relu(bn(hr))
+    act = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    mean, rstd = torch.empty(D, device=DEV), torch.empty(D, device=DEV)
+    ops.bn_relu_fwd(h, gamma, beta, bn.eps, act, mean, rstd, rm, rv, bn.momentum)
+    assert _rel(act.float(), y.detach()) < 1e-2
+    assert _rel(rm, bn.running_mean) < 1e-5 and _rel(rv, bn.running_var) < 1e-5
+    dact = torch.randn(M, D, generator=g, device=DEV).bfloat16()
+    y.backward(dact.float())
+    dh = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    dg, db = torch.full((D,), 5.0, device=DEV), torch.full((D,), -3.0, device=DEV)
+    ops.bn_relu_bwd(dact, h, gamma, beta, mean, rstd, dh, dg, db, accumulate=True)
+    assert _rel(dh.float(), hr.grad) < 1e-2
+    assert _rel(dg - 5.0, bn.weight.grad) < 1e-4 and _rel(db + 3.0, bn.bias.grad) < 1e-4
+
+
+@pytest.mark.parametrize("M,D", [(14, 128), (516, 768)])
+def test_cosine_pair_loss_matches_torch(M, D):
+    """utils/train_one_epoch.py:113-114 with nn.CosineSimilarity(dim=1) (:32), forward and gradient w.r.t. p1 / p2."""
+    import argparse
+    from vit_ae_plus_plus_b200.utils.train_one_epoch import compute_contrastive_loss
+    g = torch.Generator(device=DEV).manual_seed(M)
+    p1, p2, z1, z2 = (torch.randn(M, D, generator=g, device=DEV) for _ in range(4))
+    p1[0] = 0.0                                                     # a zero row: the eps clamp
+    crit = torch.nn.CosineSimilarity(dim=1)
+    args = argparse.Namespace(contr_weight=0.37)
+    a1, a2 = p1.clone().requires_grad_(True), p2.clone().requires_grad_(True)
+    ref = args.contr_weight * (-(crit(a1, z2).mean() + crit(a2, z1).mean()) * 0.5)
+    (ref * 3.0).backward()
+    b1, b2 = p1.clone().requires_grad_(True), p2.clone().requires_grad_(True)
+    got = compute_contrastive_loss(args, crit, b1, b2, z1, z2)
+    (got * 3.0).backward()
+    assert abs(got.item() - ref.item()) < 1e-6 + 1e-5 * abs(ref.item())
+    assert _rel(b1.grad[1:], a1.grad[1:]) < 1e-5 and _rel(b2.grad, a2.grad) < 1e-5
+    assert torch.isfinite(b1.grad).all()

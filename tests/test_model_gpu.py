@@ -314,8 +314,8 @@ def test_latent_gradient_paths_match_oracle(graphs):
     for rep in range(3 if graphs else 1):
         m.zero_grad(set_to_none=True)
         eng.use_graphs = graphs
-        recon, _edge, pred, mask, lat1, lat2 = VA._ContrastiveStep.apply(m.cls_token, m, x1.cuda(), x2.cuda(), n1.cuda(),
-                                                                         n2.cuda(), keep, False)
+        recon, _edge, pred, mask, lat1, lat2, _p1, _p2 = VA._ContrastiveStep.apply(m.cls_token, m, x1.cuda(), x2.cuda(),
+                                                                                   n1.cuda(), n2.cuda(), keep, False)
         (recon + (lat1 * G1.cuda()).sum() + (lat2 * G2.cuda()).sum()).backward()
         torch.cuda.synchronize()
         assert relmax(lat1, lat1o.reshape(G1.shape)) < TOL and relmax(lat2, lat2o.reshape(G2.shape)) < TOL
@@ -326,9 +326,8 @@ def test_latent_gradient_paths_match_oracle(graphs):
 
 def test_contrastive_model_through_the_training_loop_api():
     """contr_mae_vit_base_patch16 via get_models + train_one_stage_epoch's call sequence on a down-sized volume (the 7-tuple
-    branch of the loop, utils/train_one_epoch.py:51-58).  The predictor's parameters live outside the engine's flat buffers:
-    the fused optimizer adopts them into a second flat buffer, and the result matches the reference's unfused
-    GradScaler + torch AdamW sequence."""
+    branch of the loop, utils/train_one_epoch.py:51-58).  The predictor runs on the kernels and its parameters live in the
+    engine's flat buffers; the fused optimizer's result matches the reference's unfused GradScaler + torch AdamW sequence."""
     from vit_ae_plus_plus_b200.model import model_factory
     from vit_ae_plus_plus_b200.utils import misc, train_one_epoch as T
     args = argparse.Namespace(model="contr_mae_vit_base_patch16", volume_size=32, in_channels=1, patch_size=16,
@@ -354,7 +353,9 @@ def test_contrastive_model_through_the_training_loop_api():
         results[fused] = (stats, {k: v.detach().clone() for k, v in model.state_dict().items()})
         if fused:
             fo = model.engine().fused_optimizer()
-            assert fo.ex_total > 0 and model.predictor[0].weight.data_ptr() in fo.ex_ptrs
+            # the predictor's parameters live in the engine's flat buffers like all others: no second ("extras") buffer
+            flat = model.engine().flat
+            assert fo.ex_total == 0 and model.predictor[0].weight.data_ptr() == flat.v32["predictor.0.weight"].data_ptr()
             st = opt.state[model.predictor[3].bias]
             assert st["exp_avg"].abs().sum().item() > 0          # optimizer state stays visible in torch's layout
     (sf, pf), (su, pu) = results[True], results[False]

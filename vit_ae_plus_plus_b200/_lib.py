@@ -95,6 +95,13 @@ SIGNATURES = {
                                  c_void_p, c_int, c_void_p]),
     "vitae_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "vitae_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
+    "vitae_bn_relu_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                  c_int, c_int, c_void_p]),
+    "vitae_bn_relu_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_void_p]),
+    "vitae_cosine_loss_workspace_floats": (c_size_t, [c_int]),
+    "vitae_cosine_loss_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "vitae_cosine_loss_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
     "vitae_ingest_workspace_bytes": (c_size_t, [c_int, c_int]),
     "vitae_ingest_normalize": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p, c_void_p,
                                        c_void_p]),

@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libvitae_b200.so")
 BUILD_DIR = os.path.join(PKG_DIR, "csrc", "build")
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "layernorm.cu", "token_ops.cu", "loss.cu", "edge_loss.cu", "ingest.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "layernorm.cu", "token_ops.cu", "loss.cu", "edge_loss.cu", "ingest.cu", "predictor.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-warn-spills"]
 
@@ -71,6 +71,8 @@ def build(force: bool = False, verbose: bool = True) -> str:
         flags.append("-DVITAE_PDL_EARLY")
     if os.environ.get("VITAE_ATTN_TAIL") == "1":   # experiment: attention loops bounded by the valid part of ragged tail tiles
         flags.append("-DVITAE_ATTN_TAIL")
+    if os.environ.get("VITAE_ATTN_TRACE") == "1":  # debug build: per-phase stamps in the attention forward (tools/attn_trace.py)
+        flags.append("-DVITAE_ATTN_TRACE")
     variant = os.environ.get("VITAE_BUILD_VARIANT")     # experiment builds go to libvitae_b200_<variant>.so (VITAE_LIB selects)
     if variant:
         return _build_variant(flags, variant, verbose)

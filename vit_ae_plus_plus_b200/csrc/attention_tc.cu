@@ -36,6 +36,40 @@ constexpr int KT = 64;                  // columns per score tile
 constexpr uint32_t BOX_BYTES = 64 * 128;   // one 64-row x 64-column bf16 box
 constexpr uint32_t ROWT_BYTES = 2 * BOX_BYTES;   // a 128-row operand tile = two boxes
 
+// Phase tracing (debug build: VITAE_ATTN_TRACE=1): per CTA, %globaltimer stamps and accumulated barrier-wait cycles go to a
+// device buffer registered with vitae_debug_set_attn_trace (tools/attn_trace.py).  Compiled out by default.
+#ifdef VITAE_ATTN_TRACE
+__device__ unsigned long long* g_attn_trace = nullptr;
+#define AT_CTA() ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x)
+#define AT_STAMP(slot)                                                                        \
+    do {                                                                                      \
+        if (g_attn_trace) {                                                                   \
+            unsigned long long t__;                                                           \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                           \
+            g_attn_trace[AT_CTA() * 16 + (slot)] = t__;                                       \
+        }                                                                                     \
+    } while (0)
+#define AT_PUT(slot, v) do { if (g_attn_trace) g_attn_trace[AT_CTA() * 16 + (slot)] = (v); } while (0)
+#define AT_WAIT(acc, bar, par) do { const long long c0__ = clock64(); mbar_wait(bar, par); (acc) += clock64() - c0__; } while (0)
+// event log of CTA 0: who = 0 MMA thread, 1 one softmax thread, 2 TMA thread; 256 (id, clock) pairs each, behind the per-CTA slots
+#define AT_EV(who, id)                                                                                    \
+    do {                                                                                                  \
+        if (g_attn_trace && AT_CTA() == 0 && ev_n__ < 256) {                                              \
+            unsigned long long* e__ = g_attn_trace + (1 << 18) + ((who) * 256 + ev_n__) * 2;             \
+            e__[0] = (id);                                                                                \
+            e__[1] = clock64();                                                                           \
+            ++ev_n__;                                                                                     \
+        }                                                                                                 \
+    } while (0)
+#define AT_EV_DECL int ev_n__ = 0
+#else
+#define AT_EV(who, id) do { } while (0)
+#define AT_EV_DECL do { } while (0)
+#define AT_STAMP(slot) do { } while (0)
+#define AT_PUT(slot, v) do { } while (0)
+#define AT_WAIT(acc, bar, par) do { (void)(acc); mbar_wait(bar, par); } while (0)
+#endif
+
 __device__ __forceinline__ uint32_t at_swz(int r, int j) { return static_cast<uint32_t>(r * 128 + ((j ^ (r & 7)) << 4)); }
 __device__ __forceinline__ void at_sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
@@ -50,24 +84,31 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kk) {
 }
 
 // ------------------------------------------------------------------------------------------------------ forward
+// CFG 0: two CTAs per SM (256 TMEM columns each: two score tiles + O; two P buffers; 6 kv slots; 97 KB).
+// CFG 1: three CTAs per SM (128 TMEM columns: one score tile + O; one P buffer; 4 kv slots; 65 KB) -- every buffer single,
+//        the latency of one CTA's MMA / barrier round trips is covered by the other two; 444 CTA slots hold the 320 CTAs of
+//        the decoder shape (64 heads x 5 query tiles, one of them a single-row tail) in ONE wave, 296 do not.
+template <int CFG>
 struct FwdSmem {
-    static constexpr int NSLOT = 6;     // ring of kv boxes
-    static constexpr int NS = 2;        // score tiles in TMEM
+    static constexpr int NSLOT = CFG == 0 ? 6 : 4;     // ring of kv boxes
+    static constexpr int NS = CFG == 0 ? 2 : 1;        // score tiles in TMEM
+    static constexpr int NP = CFG == 0 ? 2 : 1;        // P tiles in shared memory
     static constexpr uint32_t Q = 0;
     static constexpr uint32_t KV = Q + ROWT_BYTES;
     static constexpr uint32_t P = KV + NSLOT * BOX_BYTES;
-    static constexpr uint32_t BAR = P + 2 * ROWT_BYTES;
-    // barriers: q_full, kv_full[NSLOT], kv_empty[NSLOT], s_full[NS], s_free[NS], p_full[2], p_free[2], o_full
-    static constexpr int NBAR = 1 + 2 * NSLOT + 2 * NS + 4 + 1;
+    static constexpr uint32_t BAR = P + NP * ROWT_BYTES;
+    // barriers: q_full, kv_full[NSLOT], kv_empty[NSLOT], s_full[NS], s_free[NS], p_full[NP], p_free[NP], o_full
+    static constexpr int NBAR = 1 + 2 * NSLOT + 2 * NS + 2 * NP + 1;
     static constexpr uint32_t TOTAL = BAR + NBAR * 8 + 16 + 1024;
-    static constexpr uint32_t TMEM_COLS = 256;      // S tiles at 0 / 64, O at 128
+    static constexpr uint32_t O_COL = NS * KT;                          // O accumulator behind the score tiles
+    static constexpr uint32_t TMEM_COLS = CFG == 0 ? 256 : 128;
 };
 
-template <int HD>
-__global__ void __launch_bounds__(AT_THREADS)
+template <int HD, int CFG>
+__global__ void __launch_bounds__(AT_THREADS, CFG == 0 ? 2 : 3)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N,
                    int H, float scale_log2) {
-    using S = FwdSmem;
+    using S = FwdSmem<CFG>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -75,7 +116,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __r
     const uint32_t q_full = base + S::BAR;
     const uint32_t kv_full = q_full + 8, kv_empty = kv_full + S::NSLOT * 8;
     const uint32_t s_full = kv_empty + S::NSLOT * 8, s_free = s_full + S::NS * 8;
-    const uint32_t p_full = s_free + S::NS * 8, p_free = p_full + 16, o_full = p_free + 16;
+    const uint32_t p_full = s_free + S::NS * 8, p_free = p_full + S::NP * 8, o_full = p_free + S::NP * 8;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + S::BAR + S::NBAR * 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,12 +127,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __r
     const int n16_last = (nv_last + 15) & ~15;
     const int qcol = h * HD, kcol = D + h * HD, vcol = 2 * D + h * HD;
 
+    if (threadIdx.x == 0) AT_STAMP(0);
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tmQKV);
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
         for (int i = 0; i < S::NSLOT; ++i) { mbar_init(kv_full + i * 8, 1); mbar_init(kv_empty + i * 8, 1); }
         for (int i = 0; i < S::NS; ++i) { mbar_init(s_full + i * 8, 1); mbar_init(s_free + i * 8, 128); }
-        for (int i = 0; i < 2; ++i) { mbar_init(p_full + i * 8, 128); mbar_init(p_free + i * 8, 1); }
+        for (int i = 0; i < S::NP; ++i) { mbar_init(p_full + i * 8, 128); mbar_init(p_free + i * 8, 1); }
         mbar_init(o_full, 1);
         fence_barrier_init();
         fence_proxy_async();
@@ -106,6 +148,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __r
     const uint32_t tmem_base = *tmem_slot;
     PDL_TRIGGER_EARLY();
     pdl_wait();
+    if (threadIdx.x == 0) {
+        AT_STAMP(1);
+        unsigned smid__;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid__));
+        AT_PUT(9, smid__);
+    }
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
@@ -114,9 +162,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __r
             tma_load_3d(base + S::Q, &tmQKV, q_full, qcol & ~63, q0, b);
             tma_load_3d(base + S::Q + BOX_BYTES, &tmQKV, q_full, qcol & ~63, q0 + 64, b);
             uint32_t seq = 0;
+            AT_EV_DECL;
             auto load = [&](int col, int t) {
                 const uint32_t slot = seq % S::NSLOT;
                 mbar_wait(kv_empty + slot * 8, ((seq / S::NSLOT) & 1) ^ 1);
+                AT_EV(2, 100 + seq);
                 mbar_arrive_expect_tx(kv_full + slot * 8, BOX_BYTES);
                 tma_load_3d(base + S::KV + slot * BOX_BYTES, &tmQKV, kv_full + slot * 8, col & ~63, t * KT, b);
                 ++seq;
@@ -136,46 +186,58 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __r
             const uint32_t subq = (qcol & 63) * 2, subk = (kcol & 63) * 2;
             constexpr uint32_t idesc_pv = umma_idesc_bf16(QT, 64, 0u, 1u);
             uint32_t seq = 0;
+            long long w_kv = 0, w_sfree = 0, w_pfull = 0;
+            AT_EV_DECL;
             auto kv_wait = [&]() -> uint32_t {
                 const uint32_t slot = seq % S::NSLOT;
-                mbar_wait(kv_full + slot * 8, (seq / S::NSLOT) & 1);
+                AT_WAIT(w_kv, kv_full + slot * 8, (seq / S::NSLOT) & 1);
+                AT_EV(0, 100 + seq);          // kv tile seq landed
                 ++seq;
                 return slot;
             };
             auto issue_s = [&](int it, int t) {          // S tile number `it` (both passes counted) = Q K_t^T
                 const uint32_t slot = kv_wait();
                 const int sb = it % S::NS;
-                mbar_wait(s_free + sb * 8, ((it / S::NS) & 1) ^ 1);
+                AT_WAIT(w_sfree, s_free + sb * 8, ((it / S::NS) & 1) ^ 1);
+                AT_EV(0, 200 + it);           // score buffer free
                 tc_fence_after();
                 const uint32_t idesc = umma_idesc_bf16(QT, t == T - 1 ? n16_last : KT, 0u, 0u);
                 const uint32_t sk = base + S::KV + slot * BOX_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < HD / 16; ++kk)
                     umma_bf16(tmem_base + sb * KT, desc_kmajor(base + S::Q, subq, kk), desc_kmajor(sk, subk, kk), idesc, kk != 0);
+                AT_EV(0, 300 + it);           // S MMAs issued
                 umma_commit(kv_empty + slot * 8);
                 umma_commit(s_full + sb * 8);
+                AT_EV(0, 400 + it);           // commits issued
             };
             auto issue_pv = [&](int u) {                 // O += P_u V_u
                 const uint32_t slot = kv_wait();
-                const int pb = u & 1;
-                mbar_wait(p_full + pb * 8, (u >> 1) & 1);
+                const int pb = u % S::NP;
+                AT_WAIT(w_pfull, p_full + pb * 8, (u / S::NP) & 1);
+                AT_EV(0, 500 + u);            // P tile ready
                 tc_fence_after();
                 const int nk = (u == T - 1 ? n16_last : KT) / 16;
                 const uint32_t sv = base + S::KV + slot * BOX_BYTES, sp = base + S::P + pb * ROWT_BYTES;
 #pragma unroll 1
                 for (int kk = 0; kk < nk; ++kk)
-                    umma_bf16(tmem_base + 128, desc_kmajor(sp, 0, kk), desc_mnmajor(sv, kk), idesc_pv, (u | kk) != 0);
+                    umma_bf16(tmem_base + S::O_COL, desc_kmajor(sp, 0, kk), desc_mnmajor(sv, kk), idesc_pv, (u | kk) != 0);
                 umma_commit(kv_empty + slot * 8);
                 umma_commit(p_free + pb * 8);
+                AT_EV(0, 600 + u);            // P V issued + committed
             };
             mbar_wait(q_full, 0);
+            AT_STAMP(2);
             for (int t = 0; t < T; ++t) issue_s(t, t);
+            AT_STAMP(3);
             for (int t = 0; t < T; ++t) {
                 issue_s(T + t, t);
                 if (t >= 1) issue_pv(t - 1);
             }
             issue_pv(T - 1);
             umma_commit(o_full);
+            AT_STAMP(5);
+            AT_PUT(13, w_sfree); AT_PUT(14, w_pfull); AT_PUT(15, w_kv);
             PDL_TRIGGER_LATE();
         }
         __syncwarp();
@@ -187,9 +249,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __r
         const bool warp_valid = q0 + q * 32 < N;             // warps without a valid row only keep the barriers going
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         float mraw = -INFINITY;
+        long long w_s1 = 0, w_s2 = 0, w_pf = 0;
+        AT_EV_DECL;
         for (int t = 0; t < T; ++t) {                        // pass 1: row maxima of the raw scores
             const int sb = t % S::NS;
-            mbar_wait(s_full + sb * 8, (t / S::NS) & 1);
+            AT_WAIT(w_s1, s_full + sb * 8, (t / S::NS) & 1);
+            if (threadIdx.x == 64) AT_EV(1, 100 + t);        // scores of tile t visible
             tc_fence_after();
             if (warp_valid) {
                 const bool last = t == T - 1;
@@ -213,16 +278,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __r
                     }
                 }
             }
+            if (threadIdx.x == 64) AT_EV(1, 200 + t);        // maxima done
             tc_fence_before();
             mbar_arrive(s_free + sb * 8);
         }
+        if (threadIdx.x == 64) AT_STAMP(4);
         const float msc = mraw * scale_log2;
         float l = 0.f;
         for (int t = 0; t < T; ++t) {                        // pass 2: p = 2^(s * scale_log2 - msc), row sums, P -> smem
-            const int it = T + t, sb = it % S::NS, pb = t & 1;
+            const int it = T + t, sb = it % S::NS, pb = t % S::NP;
             const bool last = t == T - 1;
             const int nch = last ? n16_last / 16 : 4;
-            mbar_wait(s_full + sb * 8, (it / S::NS) & 1);
+            AT_WAIT(w_s2, s_full + sb * 8, (it / S::NS) & 1);
+            if (threadIdx.x == 64) AT_EV(1, 300 + t);        // pass 2: scores visible
             tc_fence_after();
             uint32_t v[4][16];
             if (warp_valid) {
@@ -231,11 +299,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __r
                     if (c < nch) tmem_ld_32x16(t_lane + sb * KT + c * 16, v[c]);
                 tmem_ld_wait();
             }
+            if (threadIdx.x == 64) AT_EV(1, 400 + t);        // scores in registers
             tc_fence_before();
             mbar_arrive(s_free + sb * 8);                    // the scores are in registers: the MMA warp may reuse the tile
-            mbar_wait(p_free + pb * 8, ((t >> 1) & 1) ^ 1);  // P V of two tiles ago has read this P buffer
+            uint32_t pk[4][8];                               // P as packed bf16 pairs, computed before the buffer is needed
             if (warp_valid) {
-                const uint32_t sp = base + S::P + pb * ROWT_BYTES;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     if (c >= nch) continue;
@@ -246,22 +314,38 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __r
                         if (last && c * 16 + j >= nv_last) p[j] = 0.f;
                         l += p[j];
                     }
-                    at_sts128(sp + at_swz(row, 2 * c), pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]),
-                              pack_bf16(p[6], p[7]));
-                    at_sts128(sp + at_swz(row, 2 * c + 1), pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]),
-                              pack_bf16(p[12], p[13]), pack_bf16(p[14], p[15]));
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pk[c][j] = pack_bf16(p[2 * j], p[2 * j + 1]);
+                }
+            }
+            if (threadIdx.x == 64) AT_EV(1, 500 + t);        // exponentials done
+            AT_WAIT(w_pf, p_free + pb * 8, ((t / S::NP) & 1) ^ 1);   // the P V that read this buffer last has completed
+            if (threadIdx.x == 64) AT_EV(1, 600 + t);        // P buffer free
+            if (warp_valid) {
+                const uint32_t sp = base + S::P + pb * ROWT_BYTES;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c >= nch) continue;
+                    at_sts128(sp + at_swz(row, 2 * c), pk[c][0], pk[c][1], pk[c][2], pk[c][3]);
+                    at_sts128(sp + at_swz(row, 2 * c + 1), pk[c][4], pk[c][5], pk[c][6], pk[c][7]);
                 }
             }
             fence_proxy_async();
             mbar_arrive(p_full + pb * 8);
+            if (threadIdx.x == 64) AT_EV(1, 700 + t);        // P stored, fenced, signalled
         }
+        if (threadIdx.x == 64) AT_STAMP(6);
         mbar_wait(o_full, 0);
         tc_fence_after();
+        if (threadIdx.x == 64) {
+            AT_STAMP(7);
+            AT_PUT(10, w_s1); AT_PUT(11, w_s2); AT_PUT(12, w_pf);
+        }
         if (warp_valid) {
             const int subv = vcol & 63;
             uint32_t o[HD / 16][16];
 #pragma unroll
-            for (int c = 0; c < HD / 16; ++c) tmem_ld_32x16(t_lane + 128 + subv + c * 16, o[c]);
+            for (int c = 0; c < HD / 16; ++c) tmem_ld_32x16(t_lane + S::O_COL + subv + c * 16, o[c]);
             tmem_ld_wait();
             if (grow < N) {
                 const float inv = 1.f / l;
@@ -286,6 +370,286 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __r
         tc_fence_before();
     }
     __syncthreads();
+    if (threadIdx.x == 0) AT_STAMP(8);
+    if (warp == 2) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------------ forward, wide
+// Second forward layout (default): score tiles of 128 columns (5 instead of 9 barrier round trips per pass at N = 513) and
+// EIGHT softmax warps -- two per TMEM lane quadrant, each taking one 64-column half of every tile -- so that every SM
+// sub-partition interleaves four warps when two CTAs share the SM (measured with the one-warp-per-quadrant layout above:
+// a softmax warp spends 1250 cycles per 64-column tile against a 512-cycle MUFU floor, all of it serial latency --
+// tcgen05.ld round trip, fence, barrier -- that only another warp can cover; profiles/r02c_attention_trace.txt).
+// The two halves of a row exchange their maxima / sums through shared memory once per pass.  The linear block index is
+// decoded tile-major, so the ragged last query tile of every head is scheduled after all full tiles.
+constexpr int AT8_THREADS = 64 + 256;
+constexpr int KT8 = 128;
+struct Fwd8Smem {
+    static constexpr int NSLOT = 3;                               // ring of 128-row kv tiles
+    static constexpr uint32_t Q = 0;
+    static constexpr uint32_t KV = Q + ROWT_BYTES;
+    static constexpr uint32_t P = KV + NSLOT * ROWT_BYTES;        // 128 x 128 bf16 = two K-major atoms
+    static constexpr uint32_t RED = P + 2 * ROWT_BYTES;           // float [2][128]: row maxima / sums of the two halves
+    static constexpr uint32_t BAR = RED + 2 * 128 * 4;
+    // barriers: q_full, kv_full[NSLOT], kv_empty[NSLOT], s_full, s_free, p_full, p_free, o_full
+    static constexpr int NBAR = 1 + 2 * NSLOT + 5;
+    static constexpr uint32_t TOTAL = BAR + NBAR * 8 + 16 + 1024;
+    static constexpr uint32_t O_COL = KT8;
+    static constexpr uint32_t TMEM_COLS = 256;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(AT8_THREADS, 2)
+attn_fwd_tc8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N,
+                    int H, int B, float scale_log2) {
+    using S = Fwd8Smem;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw_u32);
+    const uint32_t q_full = base + S::BAR;
+    const uint32_t kv_full = q_full + 8, kv_empty = kv_full + S::NSLOT * 8;
+    const uint32_t s_full = kv_empty + S::NSLOT * 8, s_free = s_full + 8, p_full = s_free + 8, p_free = p_full + 8, o_full = p_free + 8;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + S::BAR + S::NBAR * 8);
+    float* s_red = reinterpret_cast<float*>(sm + S::RED);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile-major decode: all full query tiles of all heads first, the ragged last tiles at the end of the grid
+    const int pairs = H * B;
+    const int pair = blockIdx.x % pairs, qt = blockIdx.x / pairs;
+    const int h = pair % H, b = pair / H, q0 = qt * QT;
+    const int D = H * HD;
+    const int T = ceil_div(N, KT8);
+    const int nv_last = N - (T - 1) * KT8;
+    const int n16_last = (nv_last + 15) & ~15;
+    const int qcol = h * HD, kcol = D + h * HD, vcol = 2 * D + h * HD;
+
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmQKV);
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < S::NSLOT; ++i) { mbar_init(kv_full + i * 8, 1); mbar_init(kv_empty + i * 8, 1); }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 256);
+        mbar_init(p_full, 256);
+        mbar_init(p_free, 1);
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), S::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    PDL_TRIGGER_EARLY();
+    pdl_wait();
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- TMA producer (128-row boxes)
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, ROWT_BYTES);
+            tma_load_3d(base + S::Q, &tmQKV, q_full, qcol & ~63, q0, b);
+            uint32_t seq = 0;
+            auto load = [&](int col, int t) {
+                const uint32_t slot = seq % S::NSLOT;
+                mbar_wait(kv_empty + slot * 8, ((seq / S::NSLOT) & 1) ^ 1);
+                mbar_arrive_expect_tx(kv_full + slot * 8, ROWT_BYTES);
+                tma_load_3d(base + S::KV + slot * ROWT_BYTES, &tmQKV, kv_full + slot * 8, col & ~63, t * KT8, b);
+                ++seq;
+            };
+            for (int t = 0; t < T; ++t) load(kcol, t);
+            for (int t = 0; t < T; ++t) {
+                load(kcol, t);
+                if (t >= 1) load(vcol, t - 1);
+            }
+            load(vcol, T - 1);
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            const uint32_t subq = (qcol & 63) * 2, subk = (kcol & 63) * 2;
+            constexpr uint32_t idesc_pv = umma_idesc_bf16(QT, 64, 0u, 1u);
+            uint32_t seq = 0;
+            auto kv_wait = [&]() -> uint32_t {
+                const uint32_t slot = seq % S::NSLOT;
+                mbar_wait(kv_full + slot * 8, (seq / S::NSLOT) & 1);
+                ++seq;
+                return slot;
+            };
+            auto issue_s = [&](int it, int t) {          // score tile number `it` (both passes counted) = Q K_t^T
+                const uint32_t slot = kv_wait();
+                mbar_wait(s_free, (it & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t idesc = umma_idesc_bf16(QT, t == T - 1 ? n16_last : KT8, 0u, 0u);
+                const uint32_t sk = base + S::KV + slot * ROWT_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < HD / 16; ++kk)
+                    umma_bf16(tmem_base, desc_kmajor(base + S::Q, subq, kk), desc_kmajor(sk, subk, kk), idesc, kk != 0);
+                umma_commit(kv_empty + slot * 8);
+                umma_commit(s_full);
+            };
+            auto issue_pv = [&](int u) {                 // O += P_u V_u, K = the tile's columns in steps of 16
+                const uint32_t slot = kv_wait();
+                mbar_wait(p_full, u & 1);
+                tc_fence_after();
+                const int nk = (u == T - 1 ? n16_last : KT8) / 16;
+                const uint32_t sv = base + S::KV + slot * ROWT_BYTES, sp = base + S::P;
+#pragma unroll 1
+                for (int kk = 0; kk < nk; ++kk)
+                    umma_bf16(tmem_base + S::O_COL, desc_kmajor(sp + (kk >> 2) * ROWT_BYTES, 0, kk & 3), desc_mnmajor(sv, kk), idesc_pv,
+                              (u | kk) != 0);
+                umma_commit(kv_empty + slot * 8);
+                umma_commit(p_free);
+            };
+            mbar_wait(q_full, 0);
+            for (int t = 0; t < T; ++t) issue_s(t, t);
+            for (int t = 0; t < T; ++t) {
+                issue_s(T + t, t);
+                if (t >= 1) issue_pv(t - 1);
+            }
+            issue_pv(T - 1);
+            umma_commit(o_full);
+            PDL_TRIGGER_LATE();
+        }
+        __syncwarp();
+    } else {
+        // ---------------------------------------------------------------- softmax: thread = (row, 64-column half)
+        const int q = warp & 3;                              // TMEM lane quadrant of this warp
+        const int half = (warp - 2) >> 2;                    // which 64 columns of every 128-column tile
+        const int row = q * 32 + lane;
+        const int grow = q0 + row;
+        const bool warp_valid = q0 + q * 32 < N;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * 64;
+        float mraw = -INFINITY;
+        for (int t = 0; t < T; ++t) {                        // pass 1: row maxima of the raw scores
+            const bool last = t == T - 1;
+            const int nv = last ? nv_last - half * 64 : 64;                  // valid columns of this half (may be <= 0)
+            const int nch = last ? min(4, max(0, (n16_last - half * 64) / 16)) : 4;
+            mbar_wait(s_full, t & 1);
+            tc_fence_after();
+            if (warp_valid && nch > 0) {
+                uint32_t v[4][16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < nch) tmem_ld_32x16(t_lane + c * 16, v[c]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c >= nch) continue;
+                    if (last && (c + 1) * 16 > nv) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c * 16 + j < nv) mraw = fmaxf(mraw, __uint_as_float(v[c][j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2)
+                            mraw = fmax3(mraw, __uint_as_float(v[c][j]), __uint_as_float(v[c][j + 1]));
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(s_free);
+        }
+        s_red[half * 128 + row] = mraw;
+        named_bar_sync(1, 256);
+        mraw = fmaxf(mraw, s_red[(half ^ 1) * 128 + row]);
+        const float msc = mraw * scale_log2;
+        float l = 0.f;
+        for (int t = 0; t < T; ++t) {                        // pass 2: p = 2^(s * scale_log2 - msc), row sums, P -> smem
+            const int it = T + t;
+            const bool last = t == T - 1;
+            const int nv = last ? nv_last - half * 64 : 64;
+            const int nch = last ? min(4, max(0, (n16_last - half * 64) / 16)) : 4;
+            mbar_wait(s_full, it & 1);
+            tc_fence_after();
+            uint32_t pk[4][8];
+            // two sub-halves of 32 columns: 32 score registers live at a time (the kernel must fit 2 x 320 threads per SM)
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+                uint32_t v[2][16];
+                if (warp_valid) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        if (2 * sub + c < nch) tmem_ld_32x16(t_lane + (2 * sub + c) * 16, v[c]);
+                    tmem_ld_wait();
+                }
+                if (sub == 1) {
+                    tc_fence_before();
+                    mbar_arrive(s_free);                     // the scores are in registers: the MMA warp may overwrite the tile
+                }
+                if (warp_valid) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int cc = 2 * sub + c;
+                        if (cc >= nch) continue;
+                        float p[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            p[j] = ex2_approx(fmaf(__uint_as_float(v[c][j]), scale_log2, -msc));
+                            if (last && cc * 16 + j >= nv) p[j] = 0.f;
+                            l += p[j];
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) pk[cc][j] = pack_bf16(p[2 * j], p[2 * j + 1]);
+                    }
+                }
+            }
+            mbar_wait(p_free, (t & 1) ^ 1);                  // P V of the previous tile has read the P buffer
+            if (warp_valid) {
+                const uint32_t sp = base + S::P + half * ROWT_BYTES;     // this half's K-major atom
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c >= nch) continue;
+                    at_sts128(sp + at_swz(row, 2 * c), pk[c][0], pk[c][1], pk[c][2], pk[c][3]);
+                    at_sts128(sp + at_swz(row, 2 * c + 1), pk[c][4], pk[c][5], pk[c][6], pk[c][7]);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(p_full);
+        }
+        named_bar_sync(1, 256);                              // every thread has read its partner's maximum
+        s_red[half * 128 + row] = l;
+        named_bar_sync(1, 256);
+        l += s_red[(half ^ 1) * 128 + row];
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        if (warp_valid) {
+            // the 16-column chunks of this head's O alternate between the two halves
+            const uint32_t o_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + S::O_COL + (vcol & 63);
+            constexpr int NCH = HD / 16;
+            uint32_t o[(NCH + 1) / 2][16];
+#pragma unroll
+            for (int c = 0; c < (NCH + 1) / 2; ++c)
+                if (2 * c + half < NCH) tmem_ld_32x16(o_lane + (2 * c + half) * 16, o[c]);
+            tmem_ld_wait();
+            if (grow < N) {
+                const float inv = 1.f / l;
+                __nv_bfloat16* orow = out + (static_cast<size_t>(b) * N + grow) * D + h * HD;
+#pragma unroll
+                for (int c = 0; c < (NCH + 1) / 2; ++c) {
+                    if (2 * c + half >= NCH) continue;
+                    uint4 lo, hi;
+                    lo.x = pack_bf16(__uint_as_float(o[c][0]) * inv, __uint_as_float(o[c][1]) * inv);
+                    lo.y = pack_bf16(__uint_as_float(o[c][2]) * inv, __uint_as_float(o[c][3]) * inv);
+                    lo.z = pack_bf16(__uint_as_float(o[c][4]) * inv, __uint_as_float(o[c][5]) * inv);
+                    lo.w = pack_bf16(__uint_as_float(o[c][6]) * inv, __uint_as_float(o[c][7]) * inv);
+                    hi.x = pack_bf16(__uint_as_float(o[c][8]) * inv, __uint_as_float(o[c][9]) * inv);
+                    hi.y = pack_bf16(__uint_as_float(o[c][10]) * inv, __uint_as_float(o[c][11]) * inv);
+                    hi.z = pack_bf16(__uint_as_float(o[c][12]) * inv, __uint_as_float(o[c][13]) * inv);
+                    hi.w = pack_bf16(__uint_as_float(o[c][14]) * inv, __uint_as_float(o[c][15]) * inv);
+                    *reinterpret_cast<uint4*>(orow + (2 * c + half) * 16) = lo;
+                    *reinterpret_cast<uint4*>(orow + (2 * c + half) * 16 + 8) = hi;
+                }
+                if (half == 0) lse[(static_cast<size_t>(b) * H + h) * N + grow] = (msc + log2f(l)) * LN2_F;
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, S::TMEM_COLS);
 }
 
@@ -304,11 +668,11 @@ struct DqSmem {
 };
 
 template <int HD>
-__global__ void __launch_bounds__(AT_THREADS)
+__global__ void __launch_bounds__(AT8_THREADS, 2)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                       const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                       const float* __restrict__ lse, float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int N, int H,
-                      float scale, float scale_log2) {
+                      int B, float scale, float scale_log2) {
     using S = DqSmem;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -321,7 +685,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + S::BAR + S::NBAR * 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int h = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * QT;
+    const int pairs = H * B;                       // tile-major: the ragged last tiles are scheduled last
+    const int pair = blockIdx.x % pairs;
+    const int h = pair % H, b = pair / H, q0 = (blockIdx.x / pairs) * QT;
     const int D = H * HD;
     const int T = ceil_div(N, KT);
     const int nv_last = N - (T - 1) * KT;
@@ -336,8 +702,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         mbar_init(qdo_full, 1);
         for (int i = 0; i < S::NSLOT; ++i) { mbar_init(kv_full + i * 8, 1); mbar_init(kv_empty + i * 8, 1); }
         mbar_init(sdp_full, 1);
-        mbar_init(sdp_free, 128);
-        mbar_init(ds_full, 128);
+        mbar_init(sdp_free, 256);
+        mbar_init(ds_full, 256);
         mbar_init(ds_free, 1);
         mbar_init(dq_full, 1);
         fence_barrier_init();
@@ -423,6 +789,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         __syncwarp();
     } else {
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;                    // two warps per TMEM lane quadrant: 32 of a tile's 64 columns each
         const int row = q * 32 + lane;
         const int grow = q0 + row;
         const bool warp_valid = q0 + q * 32 < N;
@@ -445,7 +812,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
                     dl = fmaf(af.y, gf.y, dl);
                 }
             }
-            delta[(static_cast<size_t>(b) * H + h) * N + grow] = dl;
+            if (half == 0) delta[(static_cast<size_t>(b) * H + h) * N + grow] = dl;
         }
         for (int t = 0; t < T; ++t) {
             const bool last = t == T - 1;
@@ -453,8 +820,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             mbar_wait(sdp_full, t & 1);
             tc_fence_after();
             mbar_wait(ds_free, (t & 1) ^ 1);                 // dQ MMA of the previous tile has read the dS buffer
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            {
                 uint32_t sv[2][16], dv[2][16];
                 if (warp_valid) {
 #pragma unroll
@@ -465,10 +831,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
                         }
                     tmem_ld_wait();
                 }
-                if (half == 1) {
-                    tc_fence_before();
-                    mbar_arrive(sdp_free);                   // both score tiles are in registers
-                }
+                tc_fence_before();
+                mbar_arrive(sdp_free);                       // this thread's part of both score tiles is in registers
                 if (warp_valid) {
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
@@ -495,14 +859,17 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         tc_fence_after();
         if (warp_valid) {
             const int subk = kcol & 63;          // dQ = dS K: the MMA ran over the 64 columns of K's box
-            uint32_t o[HD / 16][16];
+            constexpr int NCH = HD / 16;         // 16-column chunks of this head alternate between the two halves
+            uint32_t o[(NCH + 1) / 2][16];
 #pragma unroll
-            for (int c = 0; c < HD / 16; ++c) tmem_ld_32x16(t_lane + 128 + subk + c * 16, o[c]);
+            for (int c = 0; c < (NCH + 1) / 2; ++c)
+                if (2 * c + half < NCH) tmem_ld_32x16(t_lane + 128 + subk + (2 * c + half) * 16, o[c]);
             tmem_ld_wait();
             if (grow < N) {
                 __nv_bfloat16* drow = dqkv + (static_cast<size_t>(b) * N + grow) * (3 * D) + h * HD;
 #pragma unroll
-                for (int c = 0; c < HD / 16; ++c) {
+                for (int c = 0; c < (NCH + 1) / 2; ++c) {
+                    if (2 * c + half >= NCH) continue;
                     uint4 lo, hi;
                     lo.x = pack_bf16(__uint_as_float(o[c][0]) * scale, __uint_as_float(o[c][1]) * scale);
                     lo.y = pack_bf16(__uint_as_float(o[c][2]) * scale, __uint_as_float(o[c][3]) * scale);
@@ -512,8 +879,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
                     hi.y = pack_bf16(__uint_as_float(o[c][10]) * scale, __uint_as_float(o[c][11]) * scale);
                     hi.z = pack_bf16(__uint_as_float(o[c][12]) * scale, __uint_as_float(o[c][13]) * scale);
                     hi.w = pack_bf16(__uint_as_float(o[c][14]) * scale, __uint_as_float(o[c][15]) * scale);
-                    *reinterpret_cast<uint4*>(drow + c * 16) = lo;
-                    *reinterpret_cast<uint4*>(drow + c * 16 + 8) = hi;
+                    *reinterpret_cast<uint4*>(drow + (2 * c + half) * 16) = lo;
+                    *reinterpret_cast<uint4*>(drow + (2 * c + half) * 16 + 8) = hi;
                 }
             }
         }
@@ -540,10 +907,10 @@ struct DkvSmem {
 };
 
 template <int HD>
-__global__ void __launch_bounds__(AT_THREADS)
+__global__ void __launch_bounds__(AT8_THREADS, 2)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                        const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int N,
-                       int H, float scale, float scale_log2) {
+                       int H, int B, float scale, float scale_log2) {
     using S = DkvSmem;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -558,7 +925,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     float* s_del = s_lse + 128;                                  // [2][64]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int h = blockIdx.y, b = blockIdx.z, kv0 = blockIdx.x * QT;
+    const int pairs = H * B;
+    const int pair = blockIdx.x % pairs;
+    const int h = pair % H, b = pair / H, kv0 = (blockIdx.x / pairs) * QT;
     const int D = H * HD;
     const int T = ceil_div(N, KT);                   // query tiles of 64 rows
     const int nv_last = N - (T - 1) * KT;
@@ -573,8 +942,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         mbar_init(kv_full, 1);
         for (int i = 0; i < S::NSLOT; ++i) { mbar_init(r_full + i * 8, 1); mbar_init(r_empty + i * 8, 1); }
         mbar_init(sdp_full, 1);
-        mbar_init(sdp_free, 128);
-        mbar_init(pds_full, 128);
+        mbar_init(sdp_free, 256);
+        mbar_init(pds_full, 256);
         mbar_init(pds_free, 1);
         mbar_init(dkv_full, 1);
         fence_barrier_init();
@@ -664,20 +1033,21 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         __syncwarp();
     } else {
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;                // two warps per TMEM lane quadrant: 32 of a tile's 64 query columns each
         const int row = q * 32 + lane;                   // kv row of this thread
         const int grow = kv0 + row;
         const bool warp_valid = kv0 + q * 32 < N;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const int st = threadIdx.x - 64;                 // 0..127 among the softmax threads
+        const int st = threadIdx.x - 64;                 // 0..255 among the softmax threads
         const float* lrow = lse + (static_cast<size_t>(b) * H + h) * N;
         const float* drow = delta + (static_cast<size_t>(b) * H + h) * N;
         auto stage = [&](int t) {                        // statistics of query tile t -> shared memory (buffer t & 1)
             const int c = st & 63, qi = t * KT + c;
             if (st < 64) s_lse[(t & 1) * 64 + c] = qi < N ? lrow[qi] * LOG2E_F : INFINITY;   // padded query rows: p = 0
-            else s_del[(t & 1) * 64 + c] = qi < N ? drow[qi] : 0.f;
+            else if (st < 128) s_del[(t & 1) * 64 + c] = qi < N ? drow[qi] : 0.f;
         };
         stage(0);
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         for (int t = 0; t < T; ++t) {
             const bool last = t == T - 1;
             const int nch = last ? n16_last / 16 : 4;
@@ -687,8 +1057,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
             mbar_wait(sdp_full, t & 1);
             tc_fence_after();
             mbar_wait(pds_free, (t & 1) ^ 1);            // the dK / dV MMAs of the previous tile have read P^T / dS^T
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            {
                 uint32_t sv[2][16], dv[2][16];
                 if (warp_valid) {
 #pragma unroll
@@ -699,70 +1068,65 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
                         }
                     tmem_ld_wait();
                 }
-                if (half == 1) {
-                    tc_fence_before();
-                    mbar_arrive(sdp_free);
-                }
+                tc_fence_before();
+                mbar_arrive(sdp_free);
                 if (warp_valid) {
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         const int cc = 2 * half + c;
                         if (cc >= nch) continue;
-                        float p[16], ds[16];
+                        uint32_t pp[8], dd8[8];
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
                             const float4 l4 = *reinterpret_cast<const float4*>(sl + cc * 16 + 4 * j4);
                             const float4 d4 = *reinterpret_cast<const float4*>(sd + cc * 16 + 4 * j4);
                             const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
+                            float p[4], ds[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const int j = 4 * j4 + e;
-                                p[j] = ex2_approx(fmaf(__uint_as_float(sv[c][j]), scale_log2, -lv[e]));
-                                ds[j] = p[j] * (__uint_as_float(dv[c][j]) - dd[e]);
+                                p[e] = ex2_approx(fmaf(__uint_as_float(sv[c][j]), scale_log2, -lv[e]));
+                                ds[e] = p[e] * (__uint_as_float(dv[c][j]) - dd[e]);
                             }
+                            pp[2 * j4] = pack_bf16(p[0], p[1]); pp[2 * j4 + 1] = pack_bf16(p[2], p[3]);
+                            dd8[2 * j4] = pack_bf16(ds[0], ds[1]); dd8[2 * j4 + 1] = pack_bf16(ds[2], ds[3]);
                         }
-                        at_sts128(base + S::PT + at_swz(row, 2 * cc), pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]),
-                                  pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
-                        at_sts128(base + S::PT + at_swz(row, 2 * cc + 1), pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]),
-                                  pack_bf16(p[12], p[13]), pack_bf16(p[14], p[15]));
-                        at_sts128(base + S::DST + at_swz(row, 2 * cc), pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]),
-                                  pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
-                        at_sts128(base + S::DST + at_swz(row, 2 * cc + 1), pack_bf16(ds[8], ds[9]), pack_bf16(ds[10], ds[11]),
-                                  pack_bf16(ds[12], ds[13]), pack_bf16(ds[14], ds[15]));
+                        at_sts128(base + S::PT + at_swz(row, 2 * cc), pp[0], pp[1], pp[2], pp[3]);
+                        at_sts128(base + S::PT + at_swz(row, 2 * cc + 1), pp[4], pp[5], pp[6], pp[7]);
+                        at_sts128(base + S::DST + at_swz(row, 2 * cc), dd8[0], dd8[1], dd8[2], dd8[3]);
+                        at_sts128(base + S::DST + at_swz(row, 2 * cc + 1), dd8[4], dd8[5], dd8[6], dd8[7]);
                     }
                 }
             }
             fence_proxy_async();
             mbar_arrive(pds_full);
-            named_bar_sync(1, 128);      // next tile's statistics are staged; this tile's are no longer read
+            named_bar_sync(1, 256);      // next tile's statistics are staged; this tile's are no longer read
         }
         mbar_wait(dkv_full, 0);
         tc_fence_after();
         if (warp_valid) {
             const int subq = qcol & 63;      // both accumulators span the 64 columns of the Q / dO boxes
+            const int which = half;          // half 0: dK (x scale) -> k section, half 1: dV -> v section
+            uint32_t o[HD / 16][16];
 #pragma unroll
-            for (int which = 0; which < 2; ++which) {        // 0: dK (x scale) -> k section, 1: dV -> v section
-                uint32_t o[HD / 16][16];
+            for (int c = 0; c < HD / 16; ++c) tmem_ld_32x16(t_lane + 128 + which * 64 + subq + c * 16, o[c]);
+            tmem_ld_wait();
+            if (grow < N) {
+                const float f = which ? 1.0f : scale;
+                __nv_bfloat16* orow = dqkv + (static_cast<size_t>(b) * N + grow) * (3 * D) + (which ? vcol : kcol);
 #pragma unroll
-                for (int c = 0; c < HD / 16; ++c) tmem_ld_32x16(t_lane + 128 + which * 64 + subq + c * 16, o[c]);
-                tmem_ld_wait();
-                if (grow < N) {
-                    const float f = which ? 1.0f : scale;
-                    __nv_bfloat16* orow = dqkv + (static_cast<size_t>(b) * N + grow) * (3 * D) + (which ? vcol : kcol);
-#pragma unroll
-                    for (int c = 0; c < HD / 16; ++c) {
-                        uint4 lo, hi;
-                        lo.x = pack_bf16(__uint_as_float(o[c][0]) * f, __uint_as_float(o[c][1]) * f);
-                        lo.y = pack_bf16(__uint_as_float(o[c][2]) * f, __uint_as_float(o[c][3]) * f);
-                        lo.z = pack_bf16(__uint_as_float(o[c][4]) * f, __uint_as_float(o[c][5]) * f);
-                        lo.w = pack_bf16(__uint_as_float(o[c][6]) * f, __uint_as_float(o[c][7]) * f);
-                        hi.x = pack_bf16(__uint_as_float(o[c][8]) * f, __uint_as_float(o[c][9]) * f);
-                        hi.y = pack_bf16(__uint_as_float(o[c][10]) * f, __uint_as_float(o[c][11]) * f);
-                        hi.z = pack_bf16(__uint_as_float(o[c][12]) * f, __uint_as_float(o[c][13]) * f);
-                        hi.w = pack_bf16(__uint_as_float(o[c][14]) * f, __uint_as_float(o[c][15]) * f);
-                        *reinterpret_cast<uint4*>(orow + c * 16) = lo;
-                        *reinterpret_cast<uint4*>(orow + c * 16 + 8) = hi;
-                    }
+                for (int c = 0; c < HD / 16; ++c) {
+                    uint4 lo, hi;
+                    lo.x = pack_bf16(__uint_as_float(o[c][0]) * f, __uint_as_float(o[c][1]) * f);
+                    lo.y = pack_bf16(__uint_as_float(o[c][2]) * f, __uint_as_float(o[c][3]) * f);
+                    lo.z = pack_bf16(__uint_as_float(o[c][4]) * f, __uint_as_float(o[c][5]) * f);
+                    lo.w = pack_bf16(__uint_as_float(o[c][6]) * f, __uint_as_float(o[c][7]) * f);
+                    hi.x = pack_bf16(__uint_as_float(o[c][8]) * f, __uint_as_float(o[c][9]) * f);
+                    hi.y = pack_bf16(__uint_as_float(o[c][10]) * f, __uint_as_float(o[c][11]) * f);
+                    hi.z = pack_bf16(__uint_as_float(o[c][12]) * f, __uint_as_float(o[c][13]) * f);
+                    hi.w = pack_bf16(__uint_as_float(o[c][14]) * f, __uint_as_float(o[c][15]) * f);
+                    *reinterpret_cast<uint4*>(orow + c * 16) = lo;
+                    *reinterpret_cast<uint4*>(orow + c * 16 + 8) = hi;
                 }
             }
         }
@@ -782,12 +1146,32 @@ static int set_smem(Kern kern, uint32_t bytes, bool& done) {
     return 0;
 }
 
+static int fwd_cfg() {       // VITAE_ATTN_FWD_CFG=0: two CTAs per SM with double buffers (A/B timing); default 1 (three per SM)
+    static const int cfg = [] { const char* e = getenv("VITAE_ATTN_FWD_CFG"); return e && e[0] == '0' ? 0 : 1; }();
+    return cfg;
+}
+
+template <int HD, int CFG>
+static int launch_fwd_cfg(const CUtensorMap& tq, void* out, float* lse, int B, int N, int H, float sl2, cudaStream_t st) {
+    static bool attr = false;
+    if (int rc = set_smem(attn_fwd_tc_kernel<HD, CFG>, FwdSmem<CFG>::TOTAL, attr)) return rc;
+    launch_kernel(attn_fwd_tc_kernel<HD, CFG>, dim3(ceil_div(N, QT), H, B), dim3(AT_THREADS), FwdSmem<CFG>::TOTAL, st, tq,
+                  static_cast<__nv_bfloat16*>(out), lse, N, H, sl2);
+    VITAE_CHECK_LAUNCH("attention_fwd");
+    return 0;
+}
+
 template <int HD>
 static int launch_fwd(const CUtensorMap& tq, void* out, float* lse, int B, int N, int H, float sl2, cudaStream_t st) {
+    return fwd_cfg() == 0 ? launch_fwd_cfg<HD, 0>(tq, out, lse, B, N, H, sl2, st) : launch_fwd_cfg<HD, 1>(tq, out, lse, B, N, H, sl2, st);
+}
+
+template <int HD>
+static int launch_fwd8(const CUtensorMap& tq128, void* out, float* lse, int B, int N, int H, float sl2, cudaStream_t st) {
     static bool attr = false;
-    if (int rc = set_smem(attn_fwd_tc_kernel<HD>, FwdSmem::TOTAL, attr)) return rc;
-    launch_kernel(attn_fwd_tc_kernel<HD>, dim3(ceil_div(N, QT), H, B), dim3(AT_THREADS), FwdSmem::TOTAL, st, tq,
-                  static_cast<__nv_bfloat16*>(out), lse, N, H, sl2);
+    if (int rc = set_smem(attn_fwd_tc8_kernel<HD>, Fwd8Smem::TOTAL, attr)) return rc;
+    launch_kernel(attn_fwd_tc8_kernel<HD>, dim3(ceil_div(N, QT) * H * B), dim3(AT8_THREADS), Fwd8Smem::TOTAL, st, tq128,
+                  static_cast<__nv_bfloat16*>(out), lse, N, H, B, sl2);
     VITAE_CHECK_LAUNCH("attention_fwd");
     return 0;
 }
@@ -798,13 +1182,13 @@ static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const void*
     static bool attr_dq = false, attr_dkv = false;
     if (int rc = set_smem(attn_bwd_dq_tc_kernel<HD>, DqSmem::TOTAL, attr_dq)) return rc;
     if (int rc = set_smem(attn_bwd_dkv_tc_kernel<HD>, DkvSmem::TOTAL, attr_dkv)) return rc;
-    const dim3 grid(ceil_div(N, QT), H, B);
-    launch_kernel(attn_bwd_dq_tc_kernel<HD>, grid, dim3(AT_THREADS), DqSmem::TOTAL, st, tq, tdo,
+    const dim3 grid(ceil_div(N, QT) * H * B);
+    launch_kernel(attn_bwd_dq_tc_kernel<HD>, grid, dim3(AT8_THREADS), DqSmem::TOTAL, st, tq, tdo,
                   static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), lse, delta,
-                  static_cast<__nv_bfloat16*>(dqkv), N, H, scale, sl2);
+                  static_cast<__nv_bfloat16*>(dqkv), N, H, B, scale, sl2);
     VITAE_CHECK_LAUNCH("attention_bwd_dq");
-    launch_kernel(attn_bwd_dkv_tc_kernel<HD>, grid, dim3(AT_THREADS), DkvSmem::TOTAL, st, tq, tdo, lse,
-                  static_cast<const float*>(delta), static_cast<__nv_bfloat16*>(dqkv), N, H, scale, sl2);
+    launch_kernel(attn_bwd_dkv_tc_kernel<HD>, grid, dim3(AT8_THREADS), DkvSmem::TOTAL, st, tq, tdo, lse,
+                  static_cast<const float*>(delta), static_cast<__nv_bfloat16*>(dqkv), N, H, B, scale, sl2);
     VITAE_CHECK_LAUNCH("attention_bwd_dkv");
     return 0;
 }
@@ -820,6 +1204,13 @@ int attention_bwd_legacy(const void* qkv, const void* out, const void* dout, con
                          int N, int H, int hd, float scale, void* stream);
 }  // namespace vitae
 
+#ifdef VITAE_ATTN_TRACE
+extern "C" int vitae_debug_set_attn_trace(void* buf) {
+    cudaError_t e = cudaMemcpyToSymbol(g_attn_trace, &buf, sizeof(buf));
+    return e == cudaSuccess ? 0 : set_error(-3, "set_attn_trace: %s", cudaGetErrorString(e));
+}
+#endif
+
 static bool use_legacy() {
     static const bool on = [] { const char* e = getenv("VITAE_ATTN_LEGACY"); return e && e[0] == '1'; }();
     return on;
@@ -832,10 +1223,17 @@ extern "C" int vitae_attention_fwd(const void* qkv, void* out, float* lse, int B
     VITAE_REQUIRE((H * hd) % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                   "attention_fwd: qkv / out must be 16-byte aligned and H*hd a multiple of 8");
     const int D = H * hd;
-    CUtensorMap tq;
-    if (int rc = make_tmap(&tq, qkv, 2, 3ull * D, (uint64_t)N, (uint64_t)B, 3ull * D, 64, 64)) return rc;
     const float sl2 = scale * LOG2E_F;
     cudaStream_t st = as_stream(stream);
+    CUtensorMap tq;
+    static const bool narrow = [] { const char* e = getenv("VITAE_ATTN_FWD"); return e && e[0] == 'v' && e[1] == '1'; }();
+    if (!narrow) {      // default: 128-column score tiles, eight softmax warps (VITAE_ATTN_FWD=v1 selects the first layout)
+        if (int rc = make_tmap(&tq, qkv, 2, 3ull * D, (uint64_t)N, (uint64_t)B, 3ull * D, 64, 128)) return rc;
+        if (hd == 64) return launch_fwd8<64>(tq, out, lse, B, N, H, sl2, st);
+        if (hd == 32) return launch_fwd8<32>(tq, out, lse, B, N, H, sl2, st);
+        return launch_fwd8<16>(tq, out, lse, B, N, H, sl2, st);
+    }
+    if (int rc = make_tmap(&tq, qkv, 2, 3ull * D, (uint64_t)N, (uint64_t)B, 3ull * D, 64, 64)) return rc;
     if (hd == 64) return launch_fwd<64>(tq, out, lse, B, N, H, sl2, st);
     if (hd == 32) return launch_fwd<32>(tq, out, lse, B, N, H, sl2, st);
     return launch_fwd<16>(tq, out, lse, B, N, H, sl2, st);

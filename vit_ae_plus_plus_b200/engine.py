@@ -64,8 +64,13 @@ def block_param_names(prefix: str, i: int) -> List[str]:
             f"{b}.attn.qkv.weight", f"{b}.attn.qkv.bias", f"{b}.norm1.weight", f"{b}.norm1.bias"]
 
 
-def backward_param_order(depth: int, decoder_depth: int) -> List[str]:
-    names = ["decoder_pred.weight", "decoder_pred.bias", "decoder_norm.weight", "decoder_norm.bias"]
+PREDICTOR_PARAMS = ["predictor.3.weight", "predictor.3.bias", "predictor.1.weight", "predictor.1.bias", "predictor.0.weight"]
+
+
+def backward_param_order(depth: int, decoder_depth: int, predictor: bool = False) -> List[str]:
+    # the contrastive predictor (model/vit_autoenc.py:263-268) sits downstream of everything else: its gradients come first
+    names = list(PREDICTOR_PARAMS) if predictor else []
+    names += ["decoder_pred.weight", "decoder_pred.bias", "decoder_norm.weight", "decoder_norm.bias"]
     for i in reversed(range(decoder_depth)):
         names += block_param_names("decoder_blocks", i)
     names += ["mask_token", "decoder_embed.weight", "decoder_embed.bias", "norm.weight", "norm.bias"]
@@ -386,7 +391,10 @@ class MAEEngine:
                 raise ops._lib.VitaeError(f"unsupported width {st.dim}/{st.hidden}")
         if self.P % 8 or p % 4:
             raise ops._lib.VitaeError("patch_size must be a multiple of 4")
-        self.flat = FlatParams(named_params, backward_param_order(cfg["depth"], cfg["decoder_depth"]), dev)
+        self.has_predictor = "predictor.0.weight" in named_params
+        self.flat = FlatParams(named_params, backward_param_order(cfg["depth"], cfg["decoder_depth"], self.has_predictor), dev)
+        # BatchNorm1d of the predictor: (running_mean, running_var, eps, momentum), set by ContrastiveMAEViT.engine()
+        self.bn_state = None
         self.pos = pos_embed.detach().reshape(self.L + 1, D).contiguous()
         self.dpos = decoder_pos_embed.detach().reshape(self.L + 1, Dd).contiguous()
         self.plans: Dict[Tuple[int, int], MAEPlan] = {}
@@ -438,7 +446,7 @@ class MAEEngine:
                 return 1 + n_enc
             if name.startswith("decoder_blocks."):
                 return 2 + n_enc + int(name.split(".")[1]) // db
-            return 2 + n_enc + n_dec          # decoder_norm, decoder_pred
+            return 2 + n_enc + n_dec          # decoder_norm, decoder_pred (and the contrastive predictor in front of them)
         group_of = {n: gid(n) for n in self.flat.order}
         ngroups = 3 + n_enc + n_dec
         ranges = [[None, None] for _ in range(ngroups)]
@@ -595,21 +603,26 @@ class MAEEngine:
         return pl.vol_static
 
     # ------------------------------------------------------------------------------------------------ forward
-    def forward_encoder_only(self, vol: torch.Tensor, noise: torch.Tensor, keep: int, slot: int = 1) -> MAEPlan:
+    def forward_encoder_only(self, vol: torch.Tensor, noise: torch.Tensor, keep: int, slot: int = 1,
+                             with_predictor: bool = False) -> MAEPlan:
         """Encoder pass alone (second view of the contrastive model, model/vit_autoenc.py:277) into arena ``slot``."""
         pl = self.plan(vol.shape[0], keep, slot)
         vol = self._resident(pl, vol)
         pl.vol = vol
         pl.noise.copy_(noise)
         self.refresh_shadow()
+        if with_predictor:
+            self._pred_bufs(pl)
         def body():
             self.encode(pl, vol, pl.noise)
+            if with_predictor:
+                self.predictor_forward(pl)
             self.lanes.join()
-        self._run(pl, ("enc", vol.data_ptr()), body)
+        self._run(pl, ("enc", vol.data_ptr(), with_predictor), body)
         return pl
 
     def forward(self, vol: torch.Tensor, noise: torch.Tensor, keep: int, want_loss: bool = True,
-                pred_f32: bool = False, want_edge: bool = False) -> MAEPlan:
+                pred_f32: bool = False, want_edge: bool = False, with_predictor: bool = False) -> MAEPlan:
         """vol fp32 [B,C,V,V,V] (contiguous, CUDA); noise fp32 [B,L].  Fills plan.pred / mask / loss_out (and, with
         ``want_edge``, plan.edge_out = raw edge-map loss of model/vit_autoenc.py:221-224)."""
         B = vol.shape[0]
@@ -622,6 +635,8 @@ class MAEEngine:
         self.refresh_shadow()
         if want_edge:
             pl.edge_buffers(self)
+        if with_predictor:
+            self._pred_bufs(pl)
 
         def body():
             if want_edge:
@@ -629,6 +644,8 @@ class MAEEngine:
                 # the background stream underneath the encoder / decoder, whose small GEMMs leave most SMs idle
                 self._background(lambda: ops.edge_target(vol, self.edge_taps, pl.edge_scratch, pl.edge_tgt))
             self.encode(pl, vol, pl.noise)
+            if with_predictor:
+                self.predictor_forward(pl)
             self.decode(pl, pred_f32)
             if want_loss:
                 ops.masked_mse_fwd(pl.pred, vol, pl.mask, pl.patch_sums, pl.loss_out, self.p)
@@ -637,7 +654,7 @@ class MAEEngine:
                 ops.edge_loss_fwd(pl.pred, pl.edge_tgt, pl.edge_scratch, pl.edge_resid, pl.edge_out, pl.B, self.C, self.V,
                                   self.p)
             self.lanes.join()          # the side lane carries the L2 prefetches of the forward
-        self._run(pl, ("fwd", vol.data_ptr(), pred_f32, want_loss, want_edge), body)
+        self._run(pl, ("fwd", vol.data_ptr(), pred_f32, want_loss, want_edge, with_predictor), body)
         self.params_in_flight = False      # the pass above waited for every parameter group
         return pl
 
@@ -859,7 +876,7 @@ class MAEEngine:
         if encoder_only:
             parts = [(stage_enc_top, 0)]       # slices only matter for the gradient exchange; see backward()
         else:
-            parts = [(stage_pred, off("decoder_pred.weight"))]
+            parts = [(stage_pred, 0)]          # from the start of the buffer: the predictor's gradients ride with this slice
             if dec_all:
                 parts.append((stage_dec, off(f"decoder_blocks.{dec_all[0]}.mlp.fc2.weight")))
             parts.append((stage_mid, off("mask_token")))
@@ -981,6 +998,62 @@ class MAEEngine:
             self._side(lambda jobs=jobs: ops.block_colreduce(jobs, M, pl.bcr_ws, accumulate=acc), reads=tuple(job_reads),
                        lane=1)
         return cur
+
+    # ------------------------------------------------------------------------------------------------ contrastive predictor
+    def _pred_bufs(self, pl: MAEPlan):
+        if getattr(pl, "pb", None) is None:
+            D, M, dev = self.enc.dim, pl.Me, self.device
+            b = _BlockBufs()
+            b.h = torch.empty((M, D), dtype=_F32, device=dev)
+            b.act = torch.empty((M, D), dtype=_BF16, device=dev)
+            b.mean, b.rstd = torch.empty(D, dtype=_F32, device=dev), torch.empty(D, dtype=_F32, device=dev)
+            b.p = torch.empty((M, D), dtype=_F32, device=dev)
+            b.dp32 = torch.empty((M, D), dtype=_F32, device=dev)
+            b.dp16 = torch.empty((M, D), dtype=_BF16, device=dev)
+            b.dact = torch.empty((M, D), dtype=_BF16, device=dev)
+            b.dh = torch.empty((M, D), dtype=_BF16, device=dev)
+            b.dlat = torch.empty((M, D), dtype=_F32, device=dev)
+            b.cs_ws = torch.zeros(ops.colsum_workspace_bytes(M, D), dtype=torch.uint8, device=dev)
+            pl.pb = b
+        return pl.pb
+
+    def predictor_forward(self, pl: MAEPlan) -> None:
+        """p = predictor(latent) of model/vit_autoenc.py:263-268,282-283 on the rows of ``pl.latent`` (bf16 GEMM operand) ->
+        pl.pb.p fp32 [B*Ne, D].  BatchNorm1d runs in training mode (batch statistics of the token rows, running statistics
+        updated in place)."""
+        b = self._pred_bufs(pl)
+        D, M = self.enc.dim, pl.Me
+        rm, rv, eps, mom = self.bn_state
+        self._need("predictor.0.weight")
+        ops.gemm(pl.latent, self._w("predictor.0.weight"), M, D, D, out_f32=b.h, workspace=self.ws_main)
+        ops.bn_relu_fwd(b.h, self._p("predictor.1.weight"), self._p("predictor.1.bias"), eps, b.act, b.mean, b.rstd, rm, rv, mom)
+        ops.gemm(b.act, self._w("predictor.3.weight"), M, D, D, bias=self._p("predictor.3.bias"), out_f32=b.p, workspace=self.ws_main)
+
+    def predictor_backward(self, pl: MAEPlan, dp: torch.Tensor, accumulate: bool) -> torch.Tensor:
+        """Reverse of predictor_forward for the upstream gradient ``dp`` fp32 [B*Ne, D]: parameter gradients into the flat
+        buffer, returns the gradient w.r.t. the latent (fp32, a plan buffer)."""
+        b = self._pred_bufs(pl)
+        D, M = self.enc.dim, pl.Me
+        b.dp32.copy_(dp.reshape(M, D))
+
+        def body():
+            ops.cast_f32_to_bf16(b.dp32.view(-1), b.dp16.view(-1))
+            ops.gemm(b.dp16, b.act, D, D, M, a_mn_major=True, b_mn_major=True, out_f32=self._g("predictor.3.weight"),
+                     accumulate=accumulate, workspace=self.ws_main)
+            ops.colsum(b.dp16, M, D, self._g("predictor.3.bias"), b.cs_ws, accumulate=accumulate)
+            ops.gemm(b.dp16, self._w("predictor.3.weight"), M, D, D, b_mn_major=True, out_bf16=b.dact, workspace=self.ws_main)
+            ops.bn_relu_bwd(b.dact, b.h, self._p("predictor.1.weight"), self._p("predictor.1.bias"), b.mean, b.rstd, b.dh,
+                            self._g("predictor.1.weight"), self._g("predictor.1.bias"), accumulate)
+            ops.gemm(b.dh, pl.latent, D, D, M, a_mn_major=True, b_mn_major=True, out_f32=self._g("predictor.0.weight"),
+                     accumulate=accumulate, workspace=self.ws_main)
+            ops.gemm(b.dh, self._w("predictor.0.weight"), M, D, D, b_mn_major=True, out_f32=b.dlat, workspace=self.ws_main)
+        self._run(pl, ("pred_bwd", bool(accumulate)), body)
+        return b.dlat
+
+    def zero_predictor_grads(self) -> None:
+        a = self.flat.offsets[PREDICTOR_PARAMS[0]][0]
+        o, k, _ = self.flat.offsets[PREDICTOR_PARAMS[-1]]
+        self.flat.g32[a:o + k].zero_()
 
     # ------------------------------------------------------------------------------------------------ data parallel
     def _grad_reducer(self) -> "dp.GradReducer":

@@ -204,10 +204,10 @@ class MaskedAutoencoderViT(nn.Module):
 
     # ------------------------------------------------------------------------------------------------ engine plumbing
     def _trainable(self):
-        """Parameters that live in the engine's flat buffers (everything of the MAE; the contrastive predictor /
-        projection head are ordinary torch modules with their own storage)."""
+        """Parameters that live in the engine's flat buffers: everything of the MAE and the contrastive predictor (the
+        never-called projection head of ``use_proj`` keeps its own storage)."""
         return {n: p for n, p in self.named_parameters()
-                if n not in ("pos_embed", "decoder_pos_embed") and not n.startswith(("predictor.", "projection_head."))}
+                if n not in ("pos_embed", "decoder_pos_embed") and not n.startswith("projection_head.")}
 
     def engine(self) -> MAEEngine:
         """Builds (once per device placement) the flat parameter buffers; the nn.Parameters become views of them."""
@@ -246,6 +246,15 @@ class MaskedAutoencoderViT(nn.Module):
             def __exit__(self, *exc):
                 module.require_backward_grad_sync = self.prev
         return _NoSync()
+
+    def _accumulating(self) -> bool:
+        """True when this backward adds to gradients already sitting in the aliased ``.grad`` views (accumulation
+        micro-step) rather than starting from zero."""
+        flat = self._engine.flat
+        state = flat.grads_alias()
+        if state is None:
+            state = flat.grads_alias(thorough=True)
+        return state is True and not flat.overwrite_grads
 
     def _backward(self, pl, drecon, dpred, dlatent=None, second=None, dedge=None):
         eng = self._engine
@@ -422,15 +431,16 @@ class MaskedAutoencoderViT(nn.Module):
 
 class _ContrastiveStep(torch.autograd.Function):
     """One autograd node for both views of the contrastive model: forward = full MAE pass on view 1 + encoder pass on
-    view 2; backward = full backward (with the latent gradient of view 1 added at the encoder norm) followed by the
-    encoder-only backward of view 2 accumulating into the same gradient buffers.  A single node fixes that order."""
+    view 2, each followed by the predictor (model/vit_autoenc.py:263-268,282-283) on its latent; backward = predictor
+    backward of both views (their latent gradients join whatever arrives for the latents directly), full backward of view
+    1, then the encoder-only backward of view 2 accumulating into the same gradient buffers.  A single node fixes that order."""
 
     @staticmethod
     def forward(ctx, anchor, module, vol1, vol2, noise1, noise2, keep, want_edge):
         eng = module._engine
         pl1 = eng.forward(vol1, noise1, keep, want_loss=True, pred_f32=module.pred_dtype == torch.float32,
-                          want_edge=want_edge)
-        pl2 = eng.forward_encoder_only(vol2, noise2, keep, slot=1)
+                          want_edge=want_edge, with_predictor=True)
+        pl2 = eng.forward_encoder_only(vol2, noise2, keep, slot=1, with_predictor=True)
         pl1.step_id += 1
         pl2.step_id += 1
         ctx.module, ctx.pl1, ctx.pl2, ctx.ids, ctx.want_edge = module, pl1, pl2, (pl1.step_id, pl2.step_id), want_edge
@@ -439,14 +449,29 @@ class _ContrastiveStep(torch.autograd.Function):
         raw_edge = pl1.edge_out[0].clone() if want_edge else torch.zeros((), device=vol1.device)
         pred = pl1.pred_view(module.pred_dtype)
         latent1, latent2 = pl1.latent32.clone(), pl2.latent32.clone()  # [B*Ne, D], model/vit_autoenc.py:280-281
+        p1, p2 = pl1.pb.p.clone(), pl2.pb.p.clone()
         ctx.mark_non_differentiable(mask)
-        return recon, raw_edge, pred, mask, latent1, latent2
+        return recon, raw_edge, pred, mask, latent1, latent2, p1, p2
 
     @staticmethod
-    def backward(ctx, drecon, dedge, dpred, _dmask, dlat1, dlat2):
+    def backward(ctx, drecon, dedge, dpred, _dmask, dlat1, dlat2, dp1, dp2):
         module, pl1, pl2 = ctx.module, ctx.pl1, ctx.pl2
         if (pl1.step_id, pl2.step_id) != ctx.ids:
             raise VitaeError("backward() after a later forward() of the same shape: the activation workspace was reused")
+        eng = module._engine
+        acc = module._accumulating()
+        eng.use_graphs = module.use_cuda_graph
+        for pl, dp, which in ((pl1, dp1, 0), (pl2, dp2, 1)):
+            if dp is None:
+                continue
+            g = eng.predictor_backward(pl, dp, accumulate=acc)
+            acc = True
+            if which == 0:
+                dlat1 = g if dlat1 is None else dlat1 + g
+            else:
+                dlat2 = g if dlat2 is None else dlat2 + g
+        if not acc:                       # the predictor took no part in this loss: its gradient is zero, not last step's
+            eng.zero_predictor_grads()
         module._backward(pl1, drecon, dpred, dlatent=dlat1, second=(pl2, dlat2), dedge=dedge if ctx.want_edge else None)
         return None, None, None, None, None, None, None, None
 
@@ -454,9 +479,10 @@ class _ContrastiveStep(torch.autograd.Function):
 class ContrastiveMAEViT(MaskedAutoencoderViT):
     """MAE + contrastive predictor on the encoder tokens of two views -- model/vit_autoenc.py:241-285, the k-fold scripts'
     default ``--model contr_mae_vit_base_patch16`` (k_fold_cross_valid_combined_brats.py:37).  Both encoder passes, the
-    decoder, the loss and all their gradients run in the B200 kernels; the predictor (two small Linear layers around a
-    BatchNorm1d) is ordinary torch modules for now: its parameters are outside the flat buffers, so
-    an optimizer over ``model.parameters()`` takes the reference's torch AdamW/GradScaler path."""
+    decoder, the loss, the predictor (two Linear layers on the tcgen05 GEMM around a fused BatchNorm1d + ReLU kernel,
+    SURVEY row f-2) and all their gradients run in the B200 kernels.  ``self.predictor`` is a parameter / buffer container
+    with the reference's state_dict keys; its parameters live in the engine's flat buffers like every other one, so an
+    optimizer over ``model.parameters()`` takes the fused AdamW path."""
 
     def __init__(self, volume_size=224, patch_size=16, in_chans=3, embed_dim=1024, depth=24, num_heads=16,
                  decoder_embed_dim=512, decoder_depth=8, decoder_num_heads=16, mlp_ratio=4., norm_layer=nn.LayerNorm,
@@ -475,13 +501,15 @@ class ContrastiveMAEViT(MaskedAutoencoderViT):
         self.predictor = nn.Sequential(nn.Linear(D, D, bias=False), nn.BatchNorm1d(D), nn.ReLU(inplace=True), nn.Linear(D, D))
 
     def _extra_modules(self):
-        return [self.predictor] + ([self.projection_head] if self.use_proj else [])
+        return [self.projection_head] if self.use_proj else []
 
     def _broadcast_extra_parameters(self):
         from .. import dp
         for m in self._extra_modules():
             for t in list(m.parameters()) + list(m.buffers()):
                 dp.broadcast_flat(t.data)
+        for t in self.predictor.buffers():           # BatchNorm running statistics (its parameters are in the flat buffer)
+            dp.broadcast_flat(t.data)
 
     def _sync_extra_grads(self):
         # the predictor's backward has already run when the engine node's backward is called (it is downstream of the latents)
@@ -494,6 +522,10 @@ class ContrastiveMAEViT(MaskedAutoencoderViT):
     def engine(self):
         eng = super().engine()
         eng.want_latent32 = True       # plans built from now on keep an fp32 copy of the normalised encoder output
+        bn = self.predictor[1]
+        if not bn.track_running_stats or bn.momentum is None:
+            raise VitaeError("the predictor's BatchNorm1d must track running statistics with a fixed momentum (torch defaults)")
+        eng.bn_state = (bn.running_mean, bn.running_var, float(bn.eps), float(bn.momentum))
         return eng
 
     def forward(self, view1, view2, mask_ratio=0.75, edge_map_weight=0, noise=None, noise2=None):
@@ -508,18 +540,23 @@ class ContrastiveMAEViT(MaskedAutoencoderViT):
         if keep < 1:
             raise VitaeError(f"mask_ratio={mask_ratio} keeps no patch")
         want_edge = edge_map_weight != 0 or self.report_edge_loss
+        if not self.training:
+            raise VitaeError("ContrastiveMAEViT runs its predictor's BatchNorm1d with batch statistics (training mode) only; "
+                             "the reference never evaluates this model in eval mode")
         if torch.is_grad_enabled() and self.cls_token.requires_grad:
-            recon, raw_edge, pred, mask, lat1, lat2 = _ContrastiveStep.apply(self.cls_token, self, x1, x2, n1, n2, keep,
-                                                                             want_edge)
+            recon, raw_edge, pred, mask, lat1, lat2, p1, p2 = _ContrastiveStep.apply(self.cls_token, self, x1, x2, n1, n2, keep,
+                                                                                     want_edge)
         else:
-            pl1 = eng.forward(x1, n1, keep, want_loss=True, pred_f32=self.pred_dtype == torch.float32, want_edge=want_edge)
-            pl2 = eng.forward_encoder_only(x2, n2, keep, slot=1)
+            pl1 = eng.forward(x1, n1, keep, want_loss=True, pred_f32=self.pred_dtype == torch.float32, want_edge=want_edge,
+                              with_predictor=True)
+            pl2 = eng.forward_encoder_only(x2, n2, keep, slot=1, with_predictor=True)
             pl1.step_id += 1
             pl2.step_id += 1
             recon, pred, mask = pl1.loss_out[0].clone(), pl1.pred_view(self.pred_dtype), pl1.mask.clone()
             raw_edge = pl1.edge_out[0].clone() if want_edge else None
             lat1, lat2 = pl1.latent32.clone(), pl2.latent32.clone()
-        p1, p2 = self.predictor(lat1), self.predictor(lat2)
+            p1, p2 = pl1.pb.p.clone(), pl2.pb.p.clone()
+        self.predictor[1].num_batches_tracked.add_(2)        # two BatchNorm forward calls per step (vit_autoenc.py:282-283)
         return (self._loss_list(recon, raw_edge if want_edge else None, edge_map_weight), pred, mask, p1, p2, lat1.detach(),
                 lat2.detach())
 

@@ -507,3 +507,39 @@ def ingest_normalize(raw, out, mode: str, workspace, stats=None) -> None:
     check(_lib.load().vitae_ingest_normalize(raw.data_ptr(), RAW_TYPES[raw.dtype], out.data_ptr(), B, C, vox,
                                              INGEST_MODES[mode], workspace.data_ptr(), _ptr(stats), _stream()),
           "vitae_ingest_normalize")
+
+
+def bn_relu_fwd(h, gamma, beta, eps: float, act_bf16, mean, rstd, running_mean=None, running_var=None,
+                momentum: float = 0.1) -> None:
+    _req(h, _F32, "bn h"); _req(act_bf16, _BF16, "bn act")
+    M, D = h.shape
+    check(_lib.load().vitae_bn_relu_fwd(h.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, act_bf16.data_ptr(), mean.data_ptr(),
+                                        rstd.data_ptr(), _ptr(running_mean), _ptr(running_var), momentum, M, D, _stream()),
+          "vitae_bn_relu_fwd")
+
+
+def bn_relu_bwd(dact_bf16, h, gamma, beta, mean, rstd, dh_bf16, dgamma, dbeta, accumulate: bool = False) -> None:
+    _req(dact_bf16, _BF16, "bn dact"); _req(dh_bf16, _BF16, "bn dh")
+    M, D = h.shape
+    check(_lib.load().vitae_bn_relu_bwd(dact_bf16.data_ptr(), h.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(),
+                                        rstd.data_ptr(), dh_bf16.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), int(accumulate),
+                                        M, D, _stream()), "vitae_bn_relu_bwd")
+
+
+def cosine_loss_workspace_floats(M: int) -> int:
+    return _lib.load().vitae_cosine_loss_workspace_floats(M)
+
+
+def cosine_loss_fwd(p1, z2, p2, z1, weight: float, workspace, loss) -> None:
+    for t in (p1, z2, p2, z1):
+        _req(t, _F32, "cosine operand")
+    M, D = p1.shape
+    check(_lib.load().vitae_cosine_loss_fwd(p1.data_ptr(), z2.data_ptr(), p2.data_ptr(), z1.data_ptr(), M, D, weight,
+                                            workspace.data_ptr(), loss.data_ptr(), _stream()), "vitae_cosine_loss_fwd")
+
+
+def cosine_loss_bwd(p1, z2, p2, z1, weight: float, workspace, upstream, dp1, dp2) -> None:
+    M, D = p1.shape
+    check(_lib.load().vitae_cosine_loss_bwd(p1.data_ptr(), z2.data_ptr(), p2.data_ptr(), z1.data_ptr(), M, D, weight,
+                                            workspace.data_ptr(), upstream.data_ptr(), dp1.data_ptr(), dp2.data_ptr(), _stream()),
+          "vitae_cosine_loss_bwd")

@@ -31,8 +31,37 @@ from . import lr_sched, misc
 PRINT_FREQ = 20
 
 
+class _CosinePairLoss(torch.autograd.Function):
+    """contr_weight * -(cos(p1, z2).mean() + cos(p2, z1).mean()) / 2 in two launches forward and one backward
+    (vitae_cosine_loss_fwd / _bwd, csrc/predictor.cu); z1 / z2 are detached by the model (vit_autoenc.py:285)."""
+
+    @staticmethod
+    def forward(ctx, p1, p2, z1, z2, weight):
+        from .. import ops
+        p1, p2, z1, z2 = (t.detach().float().contiguous() for t in (p1, p2, z1, z2))
+        ws = torch.empty(ops.cosine_loss_workspace_floats(p1.shape[0]), dtype=torch.float32, device=p1.device)
+        loss = torch.empty(1, dtype=torch.float32, device=p1.device)
+        ops.cosine_loss_fwd(p1, z2, p2, z1, float(weight), ws, loss)
+        ctx.save_for_backward(p1, p2, z1, z2, ws)
+        ctx.weight = float(weight)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        from .. import ops
+        p1, p2, z1, z2, ws = ctx.saved_tensors
+        dp1, dp2 = torch.empty_like(p1), torch.empty_like(p2)
+        ops.cosine_loss_bwd(p1, z2, p2, z1, ctx.weight, ws, dloss.detach().float().reshape(1).contiguous(), dp1, dp2)
+        return dp1, dp2, None, None, None
+
+
 def compute_contrastive_loss(args, criterion, p1, p2, z1, z2):
-    """-(cos(p1, z2) + cos(p2, z1)) / 2 scaled by ``args.contr_weight`` (reference :113-114)."""
+    """-(cos(p1, z2) + cos(p2, z1)) / 2 scaled by ``args.contr_weight`` (reference :113-114).  With the reference's
+    criterion (``nn.CosineSimilarity(dim=1)``, :32) on CUDA rows the fused kernels compute it; anything else is evaluated
+    with the criterion as given."""
+    if (p1.is_cuda and p1.dim() == 2 and type(criterion) is torch.nn.CosineSimilarity and criterion.dim == 1
+            and criterion.eps == 1e-8 and not z1.requires_grad and not z2.requires_grad):
+        return _CosinePairLoss.apply(p1, p2, z1, z2, args.contr_weight)
     return args.contr_weight * (-(criterion(p1, z2).mean() + criterion(p2, z1).mean()) * 0.5)
 
 

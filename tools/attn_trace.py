@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from vit_ae_plus_plus_b200 import _lib, ops  # noqa: E402
 
-NAMES = ["entry", "setup", "q_landed", "p1_issued", "p1_done", "pv_issued", "p2_done", "o_ready", "done"]
+NAMES = ["entry", "setup", "q_landed", "s_ready|p1_issued", "p1_done", "pv_issued", "p2_done", "o_ready", "done"]
 
 
 def main():
@@ -27,7 +27,7 @@ def main():
     lib.vitae_debug_set_attn_trace.argtypes = [ctypes.c_void_p]
     assert lib.vitae_debug_set_attn_trace(trace_all.data_ptr()) == 0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for B, N, H, hd in [(4, 513, 16, 32), (4, 512, 16, 32), (2, 512, 16, 32), (1, 512, 16, 32), (4, 129, 12, 64), (4, 128, 12, 64)]:
+    for B, N, H, hd in [(4, 513, 16, 32), (4, 512, 16, 32), (2, 512, 16, 32), (1, 512, 16, 32), (4, 129, 12, 64), (16, 217, 16, 32)]:
         D = H * hd
         qkv = torch.randn(B, N, 3 * D, device=dev).bfloat16()
         out = torch.empty(B, N, D, device=dev, dtype=torch.bfloat16)

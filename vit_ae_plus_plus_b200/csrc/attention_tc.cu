@@ -653,6 +653,344 @@ attn_fwd_tc8_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __
     if (warp == 2) tmem_dealloc(tmem_base, S::TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------------ forward, resident
+// Third forward layout (default for N <= 520): ALL scores of a 128-row query tile stay in tensor memory.  Why: the event log
+// of the layouts above (profiles/r02e_attention_event_log.txt) shows that every operation of the single issuing thread --
+// tcgen05.mma, tcgen05.commit, an mbarrier wait that passes at once -- costs 100-200 cycles, so a kernel that hands
+// 64-column tiles back and forth between the MMA thread and the softmax warps spends ~1000 cycles of MMA-thread time per
+// tile.  Here the MMA thread issues the whole S = Q K^T with N = 256 keys per instruction, once, and then only the P V
+// products (K = 16 per instruction: N / 16 of them, the minimum).  Both softmax passes read the scores from TMEM (no
+// recompute, no K reload); every P tile has a buffer of its own (no reuse, no back-pressure); O accumulates in the columns
+// of the first score tile once that tile has been consumed; V tiles land in the K tiles' slots.
+//   BIG   (N <= 512 + 8): 512 TMEM columns, one CTA per SM, 16 softmax warps (4 per lane quadrant, 32-column slices)
+//   SMALL (N <= 256 + 8): 256 TMEM columns, two CTAs per SM, 8 softmax warps (2 per lane quadrant, 64-column slices)
+// Key columns past the tensor-core part (N = 513 = 512 patches + cls: ONE column) are evaluated on the CUDA cores by the
+// row's first slice instead of costing a 128 x 16 MMA tile and a barrier round trip.
+constexpr int ATR_MAX_TAIL_COLS = 8;
+template <bool BIG>
+struct ResSmem {
+    static constexpr int TILES = BIG ? 4 : 2;                      // 128-key tiles
+    static constexpr int SLICES = BIG ? 4 : 2;                     // softmax warps per TMEM lane quadrant
+    static constexpr int SOFT = SLICES * 128;                      // softmax threads
+    static constexpr int THREADS = 64 + SOFT;
+    static constexpr uint32_t TMEM_COLS = BIG ? 512 : 256;
+    static constexpr uint32_t Q = 0;                               // dead once the score MMAs have completed ...
+    static constexpr uint32_t P = 0;                               // ... so the first P atom lives there; per tile two K-major atoms
+    static constexpr uint32_t KV = P + TILES * 2 * ROWT_BYTES;     // K tiles first, V tiles afterwards
+    static constexpr uint32_t RED = KV + TILES * ROWT_BYTES;       // float [SLICES][128]: partial row maxima, then sums
+    static constexpr uint32_t TAILP = RED + SLICES * 128 * 4;      // float [8][128]: p of the key columns past the MMA part
+    static constexpr uint32_t BAR = TAILP + ATR_MAX_TAIL_COLS * 128 * 4;
+    // barriers: qk_full, s_full, v_full[4], p_full[4], o_full
+    static constexpr int NBAR = 11;
+    static constexpr uint32_t TOTAL = BAR + NBAR * 8 + 16 + 1024;
+};
+
+// 8 consecutive bf16 (one uint4) times 8 floats
+__device__ __forceinline__ float dot8(const uint4& a, const float* q) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        s = fmaf(f.x, q[2 * i], s);
+        s = fmaf(f.y, q[2 * i + 1], s);
+    }
+    return s;
+}
+__device__ __forceinline__ void unpack8(const uint4& a, float* out) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        out[2 * i] = f.x;
+        out[2 * i + 1] = f.y;
+    }
+}
+
+template <int HD, bool BIG>
+__global__ void __launch_bounds__(ResSmem<BIG>::THREADS, BIG ? 1 : 2)
+attn_fwd_res_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                    float* __restrict__ lse, int N, int H, int B, float scale_log2) {
+    using S = ResSmem<BIG>;
+    constexpr int SLICES = S::SLICES;
+    constexpr int CS = 128 / SLICES;                  // columns of a tile per slice (32 or 64)
+    constexpr int NCH = CS / 16;                      // 16-column chunks per slice and tile
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw_u32);
+    const uint32_t qk_full = base + S::BAR, s_full = qk_full + 8, v_full = s_full + 8, p_full = v_full + 32, o_full = p_full + 32;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + S::BAR + S::NBAR * 8);
+    float* s_red = reinterpret_cast<float*>(sm + S::RED);
+    float* s_tailp = reinterpret_cast<float*>(sm + S::TAILP);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Warp roles: softmax warps first, TMA producer and MMA issuer LAST -- the warp scheduler prefers the highest warp id of
+    // a sub-partition, and as warps 0 / 1 the two single-thread roles were starved by the softmax warps they feed (every
+    // tcgen05.mma / commit / barrier wait took ~200 cycles; profiles/r02e_attention_event_log.txt).
+    constexpr int PROD_WARP = S::SOFT / 32, MMA_WARP = S::SOFT / 32 + 1;
+    const int pairs = H * B;                          // tile-major: ragged last query tiles are scheduled last
+    const int pair = blockIdx.x % pairs, qt = blockIdx.x / pairs;
+    const int h = pair % H, b = pair / H, q0 = qt * QT;
+    const int D = H * HD;
+    const int NM = min(N, S::TILES * 128);            // key columns on the tensor cores
+    const int NT = N - NM;                            // key columns past them: CUDA cores (<= ATR_MAX_TAIL_COLS)
+    const int n16M = (NM + 15) & ~15;
+    const int T = ceil_div(NM, 128);                  // 128-column P / V tiles
+    const int qcol = h * HD, kcol = D + h * HD, vcol = 2 * D + h * HD;
+    const size_t pitch = static_cast<size_t>(3) * D;
+    const __nv_bfloat16* qkv_b = qkv + static_cast<size_t>(b) * N * pitch;
+
+    if (threadIdx.x == 0) AT_STAMP(0);
+    if (warp == PROD_WARP && lane == 0) tma_prefetch_desc(&tmQKV);
+    if (warp == MMA_WARP && lane == 0) {
+        mbar_init(qk_full, 1);
+        mbar_init(s_full, 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(v_full + i * 8, 1); mbar_init(p_full + i * 8, S::SOFT); }
+        mbar_init(o_full, ceil_div(min(N, S::TILES * 128), 128) > 2 ? 2 : 1);      // one arrival per P V issuer (below)
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 0) {
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), S::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    PDL_TRIGGER_EARLY();
+    pdl_wait();
+    if (threadIdx.x == 0) {
+        AT_STAMP(1);
+        unsigned smid__;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid__));
+        AT_PUT(9, smid__);
+    }
+
+    // O (+)= P_t V_t for tiles [t0, t1) into the accumulator at `acc`: K = 16 keys per instruction, the minimum count; the
+    // descriptors of a tile differ only in their 14-bit start-address field, so they are formed by one add each
+    auto issue_pv = [&](int t0, int t1, uint32_t acc) {
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(QT, 64, 0u, 1u);
+        for (int t = t0; t < t1; ++t) {
+            mbar_wait(v_full + t * 8, 0);
+            mbar_wait(p_full + t * 8, 0);
+            tc_fence_after();
+            const int nk = min(128, n16M - 128 * t) / 16;
+            const uint64_t dp = desc_kmajor(base + S::P + t * 2 * ROWT_BYTES, 0, 0);
+            const uint64_t dv = desc_mnmajor(base + S::KV + t * ROWT_BYTES, 0);
+            if (nk == 8) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    umma_bf16(acc, dp + (((kk >> 2) * ROWT_BYTES + (kk & 3) * 32) >> 4), dv + ((kk * 2048) >> 4), idesc_pv,
+                              (t != t0 || kk != 0) ? 1u : 0u);
+            } else {
+#pragma unroll 1
+                for (int kk = 0; kk < nk; ++kk)
+                    umma_bf16(acc, dp + (((kk >> 2) * ROWT_BYTES + (kk & 3) * 32) >> 4), dv + ((kk * 2048) >> 4), idesc_pv,
+                              (t != t0 || kk != 0) ? 1u : 0u);
+            }
+        }
+    };
+
+    if (warp == PROD_WARP) {
+        // ---------------------------------------------------------------- TMA producer: Q and every K tile, later every V tile
+        if (lane == 0) {
+            mbar_arrive_expect_tx(qk_full, (1 + T) * ROWT_BYTES);
+            tma_load_3d(base + S::Q, &tmQKV, qk_full, qcol & ~63, q0, b);
+            for (int t = 0; t < T; ++t) tma_load_3d(base + S::KV + t * ROWT_BYTES, &tmQKV, qk_full, kcol & ~63, t * 128, b);
+            mbar_wait(s_full, 0);                     // the score MMAs have read K: its tiles become the V tiles
+            for (int t = 0; t < T; ++t) {
+                mbar_arrive_expect_tx(v_full + t * 8, ROWT_BYTES);
+                tma_load_3d(base + S::KV + t * ROWT_BYTES, &tmQKV, v_full + t * 8, vcol & ~63, t * 128, b);
+            }
+            // its loads are out: this thread becomes the second P V issuer (tiles 2, 3 into a second accumulator)
+            if (T > 2) {
+                issue_pv(2, T, tmem_base + 64);
+                umma_commit(o_full);
+            }
+        }
+        __syncwarp();
+    } else if (warp == MMA_WARP) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            const uint32_t subq = (qcol & 63) * 2, subk = (kcol & 63) * 2;
+            mbar_wait(qk_full, 0);
+            AT_STAMP(2);
+            tc_fence_after();
+            for (int j = 0; j * 256 < NM; ++j) {      // S[:, 256 j ...] = Q K^T, up to 256 keys per instruction
+                const uint32_t idesc = umma_idesc_bf16(QT, min(256, n16M - 256 * j), 0u, 0u);
+#pragma unroll
+                for (int kk = 0; kk < HD / 16; ++kk)
+                    umma_bf16(tmem_base + 256 * j, desc_kmajor(base + S::Q, subq, kk),
+                              desc_kmajor(base + S::KV + j * 2 * ROWT_BYTES, subk, kk), idesc, kk != 0);
+            }
+            umma_commit(s_full);
+            issue_pv(0, min(T, 2), tmem_base);        // O += P_t V_t, O in the columns of the (consumed) first score tile
+            umma_commit(o_full);
+            AT_STAMP(5);
+            PDL_TRIGGER_LATE();
+        }
+        __syncwarp();
+    } else {
+        // ---------------------------------------------------------------- softmax: thread = (row, CS-column slice of each tile)
+        const int q = warp & 3;
+        const int slice = warp >> 2;
+        const int row = q * 32 + lane;
+        const int grow = q0 + row;
+        const bool warp_valid = q0 + q * 32 < N;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        float mraw = -INFINITY;
+        float s_tail[ATR_MAX_TAIL_COLS];
+        mbar_wait(s_full, 0);
+        if (threadIdx.x == 32) AT_STAMP(3);
+        tc_fence_after();
+        if (NT > 0 && slice == 0 && warp_valid) {     // scores of the key columns past the MMA part: q_row . k_j
+            float qv[HD];
+            const int chunk0 = (qcol & 63) >> 3;
+#pragma unroll
+            for (int c = 0; c < HD / 8; ++c)
+                unpack8(*reinterpret_cast<const uint4*>(sm + S::Q + at_swz(row, chunk0 + c)), qv + 8 * c);
+#pragma unroll
+            for (int j = 0; j < ATR_MAX_TAIL_COLS; ++j) {
+                s_tail[j] = 0.f;
+                if (j < NT) {
+                    const uint4* kr = reinterpret_cast<const uint4*>(qkv_b + static_cast<size_t>(NM + j) * pitch + kcol);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int c = 0; c < HD / 8; ++c) acc += dot8(__ldg(kr + c), qv + 8 * c);
+                    s_tail[j] = acc;
+                    mraw = fmaxf(mraw, acc);
+                }
+            }
+        }
+        for (int t = 0; t < T; ++t) {                 // pass 1: row maxima
+            const int col0 = t * 128 + slice * CS;
+            if (!warp_valid || col0 >= n16M) continue;
+            const int nch = min(NCH, (n16M - col0) / 16);
+#pragma unroll
+            for (int c2 = 0; c2 < NCH; c2 += 2) {     // two chunks (32 score registers) at a time
+                uint32_t v[2][16];
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    if (c2 + c < nch) tmem_ld_32x16(t_lane + col0 + (c2 + c) * 16, v[c]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (c2 + c >= nch) continue;
+                    const int cb = col0 + (c2 + c) * 16;
+                    if (cb + 16 > NM) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (cb + j < NM) mraw = fmaxf(mraw, __uint_as_float(v[c][j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2)
+                            mraw = fmax3(mraw, __uint_as_float(v[c][j]), __uint_as_float(v[c][j + 1]));
+                    }
+                }
+            }
+        }
+        s_red[slice * 128 + row] = mraw;
+        named_bar_sync(1, S::SOFT);
+        if (threadIdx.x == 32) AT_STAMP(4);
+#pragma unroll
+        for (int i = 0; i < SLICES; ++i) mraw = fmaxf(mraw, s_red[i * 128 + row]);
+        const float msc = mraw * scale_log2;
+        float l = 0.f;
+        for (int t = 0; t < T; ++t) {                 // pass 2: p = 2^(s * scale_log2 - msc), P tile t -> its own buffer
+            const int col0 = t * 128 + slice * CS;
+            if (warp_valid && col0 < n16M) {
+                const int nch = min(NCH, (n16M - col0) / 16);
+                const uint32_t sp = base + S::P + t * 2 * ROWT_BYTES + ((slice * CS) >> 6) * ROWT_BYTES;
+                const int ch0 = ((slice * CS) & 63) >> 3;                   // first 16-byte chunk of this slice in its atom
+#pragma unroll
+                for (int c2 = 0; c2 < NCH; c2 += 2) {
+                    uint32_t v[2][16];
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        if (c2 + c < nch) tmem_ld_32x16(t_lane + col0 + (c2 + c) * 16, v[c]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        if (c2 + c >= nch) continue;
+                        const int cb = col0 + (c2 + c) * 16;
+                        float p[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            p[j] = ex2_approx(fmaf(__uint_as_float(v[c][j]), scale_log2, -msc));
+                            if (cb + j >= NM) p[j] = 0.f;
+                            l += p[j];
+                        }
+                        const int ch = ch0 + 2 * (c2 + c);
+                        at_sts128(sp + at_swz(row, ch), pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]),
+                                  pack_bf16(p[6], p[7]));
+                        at_sts128(sp + at_swz(row, ch + 1), pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]), pack_bf16(p[12], p[13]),
+                                  pack_bf16(p[14], p[15]));
+                    }
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive(p_full + t * 8);
+        }
+        if (NT > 0 && slice == 0 && warp_valid) {
+#pragma unroll
+            for (int j = 0; j < ATR_MAX_TAIL_COLS; ++j)
+                if (j < NT) {
+                    const float p = ex2_approx(fmaf(s_tail[j], scale_log2, -msc));
+                    l += p;
+                    s_tailp[j * 128 + row] = p;
+                }
+        }
+        if (threadIdx.x == 32) AT_STAMP(6);
+        named_bar_sync(1, S::SOFT);                   // every thread has read the maxima: the buffer takes the sums
+        s_red[slice * 128 + row] = l;
+        named_bar_sync(1, S::SOFT);
+        l = 0.f;
+#pragma unroll
+        for (int i = 0; i < SLICES; ++i) l += s_red[i * 128 + row];
+        mbar_wait(o_full, 0);
+        if (threadIdx.x == 32) AT_STAMP(7);
+        tc_fence_after();
+        for (int ch = slice; ch < HD / 16; ch += SLICES) {        // 16-column chunks of this head's O, dealt to the slices
+            if (!warp_valid) break;
+            uint32_t o[16], o2[16];
+            tmem_ld_32x16(t_lane + (vcol & 63) + ch * 16, o);
+            if (T > 2) tmem_ld_32x16(t_lane + 64 + (vcol & 63) + ch * 16, o2);     // tiles 2, 3 accumulated separately
+            tmem_ld_wait();
+            if (grow < N) {
+                float of[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) of[j] = __uint_as_float(o[j]) + (T > 2 ? __uint_as_float(o2[j]) : 0.f);
+                for (int j = 0; j < NT; ++j) {        // + p_j v_j of the key columns past the MMA part
+                    const float p = s_tailp[j * 128 + row];
+                    const uint4* vr = reinterpret_cast<const uint4*>(qkv_b + static_cast<size_t>(NM + j) * pitch + vcol + ch * 16);
+                    float vv[16];
+                    unpack8(__ldg(vr), vv);
+                    unpack8(__ldg(vr + 1), vv + 8);
+#pragma unroll
+                    for (int d = 0; d < 16; ++d) of[d] = fmaf(p, vv[d], of[d]);
+                }
+                const float inv = 1.f / l;
+                __nv_bfloat16* orow = out + (static_cast<size_t>(b) * N + grow) * D + h * HD + ch * 16;
+                uint4 lo, hi;
+                lo.x = pack_bf16(of[0] * inv, of[1] * inv); lo.y = pack_bf16(of[2] * inv, of[3] * inv);
+                lo.z = pack_bf16(of[4] * inv, of[5] * inv); lo.w = pack_bf16(of[6] * inv, of[7] * inv);
+                hi.x = pack_bf16(of[8] * inv, of[9] * inv); hi.y = pack_bf16(of[10] * inv, of[11] * inv);
+                hi.z = pack_bf16(of[12] * inv, of[13] * inv); hi.w = pack_bf16(of[14] * inv, of[15] * inv);
+                *reinterpret_cast<uint4*>(orow) = lo;
+                *reinterpret_cast<uint4*>(orow + 8) = hi;
+            }
+        }
+        if (slice == 0 && grow < N) lse[(static_cast<size_t>(b) * H + h) * N + grow] = (msc + log2f(l)) * LN2_F;
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) AT_STAMP(8);
+    if (warp == 0) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
 // ------------------------------------------------------------------------------------------------------ backward: dQ
 struct DqSmem {
     static constexpr int NSLOT = 4;
@@ -694,11 +1032,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     const int n16_last = (nv_last + 15) & ~15;
     const int qcol = h * HD, kcol = D + h * HD, vcol = 2 * D + h * HD;
 
-    if (warp == 0 && lane == 0) {
+    constexpr int PROD_WARP = 8, MMA_WARP = 9;      // after the eight softmax warps: the scheduler prefers high warp ids
+    if (warp == PROD_WARP && lane == 0) {
         tma_prefetch_desc(&tmQKV);
         tma_prefetch_desc(&tmDO);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == MMA_WARP && lane == 0) {
         mbar_init(qdo_full, 1);
         for (int i = 0; i < S::NSLOT; ++i) { mbar_init(kv_full + i * 8, 1); mbar_init(kv_empty + i * 8, 1); }
         mbar_init(sdp_full, 1);
@@ -709,7 +1048,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         fence_barrier_init();
         fence_proxy_async();
     }
-    if (warp == 2) {
+    if (warp == 0) {
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), S::TMEM_COLS);
         tmem_relinquish();
     }
@@ -720,7 +1059,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     PDL_TRIGGER_EARLY();
     pdl_wait();
 
-    if (warp == 0) {
+    if (warp == PROD_WARP) {
         if (lane == 0) {
             mbar_arrive_expect_tx(qdo_full, 2 * ROWT_BYTES);
             tma_load_3d(base + S::Q, &tmQKV, qdo_full, qcol & ~63, q0, b);
@@ -740,7 +1079,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == MMA_WARP) {
         if (lane == 0) {
             const uint32_t subq = (qcol & 63) * 2, subk = (kcol & 63) * 2, subv = (vcol & 63) * 2;
             constexpr uint32_t idesc_dq = umma_idesc_bf16(QT, 64, 0u, 1u);
@@ -789,7 +1128,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         __syncwarp();
     } else {
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;                    // two warps per TMEM lane quadrant: 32 of a tile's 64 columns each
+        const int half = warp >> 2;                    // two warps per TMEM lane quadrant: 32 of a tile's 64 columns each
         const int row = q * 32 + lane;
         const int grow = q0 + row;
         const bool warp_valid = q0 + q * 32 < N;
@@ -887,7 +1226,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, S::TMEM_COLS);
+    if (warp == 0) tmem_dealloc(tmem_base, S::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------------ backward: dK / dV
@@ -934,11 +1273,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     const int n16_last = (nv_last + 15) & ~15;
     const int qcol = h * HD, kcol = D + h * HD, vcol = 2 * D + h * HD;
 
-    if (warp == 0 && lane == 0) {
+    constexpr int PROD_WARP = 8, MMA_WARP = 9;      // after the eight softmax warps: the scheduler prefers high warp ids
+    if (warp == PROD_WARP && lane == 0) {
         tma_prefetch_desc(&tmQKV);
         tma_prefetch_desc(&tmDO);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == MMA_WARP && lane == 0) {
         mbar_init(kv_full, 1);
         for (int i = 0; i < S::NSLOT; ++i) { mbar_init(r_full + i * 8, 1); mbar_init(r_empty + i * 8, 1); }
         mbar_init(sdp_full, 1);
@@ -949,7 +1289,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         fence_barrier_init();
         fence_proxy_async();
     }
-    if (warp == 2) {
+    if (warp == 0) {
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), S::TMEM_COLS);
         tmem_relinquish();
     }
@@ -960,7 +1300,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     PDL_TRIGGER_EARLY();
     pdl_wait();
 
-    if (warp == 0) {
+    if (warp == PROD_WARP) {
         if (lane == 0) {
             mbar_arrive_expect_tx(kv_full, 2 * ROWT_BYTES);
             tma_load_3d(base + S::K, &tmQKV, kv_full, kcol & ~63, kv0, b);
@@ -980,7 +1320,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == MMA_WARP) {
         if (lane == 0) {
             const uint32_t subq = (qcol & 63) * 2, subk = (kcol & 63) * 2, subv = (vcol & 63) * 2;
             constexpr uint32_t idesc_acc = umma_idesc_bf16(QT, 64, 0u, 1u);
@@ -1033,12 +1373,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         __syncwarp();
     } else {
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;                // two warps per TMEM lane quadrant: 32 of a tile's 64 query columns each
+        const int half = warp >> 2;                // two warps per TMEM lane quadrant: 32 of a tile's 64 query columns each
         const int row = q * 32 + lane;                   // kv row of this thread
         const int grow = kv0 + row;
         const bool warp_valid = kv0 + q * 32 < N;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const int st = threadIdx.x - 64;                 // 0..255 among the softmax threads
+        const int st = threadIdx.x;                      // 0..255: the softmax threads come first
         const float* lrow = lse + (static_cast<size_t>(b) * H + h) * N;
         const float* drow = delta + (static_cast<size_t>(b) * H + h) * N;
         auto stage = [&](int t) {                        // statistics of query tile t -> shared memory (buffer t & 1)
@@ -1133,7 +1473,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, S::TMEM_COLS);
+    if (warp == 0) tmem_dealloc(tmem_base, S::TMEM_COLS);
 }
 
 template <typename Kern>
@@ -1174,6 +1514,25 @@ static int launch_fwd8(const CUtensorMap& tq128, void* out, float* lse, int B, i
                   static_cast<__nv_bfloat16*>(out), lse, N, H, B, sl2);
     VITAE_CHECK_LAUNCH("attention_fwd");
     return 0;
+}
+
+template <int HD, bool BIG>
+static int launch_fwd_res(const CUtensorMap& tq128, const void* qkv, void* out, float* lse, int B, int N, int H, float sl2,
+                          cudaStream_t st) {
+    static bool attr = false;
+    using S = ResSmem<BIG>;
+    if (int rc = set_smem(attn_fwd_res_kernel<HD, BIG>, S::TOTAL, attr)) return rc;
+    launch_kernel(attn_fwd_res_kernel<HD, BIG>, dim3(ceil_div(N, QT) * H * B), dim3(S::THREADS), S::TOTAL, st, tq128,
+                  static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, N, H, B, sl2);
+    VITAE_CHECK_LAUNCH("attention_fwd");
+    return 0;
+}
+
+template <int HD>
+static int dispatch_fwd_res(const CUtensorMap& tq128, const void* qkv, void* out, float* lse, int B, int N, int H, float sl2,
+                            cudaStream_t st) {
+    return N <= 256 + ATR_MAX_TAIL_COLS ? launch_fwd_res<HD, false>(tq128, qkv, out, lse, B, N, H, sl2, st)
+                                        : launch_fwd_res<HD, true>(tq128, qkv, out, lse, B, N, H, sl2, st);
 }
 
 template <int HD>
@@ -1227,7 +1586,14 @@ extern "C" int vitae_attention_fwd(const void* qkv, void* out, float* lse, int B
     cudaStream_t st = as_stream(stream);
     CUtensorMap tq;
     static const bool narrow = [] { const char* e = getenv("VITAE_ATTN_FWD"); return e && e[0] == 'v' && e[1] == '1'; }();
-    if (!narrow) {      // default: 128-column score tiles, eight softmax warps (VITAE_ATTN_FWD=v1 selects the first layout)
+    static const bool streaming = [] { const char* e = getenv("VITAE_ATTN_FWD"); return e && e[0] == 'v' && e[1] == '2'; }();
+    if (!narrow && !streaming && N <= 512 + ATR_MAX_TAIL_COLS) {     // default: all scores resident in TMEM
+        if (int rc = make_tmap(&tq, qkv, 2, 3ull * D, (uint64_t)N, (uint64_t)B, 3ull * D, 64, 128)) return rc;
+        if (hd == 64) return dispatch_fwd_res<64>(tq, qkv, out, lse, B, N, H, sl2, st);
+        if (hd == 32) return dispatch_fwd_res<32>(tq, qkv, out, lse, B, N, H, sl2, st);
+        return dispatch_fwd_res<16>(tq, qkv, out, lse, B, N, H, sl2, st);
+    }
+    if (!narrow) {      // longer sequences (or VITAE_ATTN_FWD=v2): 128-column score tiles streamed through TMEM, eight softmax warps
         if (int rc = make_tmap(&tq, qkv, 2, 3ull * D, (uint64_t)N, (uint64_t)B, 3ull * D, 64, 128)) return rc;
         if (hd == 64) return launch_fwd8<64>(tq, out, lse, B, N, H, sl2, st);
         if (hd == 32) return launch_fwd8<32>(tq, out, lse, B, N, H, sl2, st);

@@ -102,8 +102,15 @@ def _attn_ref(qkv, B, N, H, hd):
     return (att @ v).transpose(1, 2).reshape(B, N, H * hd), att
 
 
-@pytest.mark.parametrize("B,N,H,hd", [(4, 129, 12, 64), (2, 513, 16, 32), (2, 17, 4, 32), (2, 65, 4, 16), (1, 64, 2, 64),
-                                       (3, 55, 16, 64), (1, 217, 16, 32), (1, 1, 1, 32)])
+# encoder / decoder lengths of every BASELINE config (129 / 257 / 385 / 513: ViT-B at mask 0.75 / 0.5 / 0.25 and its decoder;
+# 55 / 217: ViT-L 96^3), the tiny configs, exact tile multiples, a two-row tail, and lengths past the score-resident
+# forward's 520 tokens (streaming layout)
+ATTN_SHAPES = [(4, 129, 12, 64), (2, 513, 16, 32), (2, 17, 4, 32), (2, 65, 4, 16), (1, 64, 2, 64), (3, 55, 16, 64),
+               (1, 217, 16, 32), (1, 1, 1, 32), (1, 385, 12, 64), (1, 257, 12, 64), (2, 128, 3, 64), (2, 130, 2, 32),
+               (1, 520, 2, 32), (1, 650, 2, 64), (1, 1025, 1, 32)]
+
+
+@pytest.mark.parametrize("B,N,H,hd", ATTN_SHAPES)
 def test_attention_fwd_bwd(B, N, H, hd):
     from vit_ae_plus_plus_b200 import ops
     g = torch.Generator(device=DEV).manual_seed(N * 7 + hd)
@@ -132,6 +139,21 @@ def test_attention_fwd_bwd(B, N, H, hd):
             assert (got[:, :, i] - gref[:, :, i]).abs().max().item() < 1e-5 + 2e-2 * gref[:, :, i].abs().max().item(), name
         else:
             assert _rel(got[:, :, i], gref[:, :, i]) < 2e-2, name
+
+
+@pytest.mark.parametrize("env", [{"VITAE_ATTN_LIGHT_TAILS": "1"}, {"VITAE_ATTN_FWD": "v2"}, {"VITAE_ATTN_FWD": "v1"},
+                                 {"VITAE_ATTN_FWD": "v1", "VITAE_ATTN_FWD_CFG": "0"}, {"VITAE_ATTN_LEGACY": "1"}])
+def test_attention_alternative_layouts(env):
+    """The opt-in variants of the attention kernels (read once per process from the environment: ragged last rows as light
+    CUDA-core CTAs, the streaming forward layouts, the round-1 mma.sync kernels) pass the same shape sweep in a fresh process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_kernels_gpu.py"), "-m", "gpu", "-q", "-x",
+                        "-k", "test_attention_fwd_bwd"], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900,
+                       cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 # ------------------------------------------------------------------------------------------------ masking

@@ -707,10 +707,194 @@ __device__ __forceinline__ void unpack8(const uint4& a, float* out) {
     }
 }
 
+// ---- ragged last rows on the CUDA cores.  Every sequence of this model is 128 k + 1 tokens long (patches + cls), so a
+// 128-row tiling leaves ONE row per head; as a tensor-core tile it costs a whole CTA slot for the full CTA duration (the
+// per-thread latency chain does not shrink with the row count) and turns the decoder's 256-CTA grids into 320 CTAs = one
+// wave more.  Instead the last `pairs` CTAs of each grid are "light": no TMEM, no TMA, no MMA -- all threads of the CTA
+// share the row's N dot products (thread t: items t and t + NTHR), block-wide reductions through shared memory.  Scheduled
+// last (tile-major block order), they fill the slots the last wave of full tiles leaves free.  N % 128 <= ATR_MAX_TAIL_ROWS.
+constexpr int ATR_MAX_TAIL_ROWS = 2;
+
+struct TailScratch {
+    float red[64];            // two block reductions of up to 32 warps
+    float vec[20 * 64];       // per-warp partial vectors (<= 20 warps x 64 columns)
+};
+
+template <int NTHR>
+__device__ __forceinline__ float block_allreduce(float v, bool is_max, float* scr, int tid) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmaxf(v, w) : v + w;
+    }
+    if ((tid & 31) == 0) scr[tid >> 5] = v;
+    __syncthreads();
+    float r = scr[0];
+#pragma unroll
+    for (int w = 1; w < NTHR / 32; ++w) r = is_max ? fmaxf(r, scr[w]) : r + scr[w];
+    return r;
+}
+
+// sum over the block of HD values per thread -> thread d < HD returns component d (others 0)
+template <int HD, int NTHR>
+__device__ __forceinline__ float block_vecsum(float (&v)[HD], float* vec, int tid) {
+#pragma unroll
+    for (int d = 0; d < HD; ++d) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[d] += __shfl_xor_sync(0xffffffffu, v[d], o);
+    }
+    __syncthreads();                      // previous readers of vec are done
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int d = 0; d < HD; ++d) vec[(tid >> 5) * HD + d] = v[d];
+    }
+    __syncthreads();
+    float r = 0.f;
+    if (tid < HD) {
+#pragma unroll
+        for (int w = 0; w < NTHR / 32; ++w) r += vec[w * HD + tid];
+    }
+    return r;
+}
+
+// dot product of two bf16 rows of HD elements (16-byte aligned)
+template <int HD>
+__device__ __forceinline__ float row_dot(const __nv_bfloat16* a, const __nv_bfloat16* b) {
+    const uint4* pa = reinterpret_cast<const uint4*>(a);
+    const uint4* pb = reinterpret_cast<const uint4*>(b);
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+        float x[8];
+        unpack8(__ldg(pa + c), x);
+        acc += dot8(__ldg(pb + c), x);
+    }
+    return acc;
+}
+// acc[0..HD) += w * row
+template <int HD>
+__device__ __forceinline__ void row_axpy(float (&acc)[HD], float w, const __nv_bfloat16* row) {
+    const uint4* pr = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+        float x[8];
+        unpack8(__ldg(pr + c), x);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[8 * c + e] = fmaf(w, x[e], acc[8 * c + e]);
+    }
+}
+
+// forward of query row gi: out row and lse
+template <int HD, int NTHR>
+__device__ __noinline__ void tail_row_fwd(const __nv_bfloat16* __restrict__ qkv_b, size_t pitch, int qcol, int kcol, int vcol, int gi,
+                                          int N, float scale_log2, __nv_bfloat16* __restrict__ orow, float* __restrict__ lse_out) {
+    __shared__ TailScratch ts;
+    const int tid = threadIdx.x;
+    const __nv_bfloat16* qr = qkv_b + static_cast<size_t>(gi) * pitch + qcol;
+    float sc[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int j = tid + k * NTHR;
+        sc[k] = j < N ? row_dot<HD>(qr, qkv_b + static_cast<size_t>(j) * pitch + kcol) : -INFINITY;
+    }
+    const float msc = block_allreduce<NTHR>(fmaxf(sc[0], sc[1]), true, ts.red, tid) * scale_log2;
+    float ov[HD], psum = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) ov[d] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int j = tid + k * NTHR;
+        if (j < N) {
+            const float p = ex2_approx(fmaf(sc[k], scale_log2, -msc));
+            psum += p;
+            row_axpy<HD>(ov, p, qkv_b + static_cast<size_t>(j) * pitch + vcol);
+        }
+    }
+    const float l = block_allreduce<NTHR>(psum, false, ts.red + 32, tid);
+    const float od = block_vecsum<HD, NTHR>(ov, ts.vec, tid);
+    if (tid < HD) orow[tid] = __float2bfloat16(od / l);
+    if (tid == 0) *lse_out = (msc + log2f(l)) * LN2_F;
+    __syncthreads();
+}
+
+// dQ of query row gi (and its delta)
+template <int HD, int NTHR>
+__device__ __noinline__ void tail_row_dq(const __nv_bfloat16* __restrict__ qkv_b, size_t pitch, int qcol, int kcol, int vcol,
+                                         const __nv_bfloat16* __restrict__ orow, const __nv_bfloat16* __restrict__ dorow, float lse_i,
+                                         int gi, int N, float scale, float scale_log2, __nv_bfloat16* __restrict__ dqrow,
+                                         float* __restrict__ delta_out) {
+    __shared__ TailScratch ts;
+    const int tid = threadIdx.x;
+    const __nv_bfloat16* qr = qkv_b + static_cast<size_t>(gi) * pitch + qcol;
+    const float dl = row_dot<HD>(orow, dorow);
+    const float lse2 = lse_i * LOG2E_F;
+    float acc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int j = tid + k * NTHR;
+        if (j < N) {
+            const __nv_bfloat16* kr = qkv_b + static_cast<size_t>(j) * pitch + kcol;
+            const float p = ex2_approx(fmaf(row_dot<HD>(qr, kr), scale_log2, -lse2));
+            const float ds = p * (row_dot<HD>(dorow, qkv_b + static_cast<size_t>(j) * pitch + vcol) - dl);
+            row_axpy<HD>(acc, ds, kr);
+        }
+    }
+    const float r = block_vecsum<HD, NTHR>(acc, ts.vec, tid);
+    if (tid < HD) dqrow[tid] = __float2bfloat16(r * scale);
+    if (tid == 0) *delta_out = dl;
+    __syncthreads();
+}
+
+// dK and dV of key row gj
+template <int HD, int NTHR>
+__device__ __noinline__ void tail_row_dkv(const __nv_bfloat16* __restrict__ qkv_b, size_t pitch, int qcol, int kcol, int vcol,
+                                          const __nv_bfloat16* __restrict__ dout_b, int D, const float* __restrict__ lrow,
+                                          const float* __restrict__ drow, int gj, int N, float scale, float scale_log2,
+                                          __nv_bfloat16* __restrict__ dkrow, __nv_bfloat16* __restrict__ dvrow, int hcol) {
+    __shared__ TailScratch ts;
+    const int tid = threadIdx.x;
+    const __nv_bfloat16* kr = qkv_b + static_cast<size_t>(gj) * pitch + kcol;
+    const __nv_bfloat16* vr = qkv_b + static_cast<size_t>(gj) * pitch + vcol;
+    float pk[2], dsk[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int i = tid + k * NTHR;
+        pk[k] = dsk[k] = 0.f;
+        if (i < N) {
+            const __nv_bfloat16* qi = qkv_b + static_cast<size_t>(i) * pitch + qcol;
+            const __nv_bfloat16* doi = dout_b + static_cast<size_t>(i) * D + hcol;
+            pk[k] = ex2_approx(fmaf(row_dot<HD>(qi, kr), scale_log2, -lrow[i] * LOG2E_F));
+            dsk[k] = pk[k] * (row_dot<HD>(doi, vr) - drow[i]);
+        }
+    }
+    float acc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int i = tid + k * NTHR;
+        if (i < N) row_axpy<HD>(acc, pk[k], dout_b + static_cast<size_t>(i) * D + hcol);
+    }
+    float r = block_vecsum<HD, NTHR>(acc, ts.vec, tid);
+    if (tid < HD) dvrow[tid] = __float2bfloat16(r);
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int i = tid + k * NTHR;
+        if (i < N) row_axpy<HD>(acc, dsk[k], qkv_b + static_cast<size_t>(i) * pitch + qcol);
+    }
+    r = block_vecsum<HD, NTHR>(acc, ts.vec, tid);
+    if (tid < HD) dkrow[tid] = __float2bfloat16(r * scale);
+    __syncthreads();
+}
+
 template <int HD, bool BIG>
 __global__ void __launch_bounds__(ResSmem<BIG>::THREADS, BIG ? 1 : 2)
 attn_fwd_res_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                    float* __restrict__ lse, int N, int H, int B, float scale_log2) {
+                    float* __restrict__ lse, int N, int H, int B, int tail_rows, float scale_log2) {
     using S = ResSmem<BIG>;
     constexpr int SLICES = S::SLICES;
     constexpr int CS = 128 / SLICES;                  // columns of a tile per slice (32 or 64)
@@ -741,6 +925,14 @@ attn_fwd_res_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfloat
     const size_t pitch = static_cast<size_t>(3) * D;
     const __nv_bfloat16* qkv_b = qkv + static_cast<size_t>(b) * N * pitch;
 
+    if (tail_rows > 0 && q0 + tail_rows == N) {       // a light CTA: the ragged last rows of this head, CUDA cores only
+        pdl_wait();
+        for (int i = 0; i < tail_rows; ++i)
+            tail_row_fwd<HD, S::THREADS>(qkv_b, pitch, qcol, kcol, vcol, q0 + i, N, scale_log2,
+                                         out + (static_cast<size_t>(b) * N + q0 + i) * D + h * HD,
+                                         lse + (static_cast<size_t>(b) * H + h) * N + q0 + i);
+        return;
+    }
     if (threadIdx.x == 0) AT_STAMP(0);
     if (warp == PROD_WARP && lane == 0) tma_prefetch_desc(&tmQKV);
     if (warp == MMA_WARP && lane == 0) {
@@ -1008,9 +1200,9 @@ struct DqSmem {
 template <int HD>
 __global__ void __launch_bounds__(AT8_THREADS, 2)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                      const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                      const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                       const float* __restrict__ lse, float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int N, int H,
-                      int B, float scale, float scale_log2) {
+                      int B, int tail_rows, float scale, float scale_log2) {
     using S = DqSmem;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -1032,6 +1224,18 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     const int n16_last = (nv_last + 15) & ~15;
     const int qcol = h * HD, kcol = D + h * HD, vcol = 2 * D + h * HD;
 
+    if (tail_rows > 0 && q0 + tail_rows == N) {       // a light CTA: the ragged last query rows of this head, CUDA cores only
+        pdl_wait();
+        const size_t pitch = static_cast<size_t>(3) * D;
+        const __nv_bfloat16* qkv_b = qkv + static_cast<size_t>(b) * N * pitch;
+        for (int i = 0; i < tail_rows; ++i) {
+            const size_t r = static_cast<size_t>(b) * N + q0 + i;
+            tail_row_dq<HD, AT8_THREADS>(qkv_b, pitch, qcol, kcol, vcol, out + r * D + h * HD, dout + r * D + h * HD,
+                                         lse[(static_cast<size_t>(b) * H + h) * N + q0 + i], q0 + i, N, scale, scale_log2,
+                                         dqkv + r * pitch + qcol, delta + (static_cast<size_t>(b) * H + h) * N + q0 + i);
+        }
+        return;
+    }
     constexpr int PROD_WARP = 8, MMA_WARP = 9;      // after the eight softmax warps: the scheduler prefers high warp ids
     if (warp == PROD_WARP && lane == 0) {
         tma_prefetch_desc(&tmQKV);
@@ -1248,8 +1452,9 @@ struct DkvSmem {
 template <int HD>
 __global__ void __launch_bounds__(AT8_THREADS, 2)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                       const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int N,
-                       int H, int B, float scale, float scale_log2) {
+                       const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
+                       const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int N, int H, int B, int tail_rows,
+                       float scale, float scale_log2) {
     using S = DkvSmem;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -1273,6 +1478,18 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     const int n16_last = (nv_last + 15) & ~15;
     const int qcol = h * HD, kcol = D + h * HD, vcol = 2 * D + h * HD;
 
+    if (tail_rows > 0 && kv0 + tail_rows == N) {      // a light CTA: the ragged last key rows of this head, CUDA cores only
+        pdl_wait();
+        const size_t pitch = static_cast<size_t>(3) * D;
+        const __nv_bfloat16* qkv_b = qkv + static_cast<size_t>(b) * N * pitch;
+        for (int i = 0; i < tail_rows; ++i) {
+            const size_t r = static_cast<size_t>(b) * N + kv0 + i;
+            tail_row_dkv<HD, AT8_THREADS>(qkv_b, pitch, qcol, kcol, vcol, dout + static_cast<size_t>(b) * N * D, D,
+                                          lse + (static_cast<size_t>(b) * H + h) * N, delta + (static_cast<size_t>(b) * H + h) * N,
+                                          kv0 + i, N, scale, scale_log2, dqkv + r * pitch + kcol, dqkv + r * pitch + vcol, h * HD);
+        }
+        return;
+    }
     constexpr int PROD_WARP = 8, MMA_WARP = 9;      // after the eight softmax warps: the scheduler prefers high warp ids
     if (warp == PROD_WARP && lane == 0) {
         tma_prefetch_desc(&tmQKV);
@@ -1516,14 +1733,27 @@ static int launch_fwd8(const CUtensorMap& tq128, void* out, float* lse, int B, i
     return 0;
 }
 
+// query tiles on the tensor cores and ragged last rows on the CUDA cores for a sequence of N tokens
+// Light tail CTAs are opt-in (VITAE_ATTN_LIGHT_TAILS=1): measured on B200 (profiles/r02j_attention_light_tails.txt) their
+// chain of dependent global loads makes them the longest CTAs of the small encoder grids (N = 129: backward 21 -> 28 us) and
+// buys the decoder grid 4 us of 60; by default a ragged last row is one more (mostly empty) tensor-core tile.
+static void res_tiling(int N, int* q_tiles, int* tail_rows) {
+    static const bool light = [] { const char* e = getenv("VITAE_ATTN_LIGHT_TAILS"); return e && e[0] == '1'; }();
+    const int full = N / QT, r = N % QT;
+    *tail_rows = (light && full > 0 && r > 0 && r <= ATR_MAX_TAIL_ROWS) ? r : 0;
+    *q_tiles = full + ((r > *tail_rows) ? 1 : 0);
+}
+
 template <int HD, bool BIG>
 static int launch_fwd_res(const CUtensorMap& tq128, const void* qkv, void* out, float* lse, int B, int N, int H, float sl2,
                           cudaStream_t st) {
     static bool attr = false;
     using S = ResSmem<BIG>;
     if (int rc = set_smem(attn_fwd_res_kernel<HD, BIG>, S::TOTAL, attr)) return rc;
-    launch_kernel(attn_fwd_res_kernel<HD, BIG>, dim3(ceil_div(N, QT) * H * B), dim3(S::THREADS), S::TOTAL, st, tq128,
-                  static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, N, H, B, sl2);
+    int q_tiles, tail_rows;
+    res_tiling(N, &q_tiles, &tail_rows);
+    launch_kernel(attn_fwd_res_kernel<HD, BIG>, dim3((q_tiles + (tail_rows ? 1 : 0)) * H * B), dim3(S::THREADS), S::TOTAL, st, tq128,
+                  static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, N, H, B, tail_rows, sl2);
     VITAE_CHECK_LAUNCH("attention_fwd");
     return 0;
 }
@@ -1536,18 +1766,21 @@ static int dispatch_fwd_res(const CUtensorMap& tq128, const void* qkv, void* out
 }
 
 template <int HD>
-static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const void* out, const void* dout, const float* lse,
-                      float* delta, void* dqkv, int B, int N, int H, float scale, float sl2, cudaStream_t st) {
+static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const void* qkv, const void* out, const void* dout,
+                      const float* lse, float* delta, void* dqkv, int B, int N, int H, float scale, float sl2, cudaStream_t st) {
     static bool attr_dq = false, attr_dkv = false;
     if (int rc = set_smem(attn_bwd_dq_tc_kernel<HD>, DqSmem::TOTAL, attr_dq)) return rc;
     if (int rc = set_smem(attn_bwd_dkv_tc_kernel<HD>, DkvSmem::TOTAL, attr_dkv)) return rc;
-    const dim3 grid(ceil_div(N, QT) * H * B);
+    int q_tiles, tail_rows;
+    res_tiling(N, &q_tiles, &tail_rows);
+    const dim3 grid((q_tiles + (tail_rows ? 1 : 0)) * H * B);
     launch_kernel(attn_bwd_dq_tc_kernel<HD>, grid, dim3(AT8_THREADS), DqSmem::TOTAL, st, tq, tdo,
-                  static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), lse, delta,
-                  static_cast<__nv_bfloat16*>(dqkv), N, H, B, scale, sl2);
+                  static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
+                  static_cast<const __nv_bfloat16*>(dout), lse, delta, static_cast<__nv_bfloat16*>(dqkv), N, H, B, tail_rows, scale, sl2);
     VITAE_CHECK_LAUNCH("attention_bwd_dq");
-    launch_kernel(attn_bwd_dkv_tc_kernel<HD>, grid, dim3(AT8_THREADS), DkvSmem::TOTAL, st, tq, tdo, lse,
-                  static_cast<const float*>(delta), static_cast<__nv_bfloat16*>(dqkv), N, H, B, scale, sl2);
+    launch_kernel(attn_bwd_dkv_tc_kernel<HD>, grid, dim3(AT8_THREADS), DkvSmem::TOTAL, st, tq, tdo,
+                  static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), lse,
+                  static_cast<const float*>(delta), static_cast<__nv_bfloat16*>(dqkv), N, H, B, tail_rows, scale, sl2);
     VITAE_CHECK_LAUNCH("attention_bwd_dkv");
     return 0;
 }
@@ -1619,7 +1852,7 @@ extern "C" int vitae_attention_bwd(const void* qkv, const void* out, const void*
     if (int rc = make_tmap(&tdo, dout, 2, (uint64_t)D, (uint64_t)N, (uint64_t)B, (uint64_t)D, 64, 64)) return rc;
     const float sl2 = scale * LOG2E_F;
     cudaStream_t st = as_stream(stream);
-    if (hd == 64) return launch_bwd<64>(tq, tdo, out, dout, lse, delta, dqkv, B, N, H, scale, sl2, st);
-    if (hd == 32) return launch_bwd<32>(tq, tdo, out, dout, lse, delta, dqkv, B, N, H, scale, sl2, st);
-    return launch_bwd<16>(tq, tdo, out, dout, lse, delta, dqkv, B, N, H, scale, sl2, st);
+    if (hd == 64) return launch_bwd<64>(tq, tdo, qkv, out, dout, lse, delta, dqkv, B, N, H, scale, sl2, st);
+    if (hd == 32) return launch_bwd<32>(tq, tdo, qkv, out, dout, lse, delta, dqkv, B, N, H, scale, sl2, st);
+    return launch_bwd<16>(tq, tdo, qkv, out, dout, lse, delta, dqkv, B, N, H, scale, sl2, st);
 }

@@ -59,13 +59,14 @@ def allreduce_mean_bucketed_(flat: torch.Tensor, slices: Sequence[Tuple[int, int
 
 
 def exchange_dtype() -> str:
-    """'bf16' (default over NCCL) or 'fp32' (VITAE_GRAD_EXCHANGE=fp32, and always over gloo): the element type in which
-    gradient slices cross NVLink.  bf16 halves the bytes of the one exchange the step has (527 -> 263 MB per step for
-    ViT-B); every rank's slice is rounded to bf16 before the reduction, the mean is widened back into the fp32 gradient
-    buffer, and optimizer / loss-scale arithmetic stay fp32."""
+    """'fp32' (default) or 'bf16' (VITAE_GRAD_EXCHANGE=bf16, NCCL only): the element type in which gradient slices cross
+    NVLink.  bf16 halves the bytes of the one exchange the step has (527 -> 263 MB per step for ViT-B): every rank's slice
+    is rounded to bf16 before the reduction and the mean is widened back into the fp32 gradient buffer; optimizer and
+    loss-scale arithmetic stay fp32.  Measured on 2 x B200 (profiles/r02i_bench2_*.json) the two staging copies cost more
+    than the halved transfer saves (5.06 vs 4.74 ms per step), so it is opt-in for larger rank counts."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_backend() != "nccl":
         return "fp32"
-    return "fp32" if os.environ.get("VITAE_GRAD_EXCHANGE", "bf16").lower() in ("fp32", "f32", "float32") else "bf16"
+    return "bf16" if os.environ.get("VITAE_GRAD_EXCHANGE", "fp32").lower() in ("bf16", "bfloat16") else "fp32"
 
 
 class GradReducer:
@@ -98,10 +99,10 @@ class GradReducer:
         ev.record(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ev)
-            ops.cast_f32_to_bf16(t, h, max_blocks=148)
+            ops.cast_f32_to_bf16(t, h)
             work = dist.all_reduce(h, op=dist.ReduceOp.AVG, async_op=True)
             work.wait()                       # the communication stream waits for NCCL's
-            ops.cast_bf16_to_f32(h, t, max_blocks=148)
+            ops.cast_bf16_to_f32(h, t)
         self.pending.append((None, None))
 
     def wait(self) -> None:

@@ -242,7 +242,7 @@ def run_ours(a):
     torch.manual_seed(42 + rank)                                    # k_fold_cross_valid_combined_brats.py:57,87-89
     model = model_factory.get_models("autoenc", margs).to(dev)
     model.train(True)
-    model.pred_dtype = torch.float32
+    model.pred_dtype = torch.bfloat16       # as inside train_one_stage_epoch, which discards ``pred`` (no fp32 copy of it)
     model.use_cuda_graph = not a.no_graph
     eff_batch = a.batch * world
     lr = 1.5e-4 * eff_batch / 256                                   # blr * eff_batch / 256 (brats.py:157-160)
@@ -396,7 +396,7 @@ def run_ours(a):
         x = pool[0]
         eng.use_graphs = False
         with torch.no_grad(), ops.record_gemms() as rec:
-            pl = eng.forward(x, torch.rand(B, eng.L, device=dev), int(eng.L * (1 - a.mask_ratio)), pred_f32=True)
+            pl = eng.forward(x, torch.rand(B, eng.L, device=dev), int(eng.L * (1 - a.mask_ratio)), pred_f32=False)
             eng.backward(pl, torch.ones(1, device=dev), accumulate=True)
         eng.use_graphs = not a.no_graph
         torch.cuda.synchronize()

@@ -1740,7 +1740,7 @@ static int launch_fwd8(const CUtensorMap& tq128, void* out, float* lse, int B, i
 static void res_tiling(int N, int* q_tiles, int* tail_rows) {
     static const bool light = [] { const char* e = getenv("VITAE_ATTN_LIGHT_TAILS"); return e && e[0] == '1'; }();
     const int full = N / QT, r = N % QT;
-    *tail_rows = (light && full > 0 && r > 0 && r <= ATR_MAX_TAIL_ROWS) ? r : 0;
+    *tail_rows = (light && full > 0 && r > 0 && r <= ATR_MAX_TAIL_ROWS && N <= 2 * AT8_THREADS) ? r : 0;   // two items per thread
     *q_tiles = full + ((r > *tail_rows) ? 1 : 0);
 }
 

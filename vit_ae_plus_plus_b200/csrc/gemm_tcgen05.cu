@@ -34,7 +34,12 @@ constexpr int BK = 64;             // K elements per sub-block (= one 128-byte s
 #define VITAE_EPI_WARPS 8          // 8: two warps per TMEM lane quadrant, each takes half of the tile's columns (BN >= 128)
 #endif
 constexpr int EPI_THREADS = VITAE_EPI_WARPS * 32;
-constexpr int GEMM_THREADS = 64 + EPI_THREADS;   // warp 0: TMA producer, warp 1: MMA issuer, then the epilogue warps
+// Warp roles: the epilogue warps come FIRST, the TMA producer and the MMA issuer LAST.  The warp scheduler favours the highest
+// warp id of a sub-partition; as warps 0 / 1 the two single-thread roles queued behind the epilogue warps that poll the
+// accumulator barrier next to them (measured on the attention kernels, profiles/r02e_attention_event_log.txt: ~200 cycles
+// per tcgen05.mma / commit / barrier wait of a warp-0/1 thread).
+constexpr int GEMM_THREADS = 64 + EPI_THREADS;
+constexpr int GEMM_PROD_WARP = VITAE_EPI_WARPS, GEMM_MMA_WARP = VITAE_EPI_WARPS + 1;
 
 // generic epilogue description (finalize kernel); mirrors vitae_gemm_epilogue
 struct EpiParams {
@@ -65,6 +70,7 @@ struct EpiLite {
     const __nv_bfloat16* dgelu_src;   // bf16 [M, ld_dgelu] (EPI_DGELU_BF16)
     int ld_dgelu;
     int accumulate;                   // EPI_F32: add into the destination (TMA reduce-add)
+    int a_atoms, b_atoms;             // MN-major operand loaded through the 3-D "atom" tensor map: one TMA per sub-block
 };
 
 // in-kernel epilogue kinds (everything else is "generic": slabs + finalize kernel)
@@ -154,13 +160,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int niter = (nsub + SPB - 1) / SPB;
     if (threadIdx.x == 0) GEMM_TRACE(0);
 
-    if (warp == 0 && lane == 0) {
+    if (warp == GEMM_PROD_WARP && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmO0);
         if (KIND == EPI_BF16_GELU || KIND == EPI_BF16_F32) tma_prefetch_desc(&tmO1);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == GEMM_MMA_WARP && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar + s * 8, 1);
             mbar_init(empty_bar + s * 8, 1);
@@ -169,7 +175,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         fence_barrier_init();
         fence_proxy_async();
     }
-    if (warp == 2) {
+    if (warp == 0) {
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), BN);
         tmem_relinquish();
     }
@@ -184,7 +190,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     pdl_wait();
     if (threadIdx.x == 0) GEMM_TRACE(2);
 
-    if (warp == 0) {
+    if (warp == GEMM_PROD_WARP) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             for (int it = 0; it < niter; ++it) {
@@ -200,16 +206,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         const uint32_t sb = sa + S::A_BYTES;
                         const int k0 = (sub_begin + it * SPB + u) * BK;
                         if (A_MN) {
+                            if (ep.a_atoms) {
+                                tma_load_3d(sa, &tmA, full_bar + s * 8, 0, k0, m0 >> 6);
+                            } else {
 #pragma unroll
-                            for (int j = 0; j < BM / 64; ++j)
-                                tma_load_2d(sa + j * (BK * 128), &tmA, full_bar + s * 8, m0 + 64 * j, k0);
+                                for (int j = 0; j < BM / 64; ++j)
+                                    tma_load_2d(sa + j * (BK * 128), &tmA, full_bar + s * 8, m0 + 64 * j, k0);
+                            }
                         } else {
                             tma_load_2d(sa, &tmA, full_bar + s * 8, k0, m0);
                         }
                         if (B_MN) {
+                            if (ep.b_atoms) {
+                                tma_load_3d(sb, &tmB, full_bar + s * 8, 0, k0, n0 >> 6);
+                            } else {
 #pragma unroll
-                            for (int j = 0; j < BN / 64; ++j)
-                                tma_load_2d(sb + j * (BK * 128), &tmB, full_bar + s * 8, n0 + 64 * j, k0);
+                                for (int j = 0; j < BN / 64; ++j)
+                                    tma_load_2d(sb + j * (BK * 128), &tmB, full_bar + s * 8, n0 + 64 * j, k0);
+                            }
                         } else {
                             tma_load_2d(sb, &tmB, full_bar + s * 8, k0, n0);
                         }
@@ -220,7 +234,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             GEMM_TRACE(4);
         }
         __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == GEMM_MMA_WARP) {
         // ------------------------------------------------------------------ MMA issuer (single thread)
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
@@ -257,8 +271,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     } else {
         // ------------------------------------------------------------------ epilogue warps
         const int q = warp & 3;                    // TMEM lane quadrant this warp may access
-        const int half = (warp - 2) >> 2;          // which half of the tile's columns (BN >= 128); BN = 64: half 1 idles
-        const int et = threadIdx.x - 64;           // 0..255 among the epilogue threads
+        const int half = warp >> 2;                // which half of the tile's columns (BN >= 128); BN = 64: half 1 idles
+        const int et = threadIdx.x;                // 0..255: the epilogue threads come first
         const int mrow = m0 + q * 32 + lane;       // this lane's accumulator row
         // bias slice of this tile -> shared memory (read by every lane for every row)
         for (int c = et; c < BN; c += EPI_THREADS) bias_s[c] = (ep.bias && n0 + c < N) ? ep.bias[n0 + c] : 0.f;
@@ -267,11 +281,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         constexpr int CW = (BN >= 128 && VITAE_EPI_WARPS == 8) ? BN / 2 : BN;      // columns per epilogue warp
         constexpr bool TWO_OUT = KIND == EPI_BF16_GELU || KIND == EPI_BF16_F32;
         // staging per warp: 8 KB = two 32-row x 128-byte boxes; one output: they alternate, two outputs: one each
-        const uint32_t stg = base + (warp - 2) * 8192;
+        const uint32_t stg = base + warp * 8192;
         const bool active = (BN >= 128 && VITAE_EPI_WARPS == 8) || half == 0;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        if (threadIdx.x == 64) GEMM_TRACE(7);
+        if (threadIdx.x == 0) GEMM_TRACE(7);
 
         constexpr bool OUT0_BF16 = KIND != EPI_ADD_F32 && KIND != EPI_F32;   // primary output element type
         int nbox = 0;   // bf16 boxes committed so far
@@ -382,11 +396,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (lane == 0) tma_store_wait_read<0>();   // the engine must have read our staging buffers before the CTA exits
         __syncwarp();
         tc_fence_before();
-        if (threadIdx.x == 64) GEMM_TRACE(8);
+        if (threadIdx.x == 0) GEMM_TRACE(8);
     }
     __syncthreads();
     if (threadIdx.x == 0) GEMM_TRACE(9);
-    if (warp == 2) tmem_dealloc(tmem_base, BN);
+    if (warp == 0) tmem_dealloc(tmem_base, BN);
 }
 
 // ---------------------------------------------------------------------------------------------------- generic epilogue
@@ -516,6 +530,39 @@ int make_tmap(CUtensorMap* out, const void* ptr, uint32_t esize, uint64_t d0, ui
         return set_error(-5, "cuTensorMapEncodeTiled failed (%d) ptr=%p esize=%u dims=%llu,%llu,%llu ld=%llu box=%u,%u", (int)r,
                          ptr, esize, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
                          (unsigned long long)ld, b0, b1);
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(key, *out);
+    return 0;
+}
+
+// MN-major operand [K rows, MN columns] (pitch ld) seen as (64 columns, K rows, MN/64 column atoms): ONE box
+// (64, BK, atoms) lands in shared memory as [atom][k][64] -- the 128-byte-swizzled MN-major layout the MMA descriptors
+// expect -- where the 2-D map needs one TMA per 64-column atom (6 per sub-block for a 128 x 256 tile; an issue of the
+// single producer thread costs ~100 cycles, about the transfer time of one 8 KB atom).  Needs MN % 64 == 0 (the view would
+// otherwise read past the row); atoms past MN / 64 are out of bounds of the map and read as zero.
+static int make_tmap_atoms(CUtensorMap* out, const void* ptr, uint64_t MN, uint64_t K, uint64_t ld, uint32_t atoms) {
+    static std::mutex mu;
+    static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+    const TmapKey key{ptr, MN, K, 0xA70115ull, ld, atoms, BK, 2};
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) {
+            *out = it->second;
+            return 0;
+        }
+    }
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return -4;
+    const cuuint64_t dims[3] = {64, K, MN / 64};
+    const cuuint64_t strides[2] = {ld * 2, 128};
+    const cuuint32_t box[3] = {64, BK, atoms};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return -5;       // the caller falls back to one 2-D box per atom
     std::lock_guard<std::mutex> g(mu);
     if (cache.size() > 8192) cache.clear();
     cache.emplace(key, *out);
@@ -672,11 +719,19 @@ extern "C" int vitae_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
     GemmLaunch g;
     g.M = M; g.N = N; g.num_sub = num_sub; g.splits = splits; g.stream = as_stream(stream);
     int rc;
-    if (amn) rc = make_tmap(&g.ta, A, 2, (uint64_t)M, (uint64_t)K, 0, (uint64_t)lda, 64, BK);
-    else     rc = make_tmap(&g.ta, A, 2, (uint64_t)K, (uint64_t)M, 0, (uint64_t)lda, BK, BM);
+    static const bool use_atoms = [] { const char* e = getenv("VITAE_GEMM_ATOM_TMA"); return !(e && e[0] == '0'); }();
+    g.ep.a_atoms = g.ep.b_atoms = 0;
+    if (amn && use_atoms && M % 64 == 0 && make_tmap_atoms(&g.ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM / 64) == 0) {
+        g.ep.a_atoms = 1;
+        rc = 0;
+    } else if (amn) rc = make_tmap(&g.ta, A, 2, (uint64_t)M, (uint64_t)K, 0, (uint64_t)lda, 64, BK);
+    else            rc = make_tmap(&g.ta, A, 2, (uint64_t)K, (uint64_t)M, 0, (uint64_t)lda, BK, BM);
     if (rc) return rc;
-    if (bmn) rc = make_tmap(&g.tb, B, 2, (uint64_t)N, (uint64_t)K, 0, (uint64_t)ldb, 64, BK);
-    else     rc = make_tmap(&g.tb, B, 2, (uint64_t)K, (uint64_t)N, 0, (uint64_t)ldb, BK, (uint32_t)bn);
+    if (bmn && use_atoms && N % 64 == 0 && make_tmap_atoms(&g.tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, (uint32_t)bn / 64) == 0) {
+        g.ep.b_atoms = 1;
+        rc = 0;
+    } else if (bmn) rc = make_tmap(&g.tb, B, 2, (uint64_t)N, (uint64_t)K, 0, (uint64_t)ldb, 64, BK);
+    else            rc = make_tmap(&g.tb, B, 2, (uint64_t)K, (uint64_t)N, 0, (uint64_t)ldb, BK, (uint32_t)bn);
     if (rc) return rc;
 
     g.ep.alpha = e->alpha; g.ep.alpha_ptr = e->alpha_ptr; g.ep.bias = e->bias; g.ep.addend = e->addend; g.ep.ldadd = e->ldadd;

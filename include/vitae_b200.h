@@ -123,9 +123,10 @@ int vitae_reduce_partials(const float* partials, int nblk, int D, float* out0, f
 /* Column sums in one launch: out[c] = (accumulate ? out[c] : 0) + sum_r in[r*ld + c]  (bias gradients of
  * nn.Linear, model/vit.py:84-86,107-109).  Exactly one of in_bf16 / in_f32 is non-NULL; cols % 8 == 0, ld % 8 == 0.
  * workspace: vitae_colsum_workspace_bytes(rows, cols) bytes, ZERO-FILLED before its first use (ticket counters;
- * every call leaves them zero again) and not shared by calls that may run concurrently.  Deterministic. */
+ * every call leaves them zero again) and not shared by calls that may run concurrently.  Deterministic.
+ * scale_ptr (optional): device scalar multiplied into the sums (an upstream loss gradient that lives on the device). */
 int vitae_colsum(const void* in_bf16, const float* in_f32, int rows, int cols, int ld, float* out, int accumulate,
-                 void* workspace, void* stream);
+                 void* workspace, const float* scale_ptr, void* stream);
 size_t vitae_colsum_workspace_bytes(int rows, int cols);
 
 /* All column reductions of one transformer block's backward in one launch: each job is a plain column sum
@@ -264,9 +265,30 @@ int vitae_adamw_step(float* param, const float* grad, float* exp_avg, float* exp
 int vitae_optim_prepare(const float* grad, long long n, const float* grad2, long long n2, float* ctl, float* workspace,
                         float growth_factor, float backoff_factor, int growth_interval, int use_scaler, void* stream);
 size_t vitae_optim_workspace_bytes(void);
+/* The two halves of vitae_optim_prepare on their own.  vitae_grad_sqnorm: vitae_grad_sqnorm_blocks(n, max_blocks)
+ * partial sums of squares of a gradient slice -> partials[] (the backward computes them per stage, underneath the later
+ * stages, so that the step does not start with an 80 us pass over all gradients, utils/misc.py:280-292).
+ * vitae_optim_finalize: ctl[2..5] and the GradScaler.update of ctl[0..1] from npartials partial sums (any layout). */
+int vitae_grad_sqnorm_blocks(long long n, int max_blocks);
+int vitae_grad_sqnorm(const float* grad, long long n, float* partials, int max_blocks, void* stream);
+int vitae_optim_finalize(const float* partials, int npartials, float* ctl, float growth_factor, float backoff_factor,
+                         int growth_interval, int use_scaler, void* stream);
 int vitae_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16,
                      long long n, const unsigned char* group_of_chunk, const float* hyper, int ngroups,
                      const float* ctl, int max_blocks, void* stream);
+
+/* decoder_pred (model/vit_autoenc.py:198) with the masked patch-reconstruction loss (:226-227, utils/custom_loss.py's role in
+ * the north star) fused into its epilogue.  hN bf16 [B*(L+1), Dd] (decoder_norm output, cls row first per sample), W bf16
+ * [P, Dd], bias fp32 [P], P = p^3 * C with C == 4 and p % 8 == 0; vol fp32 [B, C, V, V, V] read in place; mask fp32 [B, L];
+ * mask_sum = sum(mask) (known on the host: B * (L - keep)).  Writes pred bf16 [B*(L+1), P], g bf16 (same shape) =
+ * 2 (pred - target) mask / (P mask_sum) with zero rows for kept patches and the cls token (the backward GEMMs multiply the
+ * upstream gradient in through alpha_ptr) and partials fp32 [vitae_pred_mse_partial_floats(M, P, tile_n)].
+ * vitae_pred_mse_finalize: loss_out[0] = sum(partials) / (P mask_sum), loss_out[1] = mask_sum, fixed order. */
+size_t vitae_pred_mse_partial_floats(int M, int P, int tile_n);
+int vitae_gemm_pred_mse(const void* hN, const void* W, const float* bias, int B, int L, int Dd, const float* vol,
+                        const float* mask, int C, int V, int p, float mask_sum, void* pred_bf16, void* g_bf16,
+                        float* partials, int tile_n, void* stream);
+int vitae_pred_mse_finalize(const float* partials, long long n, int P, float mask_sum, float* loss_out, void* stream);
 
 /* fp32 <-> bf16 copies of a flat gradient slice: the data-parallel exchange (one all-reduce of the trainable parameters'
  * gradients per optimizer step; the reference scripts never wrap the model in DDP,

@@ -131,3 +131,37 @@ def test_auto_config_matches():
         ops.gemm(a, w, M, N, K, out_f32=out)
         torch.cuda.synchronize()
         _check(out, a.float() @ w.float().t(), 2e-3)
+
+
+@pytest.mark.parametrize("B,V,p,keep,tile_n", [(2, 32, 8, 16, 128), (1, 64, 16, 16, 256), (3, 32, 8, 40, 128)])
+def test_pred_gemm_with_fused_masked_mse(B, V, p, keep, tile_n):
+    """vitae_gemm_pred_mse: decoder_pred (model/vit_autoenc.py:198) + masked patch-reconstruction loss (:226-227) in one
+    kernel, against torch fp32 on the same bf16 operands: pred, the unscaled gradient g, and the loss value."""
+    from vit_ae_plus_plus_b200 import ops
+    C, Dd = 4, 64
+    g_, L, P = V // p, (V // p) ** 3, p ** 3 * 4
+    M = B * (L + 1)
+    hN, W = _mk((M, Dd), 11), _mk((P, Dd), 12, 0.2)
+    bias = torch.randn(P, device="cuda") * 0.1
+    vol = torch.randn(B, C, V, V, V, device="cuda")
+    mask = torch.zeros(B, L, device="cuda")
+    for b in range(B):
+        mask[b, torch.randperm(L, device="cuda")[:L - keep]] = 1.0
+    mask_sum = float(B * (L - keep))
+    pred = torch.empty(M, P, device="cuda", dtype=torch.bfloat16)
+    gq = torch.full((M, P), float("nan"), device="cuda", dtype=torch.bfloat16)
+    part = torch.empty(ops.pred_mse_partial_floats(M, P, tile_n), device="cuda")
+    loss_out = torch.empty(2, device="cuda")
+    ops.gemm_pred_mse(hN, W, bias, B, L, Dd, vol, mask, p, mask_sum, pred, gq, part, tile_n)
+    ops.pred_mse_finalize(part, P, mask_sum, loss_out)
+    torch.cuda.synchronize()
+    ref = hN.float() @ W.float().t() + bias                                            # [M, P]
+    _check(pred, ref, 1e-2)
+    target = vol.reshape(B, C, g_, p, g_, p, g_, p).permute(0, 2, 4, 6, 3, 5, 7, 1).reshape(B, L, P)   # vit_autoenc.py:100-113
+    rp = ref.reshape(B, L + 1, P)[:, 1:, :]
+    loss_ref = (((rp - target) ** 2).mean(-1) * mask).sum() / mask.sum()
+    assert abs(loss_out[0].item() - loss_ref.item()) < 1e-4 * abs(loss_ref.item()) and loss_out[1].item() == mask_sum
+    g_ref = torch.zeros(B, L + 1, P, device="cuda")
+    g_ref[:, 1:, :] = 2.0 * (rp - target) * mask[:, :, None] / (P * mask_sum)
+    _check(gq.reshape(B, L + 1, P), g_ref, 1e-2)
+    assert torch.isfinite(gq.float()).all() and (gq.reshape(B, L + 1, P)[:, 0].float() == 0).all()

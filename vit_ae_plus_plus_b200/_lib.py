@@ -66,7 +66,11 @@ SIGNATURES = {
     "vitae_reduce_partials": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "vitae_block_colreduce": (c_int, [POINTER(ColJob), c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "vitae_block_colreduce_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "vitae_colsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "vitae_colsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "vitae_pred_mse_partial_floats": (c_size_t, [c_int, c_int, c_int]),
+    "vitae_gemm_pred_mse": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                    c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "vitae_pred_mse_finalize": (c_int, [c_void_p, c_longlong, c_int, c_float, c_void_p, c_void_p]),
     "vitae_colsum_workspace_bytes": (c_size_t, [c_int, c_int]),
     "vitae_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "vitae_attention_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_float, c_void_p]),
@@ -91,6 +95,9 @@ SIGNATURES = {
     "vitae_optim_prepare": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_float, c_float, c_int,
                                     c_int, c_void_p]),
     "vitae_optim_workspace_bytes": (c_size_t, []),
+    "vitae_grad_sqnorm_blocks": (c_int, [c_longlong, c_int]),
+    "vitae_grad_sqnorm": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_void_p]),
+    "vitae_optim_finalize": (c_int, [c_void_p, c_int, c_void_p, c_float, c_float, c_int, c_int, c_void_p]),
     "vitae_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_int,
                                  c_void_p, c_int, c_void_p]),
     "vitae_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),

@@ -270,7 +270,8 @@ __device__ __forceinline__ void cs_load8<__nv_bfloat16>(const __nv_bfloat16* p, 
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ in, int rows, int cols, int ld, float* __restrict__ out, int accumulate,
-              float* __restrict__ ws_partials, unsigned int* __restrict__ counters, int rows_per_slice) {
+              float* __restrict__ ws_partials, unsigned int* __restrict__ counters, int rows_per_slice,
+              const float* __restrict__ scale_ptr) {
     pdl_trigger();
     pdl_wait();
     __shared__ float red[8][CS_COLS + 8];
@@ -305,8 +306,9 @@ colsum_kernel(const T* __restrict__ in, int rows, int cols, int ld, float* __res
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    const float scale = scale_ptr ? *scale_ptr : 1.0f;
     if (gridDim.y == 1) {
-        if (col < cols) out[col] = accumulate ? out[col] + s : s;
+        if (col < cols) out[col] = accumulate ? out[col] + s * scale : s * scale;
         return;
     }
     if (col < cols) ws_partials[static_cast<size_t>(blockIdx.y) * cols + col] = s;
@@ -327,7 +329,7 @@ colsum_kernel(const T* __restrict__ in, int rows, int cols, int ld, float* __res
             t3 += __ldcg(ws_partials + static_cast<size_t>(y + 3) * cols + col);
         }
         for (; y < ns; ++y) t0 += __ldcg(ws_partials + static_cast<size_t>(y) * cols + col);
-        const float t = (t0 + t1) + (t2 + t3);
+        const float t = ((t0 + t1) + (t2 + t3)) * scale;
         out[col] = accumulate ? out[col] + t : t;
     }
     if (threadIdx.x == 0) counters[blockIdx.x] = 0u;
@@ -611,7 +613,7 @@ extern "C" size_t vitae_colsum_workspace_bytes(int rows, int cols) {
 }
 
 extern "C" int vitae_colsum(const void* in_bf16, const float* in_f32, int rows, int cols, int ld, float* out,
-                            int accumulate, void* workspace, void* stream) {
+                            int accumulate, void* workspace, const float* scale_ptr, void* stream) {
     VITAE_REQUIRE((in_bf16 != nullptr) != (in_f32 != nullptr), "colsum: exactly one input");
     VITAE_REQUIRE(out && workspace && rows > 0 && cols > 0 && ld >= cols, "colsum: bad arguments");
     VITAE_REQUIRE(cols % 8 == 0 && ld % 8 == 0, "colsum: cols and ld must be multiples of 8 (cols=%d ld=%d)", cols, ld);
@@ -623,9 +625,9 @@ extern "C" int vitae_colsum(const void* in_bf16, const float* in_f32, int rows, 
     auto* parts = reinterpret_cast<float*>(static_cast<char*>(workspace) + ((static_cast<size_t>(strips) * sizeof(unsigned int) + 255) / 256) * 256);
     dim3 grid(strips, eff_slices);
     if (in_bf16)
-        launch_kernel(colsum_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(in_bf16), rows, cols, ld, out, accumulate, parts, counters, rows_per_slice);
+        launch_kernel(colsum_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(in_bf16), rows, cols, ld, out, accumulate, parts, counters, rows_per_slice, scale_ptr);
     else
-        launch_kernel(colsum_kernel<float>, dim3(grid), dim3(256), 0, as_stream(stream), in_f32, rows, cols, ld, out, accumulate, parts, counters, rows_per_slice);
+        launch_kernel(colsum_kernel<float>, dim3(grid), dim3(256), 0, as_stream(stream), in_f32, rows, cols, ld, out, accumulate, parts, counters, rows_per_slice, scale_ptr);
     VITAE_CHECK_LAUNCH("colsum");
     return 0;
 }

@@ -642,6 +642,31 @@ extern "C" int vitae_optim_prepare(const float* grad, long long n, const float* 
     return 0;
 }
 
+// The two halves of vitae_optim_prepare on their own: squared-norm partials of a gradient SLICE (the backward computes them
+// per stage on a side lane, underneath the later stages) and the control-block update over any number of partials.
+extern "C" int vitae_grad_sqnorm_blocks(long long n, int max_blocks) {
+    const int cap = max_blocks > 0 ? std::min(max_blocks, OPT_NORM_BLOCKS) : OPT_NORM_BLOCKS;
+    return static_cast<int>(std::min<long long>(ceil_div<long long>(n, 1024), cap));
+}
+
+extern "C" int vitae_grad_sqnorm(const float* grad, long long n, float* partials, int max_blocks, void* stream) {
+    VITAE_REQUIRE(grad && partials && n > 0, "grad_sqnorm: bad arguments");
+    VITAE_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0, "grad_sqnorm: grad must be 16-byte aligned");
+    const int blocks = vitae_grad_sqnorm_blocks(n, max_blocks);
+    launch_kernel(grad_sqnorm_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), grad, n, partials);
+    VITAE_CHECK_LAUNCH("grad_sqnorm");
+    return 0;
+}
+
+extern "C" int vitae_optim_finalize(const float* partials, int npartials, float* ctl, float growth_factor, float backoff_factor,
+                                    int growth_interval, int use_scaler, void* stream) {
+    VITAE_REQUIRE(partials && ctl && npartials > 0, "optim_finalize: bad arguments");
+    launch_kernel(optim_finalize_kernel, dim3(1), dim3(256), 0, as_stream(stream), partials, npartials, ctl, growth_factor,
+                  backoff_factor, growth_interval, use_scaler);
+    VITAE_CHECK_LAUNCH("optim_finalize");
+    return 0;
+}
+
 extern "C" int vitae_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16,
                                 long long n, const unsigned char* group_of_chunk, const float* hyper, int ngroups,
                                 const float* ctl, int max_blocks, void* stream) {

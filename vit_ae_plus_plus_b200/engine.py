@@ -175,6 +175,7 @@ class _Lanes:
         self.readers: Dict[object, Dict[int, torch.cuda.Event]] = {}
         self.dirty = [False, False]
         self.extra_dirty: Optional[torch.cuda.Stream] = None   # another forked stream to join (L2 prefetches)
+        self.forked: List[torch.cuda.Stream] = []             # further streams to join (gradient-norm partials)
 
     def side(self, fn, reads=(), lane: int = 0) -> None:
         main = torch.cuda.current_stream()
@@ -208,7 +209,24 @@ class _Lanes:
                 ev.record(st)
                 torch.cuda.current_stream().wait_event(ev)
                 self.dirty[lane] = False
+        for st in self.forked:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            torch.cuda.current_stream().wait_event(ev)
+        self.forked = []
         self.readers.clear()
+
+    def after_all(self, st: torch.cuda.Stream, fn) -> None:
+        """Runs ``fn`` on stream ``st`` after everything enqueued so far on the main lane AND the side lanes; ``join``
+        orders the main lane after it."""
+        for src in [torch.cuda.current_stream()] + [s for lane, s in enumerate(self.streams) if self.dirty[lane]]:
+            ev = torch.cuda.Event()
+            ev.record(src)
+            st.wait_event(ev)
+        with torch.cuda.stream(st):
+            fn()
+        if st not in self.forked:
+            self.forked.append(st)
 
 
 class _GraphSlot:
@@ -291,6 +309,8 @@ class MAEPlan:
         self.pred = a.new((B, self.Nd, P), _BF16)
         self.pred32: Optional[torch.Tensor] = None   # fp32 copy of pred, allocated when the caller wants fp32 back
         self.step_id = 0
+        self.mse_part: Optional[torch.Tensor] = None    # row partials of the loss fused into the decoder_pred GEMM
+        self.fused_loss = False                         # the last forward left d recon / d pred (unscaled) in dpred
         self.patch_sums = a.new((B * L,), _F32)
         self.loss_out = a.new((2,), _F32)
         # backward scratch
@@ -426,6 +446,12 @@ class MAEEngine:
         self._waited = set()               # groups the pass being enqueued has already waited for
         self.grad_buckets = None
         self.bucket_elems = 32 << 20       # 128 MB of fp32 gradients per all-reduce bucket
+        # squared-norm partials of the gradient slices, computed per backward part on a stream of their own underneath the
+        # later parts (FusedAdamW.step then starts with the tiny finalize instead of an 80 us pass over all gradients)
+        self.norm_stream = torch.cuda.Stream(device=dev, priority=0)
+        self.norm_blocks = 148
+        self.norm_ws = torch.zeros(16 * self.norm_blocks, dtype=_F32, device=dev)
+        self.norm_partials = 0             # > 0: norm_ws[:norm_partials] covers the whole gradient buffer as it is now
         self.g16: Optional[torch.Tensor] = None            # bf16 staging of the gradient exchange (allocated for N > 1)
         self.comm_stream: Optional[torch.cuda.Stream] = None
 
@@ -637,6 +663,13 @@ class MAEEngine:
             pl.edge_buffers(self)
         if with_predictor:
             self._pred_bufs(pl)
+        # the reconstruction loss rides in the epilogue of the decoder_pred GEMM (vitae_gemm_pred_mse) whenever nothing needs
+        # the separate kernels: 4 channels, patch % 8 == 0, no fp32 copy of pred, no edge-map term reading pred
+        fuse_loss = (want_loss and not want_edge and not pred_f32 and self.C == 4 and self.p % 8 == 0 and self.P % 128 == 0
+                     and pl.nmask > 0 and os.environ.get("VITAE_FUSED_LOSS", "1") != "0")
+        if fuse_loss and pl.mse_part is None:
+            pl.mse_part = torch.empty(ops.pred_mse_partial_floats(pl.Md, self.P, 128), dtype=_F32, device=self.device)
+        pl.fused_loss = fuse_loss
 
         def body():
             if want_edge:
@@ -646,15 +679,15 @@ class MAEEngine:
             self.encode(pl, vol, pl.noise)
             if with_predictor:
                 self.predictor_forward(pl)
-            self.decode(pl, pred_f32)
-            if want_loss:
+            self.decode(pl, pred_f32, loss_vol=vol if fuse_loss else None)
+            if want_loss and not fuse_loss:
                 ops.masked_mse_fwd(pl.pred, vol, pl.mask, pl.patch_sums, pl.loss_out, self.p)
             if want_edge:
                 self._background_join()
                 ops.edge_loss_fwd(pl.pred, pl.edge_tgt, pl.edge_scratch, pl.edge_resid, pl.edge_out, pl.B, self.C, self.V,
                                   self.p)
             self.lanes.join()          # the side lane carries the L2 prefetches of the forward
-        self._run(pl, ("fwd", vol.data_ptr(), pred_f32, want_loss, want_edge, with_predictor), body)
+        self._run(pl, ("fwd", vol.data_ptr(), pred_f32, want_loss, want_edge, with_predictor, fuse_loss), body)
         self.params_in_flight = False      # the pass above waited for every parameter group
         return pl
 
@@ -685,8 +718,10 @@ class MAEEngine:
         ops.layernorm_fwd(pl.enc.x[-1], self._p("norm.weight"), self._p("norm.bias"), pl.latent, pl.mean_n, pl.rstd_n,
                           self.eps, y_f32=pl.latent32)
 
-    def decode(self, pl: MAEPlan, pred_f32: bool = False) -> None:
-        """model/vit_autoenc.py:179-203 (forward_decoder); pl.pred keeps the cls row (row 0 of each sample)."""
+    def decode(self, pl: MAEPlan, pred_f32: bool = False, loss_vol: Optional[torch.Tensor] = None) -> None:
+        """model/vit_autoenc.py:179-203 (forward_decoder); pl.pred keeps the cls row (row 0 of each sample).  ``loss_vol``:
+        evaluate the masked reconstruction loss against this volume in the decoder_pred epilogue (fills pl.loss_out and
+        pl.dpred = d recon / d pred before the upstream factor)."""
         if pred_f32 and pl.pred32 is None:
             pl.pred32 = torch.empty((pl.B, pl.Nd, self.P), dtype=_F32, device=self.device)
         B, D, Dd = pl.B, self.enc.dim, self.dec.dim
@@ -703,6 +738,14 @@ class MAEEngine:
         self._need("decoder_norm.weight")
         ops.layernorm_fwd(pl.dec.x[-1], self._p("decoder_norm.weight"), self._p("decoder_norm.bias"), pl.hN,
                           pl.mean_dn, pl.rstd_dn, self.eps)
+        if loss_vol is not None:
+            mask_sum = float(pl.B * pl.nmask)          # every sample removes exactly L - keep patches (vit_autoenc.py:137-153)
+            self.lanes.before_write("dpred")
+            ops.gemm_pred_mse(pl.hN, self._w("decoder_pred.weight"), self._p("decoder_pred.bias"), B, self.L, Dd, loss_vol,
+                              pl.mask, self.p, mask_sum, pl.pred.view(pl.Md, self.P), pl.dpred.view(pl.Md, self.P), pl.mse_part)
+            # the loss value itself is off the dependency chain: reduce the row partials on a side lane
+            self._side(lambda: ops.pred_mse_finalize(pl.mse_part, self.P, mask_sum, pl.loss_out), lane=1)
+            return
         ops.gemm(pl.hN, self._w("decoder_pred.weight"), pl.Md, self.P, Dd, bias=self._p("decoder_pred.bias"),
                  out_bf16=pl.pred.view(pl.Md, self.P), out_f32=pl.pred32.view(pl.Md, self.P) if pred_f32 else None,
                  workspace=self.ws_main)
@@ -767,16 +810,26 @@ class MAEEngine:
         stages = self._backward_stages(pl, dpred_extra, accumulate, split=staged, with_dlatent=dlatent is not None,
                                        encoder_only=encoder_only, with_edge=dedge is not None)
         reducer = self._grad_reducer() if staged else None
+        self._norm_count = 0
+        self.norm_partials = 0
         for i, (fn, (a, b)) in enumerate(stages):
             if dpred_extra is not None and i == 0:   # auxiliary torch-side terms that consume ``pred``: not graphed
                 fn()
             else:
                 self._run(pl, ("bwd", i, len(stages), pl.vol.data_ptr(), bool(accumulate), dlatent is not None,
-                               encoder_only, dedge is not None), fn)
+                               encoder_only, dedge is not None, pl.fused_loss), fn)
             if reducer is not None:
                 reducer.launch(self.flat.g32[a:b])
         if reducer is not None:
             reducer.wait()
+        if len(stages) == 1 and not staged and not encoder_only and dpred_extra is None:
+            # (a replayed graph does not run the python above: the count is kept from the pass that was captured)
+            key = ("bwd", 0, 1, pl.vol.data_ptr(), bool(accumulate), dlatent is not None, encoder_only, dedge is not None,
+                   pl.fused_loss)
+            if self._norm_count:
+                pl.norm_counts = getattr(pl, "norm_counts", {})
+                pl.norm_counts[key] = self._norm_count
+            self.norm_partials = getattr(pl, "norm_counts", {}).get(key, 0)
 
     def _backward_stages(self, pl: MAEPlan, dpred_extra: Optional[torch.Tensor], acc: bool, split: bool,
                          with_dlatent: bool = False, encoder_only: bool = False, with_edge: bool = False):
@@ -795,25 +848,32 @@ class MAEEngine:
         enc_hi, enc_rest = enc_groups[0], enc_groups[1:]
         dec_all = list(reversed(range(self.dec.depth)))
 
+        # the forward's fused loss epilogue already left g = d recon / d pred in dpred, without the upstream factor: the
+        # GEMMs below apply it through alpha_ptr.  Any other term that writes into dpred needs the scaled gradient instead.
+        use_g = pl.fused_loss and dpred_extra is None and not with_edge
+        up = pl.dloss if use_g else None
+
         def stage_pred():
             self._prefetch_block(self.dec, pl.dec, self.dec.depth - 1, with_acts=True)
-            # ---- loss: d recon / d pred (model/vit_autoenc.py:226-227), zeros for kept patches and the cls row
-            lanes.before_write("dpred")
-            ops.masked_mse_bwd(pl.pred, pl.vol, pl.mask, pl.loss_out[1:], pl.dloss, pl.dpred, self.p)
-            if with_edge:       # + dedge * d raw_edge / d pred (transposed Sobel stencil over the kept residual)
-                ops.edge_loss_bwd(pl.edge_resid, pl.edge_scratch, pl.dedge, pl.dpred, pl.B, self.C, self.V, self.p)
-            if dpred_extra is not None:
-                pl.dpred[:, 1:, :].add_(dpred_extra.to(_BF16))
+            if not use_g:
+                # ---- loss: d recon / d pred (model/vit_autoenc.py:226-227), zeros for kept patches and the cls row
+                lanes.before_write("dpred")
+                ops.masked_mse_bwd(pl.pred, pl.vol, pl.mask, pl.loss_out[1:], pl.dloss, pl.dpred, self.p)
+                if with_edge:       # + dedge * d raw_edge / d pred (transposed Sobel stencil over the kept residual)
+                    ops.edge_loss_bwd(pl.edge_resid, pl.edge_scratch, pl.dedge, pl.dpred, pl.B, self.C, self.V, self.p)
+                if dpred_extra is not None:
+                    pl.dpred[:, 1:, :].add_(dpred_extra.to(_BF16))
             dpred = pl.dpred.view(pl.Md, P)
             # ---- decoder_pred (vit_autoenc.py:198)
 
             def side_pred():
                 ops.gemm(dpred, pl.hN, P, Dd, pl.Md, a_mn_major=True, b_mn_major=True,
-                         out_f32=self._g("decoder_pred.weight"), accumulate=acc, workspace=wss)
-                ops.colsum(dpred, pl.Md, P, self._g("decoder_pred.bias"), cws, accumulate=acc)
+                         out_f32=self._g("decoder_pred.weight"), accumulate=acc, alpha_ptr=up, workspace=wss)
+                ops.colsum(dpred, pl.Md, P, self._g("decoder_pred.bias"), cws, accumulate=acc, scale_ptr=up)
             self._side(side_pred, reads=("dpred",))
             d_d = self._ln_in(pl, pl.Md, Dd)
-            ops.gemm(dpred, self._w("decoder_pred.weight"), pl.Md, Dd, P, b_mn_major=True, out_bf16=d_d, workspace=wsm)
+            ops.gemm(dpred, self._w("decoder_pred.weight"), pl.Md, Dd, P, b_mn_major=True, out_bf16=d_d, alpha_ptr=up,
+                     workspace=wsm)
             last_dec = f"decoder_blocks.{self.dec.depth - 1}.mlp.fc2.bias" if self.dec.depth else None
             state["cur"] = self._ln_bwd(pl, d_d, pl.dec.x[-1], "decoder_norm", pl.mean_dn, pl.rstd_dn, None, 0, pl.Md, Dd,
                                         acc, last_dec)
@@ -884,16 +944,27 @@ class MAEEngine:
             parts.append((stage_enc_group(grp), off(f"blocks.{grp[0]}.mlp.fc2.weight")))
         parts.append((stage_embed, off("cls_token")))
 
-        def joined(fns):
-            def run():
-                for f in fns:
-                    f()
-                lanes.join()      # a stage is self-contained: its side-lane work is part of it
-            return run
-        if not split:
-            return [(joined([f for f, _ in parts]), (0, self.flat.total))]
         starts = [o for _, o in parts] + [self.flat.total]
         assert starts[0] == 0 and all(a < b for a, b in zip(starts, starts[1:])), "stage slices must tile the gradient buffer"
+        norm_parts = self.use_side_lane and not split and not encoder_only and len(parts) <= 16
+
+        def joined(fns, with_norm=False):
+            def run():
+                off_p = 0
+                for k, f in enumerate(fns):
+                    f()
+                    if with_norm:     # this part's slice of the gradient buffer is final once its lanes have drained
+                        a, b = starts[k], starts[k + 1]
+                        nb = ops.grad_sqnorm_blocks(b - a, self.norm_blocks)
+                        lanes.after_all(self.norm_stream, lambda a=a, b=b, o=off_p: ops.grad_sqnorm(
+                            self.flat.g32[a:b], self.norm_ws[o:], self.norm_blocks))
+                        off_p += nb
+                lanes.join()      # a stage is self-contained: its side-lane work is part of it
+                if with_norm:
+                    self._norm_count = off_p
+            return run
+        if not split:
+            return [(joined([f for f, _ in parts], with_norm=norm_parts), (0, self.flat.total))]
         return [(joined([f]), (starts[i], starts[i + 1])) for i, (f, _) in enumerate(parts)]
 
     def _ln_in(self, pl: MAEPlan, M: int, D: int) -> torch.Tensor:
@@ -1231,8 +1302,13 @@ class FusedAdamW:
                 self.ex_g32.zero_()
             if have:
                 torch._foreach_copy_([d for d, _ in have], [g for _, g in have])
-        ops.optim_prepare(flat.g32, flat.total, self.ctl, self.ws, gf, bf, gi, use_scaler,
-                          grad2=self.ex_g32 if self.ex_total else None, n2=self.ex_total)
+        if eng.norm_partials and not self.ex_total:
+            # the backward left the squared-norm partials of every gradient slice behind (computed under its later stages)
+            ops.optim_finalize(eng.norm_ws, eng.norm_partials, self.ctl, gf, bf, gi, use_scaler)
+        else:
+            ops.optim_prepare(flat.g32, flat.total, self.ctl, self.ws, gf, bf, gi, use_scaler,
+                              grad2=self.ex_g32 if self.ex_total else None, n2=self.ex_total)
+        eng.norm_partials = 0
         rows = [(g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"]) for g in optimizer.param_groups]
         norm = self.ctl[4].clone()
         if self.ex_total:

@@ -276,6 +276,8 @@ class MaskedAutoencoderViT(nn.Module):
         eng.backward(pl, drecon, dpred_extra=dpred, accumulate=acc, sync_grads=overlap_sync, dlatent=dlatent, dedge=dedge)
         if second is not None and second[1] is not None:
             eng.backward(second[0], None, accumulate=True, dlatent=second[1], encoder_only=True)
+        if saved is not None:
+            eng.norm_partials = 0        # foreign gradients are added below: the per-stage norm partials no longer cover them
         if state is not True:
             for n in flat.order:
                 p = flat.params[n]

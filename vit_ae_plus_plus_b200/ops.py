@@ -282,7 +282,8 @@ def block_colreduce(jobs, rows: int, workspace, accumulate: bool = False) -> Non
                                     workspace.numel() * workspace.element_size(), _stream()), "vitae_block_colreduce")
 
 
-def colsum(inp, rows: int, cols: int, out, workspace, accumulate: bool = False, ld: Optional[int] = None) -> None:
+def colsum(inp, rows: int, cols: int, out, workspace, accumulate: bool = False, ld: Optional[int] = None,
+           scale_ptr: Optional[torch.Tensor] = None) -> None:
     """workspace: uint8 tensor of >= colsum_workspace_bytes(rows, cols) bytes, zero-filled at allocation (see header)."""
     lib = _lib.load()
     if workspace.numel() * workspace.element_size() < lib.vitae_colsum_workspace_bytes(rows, cols):
@@ -290,7 +291,7 @@ def colsum(inp, rows: int, cols: int, out, workspace, accumulate: bool = False, 
     in16 = inp.data_ptr() if inp.dtype == _BF16 else None
     in32 = inp.data_ptr() if inp.dtype == _F32 else None
     check(lib.vitae_colsum(in16, in32, rows, cols, ld if ld is not None else cols, out.data_ptr(), int(accumulate),
-                           workspace.data_ptr(), _stream()), "vitae_colsum")
+                           workspace.data_ptr(), _ptr(scale_ptr), _stream()), "vitae_colsum")
 
 
 def attention_fwd(qkv, out, lse, B: int, N: int, H: int, hd: int, scale: float) -> None:
@@ -543,3 +544,44 @@ def cosine_loss_bwd(p1, z2, p2, z1, weight: float, workspace, upstream, dp1, dp2
     check(_lib.load().vitae_cosine_loss_bwd(p1.data_ptr(), z2.data_ptr(), p2.data_ptr(), z1.data_ptr(), M, D, weight,
                                             workspace.data_ptr(), upstream.data_ptr(), dp1.data_ptr(), dp2.data_ptr(), _stream()),
           "vitae_cosine_loss_bwd")
+
+
+def grad_sqnorm_blocks(n: int, max_blocks: int = 0) -> int:
+    return _lib.load().vitae_grad_sqnorm_blocks(n, max_blocks)
+
+
+def grad_sqnorm(grad, partials, max_blocks: int = 0) -> None:
+    """Partial sums of squares of a flat fp32 gradient slice -> partials[: grad_sqnorm_blocks(n, max_blocks)]."""
+    _req(grad, _F32, "sqnorm grad"); _req(partials, _F32, "sqnorm partials")
+    check(_lib.load().vitae_grad_sqnorm(grad.data_ptr(), grad.numel(), partials.data_ptr(), max_blocks, _stream()),
+          "vitae_grad_sqnorm")
+
+
+def optim_finalize(partials, npartials: int, ctl, growth_factor: float, backoff_factor: float, growth_interval: int,
+                   use_scaler: bool) -> None:
+    check(_lib.load().vitae_optim_finalize(partials.data_ptr(), npartials, ctl.data_ptr(), growth_factor, backoff_factor,
+                                           growth_interval, int(use_scaler), _stream()), "vitae_optim_finalize")
+
+
+def pred_mse_partial_floats(M: int, P: int, tile_n: int = 128) -> int:
+    return _lib.load().vitae_pred_mse_partial_floats(M, P, tile_n)
+
+
+def gemm_pred_mse(hN, W, bias, B: int, L: int, Dd: int, vol, mask, p: int, mask_sum: float, pred_bf16, g_bf16, partials,
+                  tile_n: int = 128) -> None:
+    """decoder_pred GEMM with the masked reconstruction loss in its epilogue (include/vitae_b200.h: vitae_gemm_pred_mse)."""
+    _req(hN, _BF16, "pred_mse hN"); _req(W, _BF16, "pred_mse W"); _req(vol, _F32, "pred_mse vol"); _req(mask, _F32, "pred_mse mask")
+    _req(pred_bf16, _BF16, "pred_mse pred"); _req(g_bf16, _BF16, "pred_mse g"); _req(partials, _F32, "pred_mse partials")
+    C, V = vol.shape[1], vol.shape[2]
+    check(_lib.load().vitae_gemm_pred_mse(hN.data_ptr(), W.data_ptr(), _ptr(bias), B, L, Dd, vol.data_ptr(), mask.data_ptr(), C, V, p,
+                                          float(mask_sum), pred_bf16.data_ptr(), g_bf16.data_ptr(), partials.data_ptr(), tile_n,
+                                          _stream()), "vitae_gemm_pred_mse")
+    if _gemm_log is not None:
+        M, P = B * (L + 1), p ** 3 * C
+        _gemm_log.append((2.0 * M * P * Dd, lambda: gemm_pred_mse(hN, W, bias, B, L, Dd, vol, mask, p, mask_sum, pred_bf16, g_bf16,
+                                                                  partials, tile_n)))
+
+
+def pred_mse_finalize(partials, P: int, mask_sum: float, loss_out) -> None:
+    check(_lib.load().vitae_pred_mse_finalize(partials.data_ptr(), partials.numel(), P, float(mask_sum), loss_out.data_ptr(),
+                                              _stream()), "vitae_pred_mse_finalize")

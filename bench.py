@@ -32,6 +32,9 @@ WORKLOADS = {
     "vit_base_128": dict(model="mae_vit_base_patch16", volume_size=128, in_channels=4, patch_size=16, oracle="vit_base_128"),
     # configs[3]: ViT-L/16 autoenc on 96^3 x 4
     "vit_large_96": dict(model="mae_vit_large_patch16", volume_size=96, in_channels=4, patch_size=16, oracle="vit_large_96"),
+    # the k-fold scripts' default --model (k_fold_cross_valid_combined_brats.py:37): MAE + contrastive predictor on two views
+    "contr_vit_base_128": dict(model="contr_mae_vit_base_patch16", volume_size=128, in_channels=4, patch_size=16,
+                               oracle="vit_base_128", contrastive=True),
 }
 METRIC = "training volumes/sec (fwd+bwd+AdamW), ViT-AE on synthetic 128^3x4 volumes"
 UNIT = "volumes/s"
@@ -64,7 +67,7 @@ def parse_args():
 def model_args(w, a):
     return argparse.Namespace(model=w["model"], volume_size=w["volume_size"], in_channels=w["in_channels"],
                               patch_size=w["patch_size"], perceptual_weight=0, use_imagenet=False,
-                              mask_ratio=a.mask_ratio, accum_iter=1)
+                              mask_ratio=a.mask_ratio, accum_iter=1, contr_weight=0.1)
 
 
 def workload_name(w, a, n):
@@ -82,6 +85,9 @@ def cpu_reference_rate(workload: dict, mask_ratio: float, batch: int, steps: int
     torch.set_num_threads(threads)
     cfg = O.CONFIGS[workload["oracle"]]
     P = O.init_params(cfg, 0)
+    contrastive = bool(workload.get("contrastive"))
+    if contrastive:
+        P.update(O.init_predictor_params(cfg, 0))
     leaves = {k: v.clone().requires_grad_(k not in O.FROZEN) for k, v in P.items()}
     opt = torch.optim.AdamW(O.weight_decay_groups(list(leaves.items()), 0.05), lr=1e-4, betas=(0.9, 0.95))
     V, C = cfg["volume_size"], cfg["in_chans"]
@@ -92,7 +98,13 @@ def cpu_reference_rate(workload: dict, mask_ratio: float, batch: int, steps: int
     for it in range(warmup + steps):
         noise = torch.rand(batch, L, generator=gen)
         t0 = time.perf_counter()
-        losses, _, _, _ = O.forward(x, leaves, cfg, mask_ratio, noise, edge_w, with_edge=edge_w != 0)
+        if contrastive:       # two views, the second with its own mask (model/vit_autoenc.py:270-285) + the loop's cosine term
+            noise2 = torch.rand(batch, L, generator=gen)
+            losses, _, _, p1, p2, z1, z2 = O.forward_contrastive(x, x.flip(2), leaves, cfg, mask_ratio, noise, noise2, edge_w,
+                                                                 with_edge=edge_w != 0)
+            losses[0] = losses[0] + O.contrastive_loss(p1, p2, z1, z2, 0.1)
+        else:
+            losses, _, _, _ = O.forward(x, leaves, cfg, mask_ratio, noise, edge_w, with_edge=edge_w != 0)
         opt.zero_grad(set_to_none=True)
         losses[0].backward()
         opt.step()
@@ -240,7 +252,7 @@ def run_ours(a):
     w = WORKLOADS[a.workload]
     margs = model_args(w, a)
     torch.manual_seed(42 + rank)                                    # k_fold_cross_valid_combined_brats.py:57,87-89
-    model = model_factory.get_models("autoenc", margs).to(dev)
+    model = model_factory.get_models("autoenc_contr" if w.get("contrastive") else "autoenc", margs).to(dev)
     model.train(True)
     model.pred_dtype = torch.bfloat16       # as inside train_one_stage_epoch, which discards ``pred`` (no fp32 copy of it)
     model.use_cuda_graph = not a.no_graph
@@ -267,11 +279,22 @@ def run_ours(a):
         assert dp_check["ok"], f"data-parallel self-check failed: {dp_check}"
         del chk
 
+    contrastive = bool(w.get("contrastive"))
+    if contrastive:
+        from vit_ae_plus_plus_b200.utils.train_one_epoch import compute_contrastive_loss
+        criterion = torch.nn.CosineSimilarity(dim=1)
+
     def step(x):
-        losses, _pred, _mask = model(x, mask_ratio=a.mask_ratio, edge_map_weight=a.edge_map_weight)
-        scaler(losses[0], opt, parameters=model.parameters(), update_grad=True)
+        if contrastive:       # the loop's 7-tuple branch (utils/train_one_epoch.py:51-58); view 2 = the flipped volume
+            losses, _pred, _mask, p1, p2, z1, z2 = model(view1=x, view2=x.flip(2), mask_ratio=a.mask_ratio,
+                                                         edge_map_weight=a.edge_map_weight)
+            loss = losses[0] + compute_contrastive_loss(margs, criterion, p1, p2, z1, z2)
+        else:
+            losses, _pred, _mask = model(x, mask_ratio=a.mask_ratio, edge_map_weight=a.edge_map_weight)
+            loss = losses[0]
+        scaler(loss, opt, parameters=model.parameters(), update_grad=True)
         opt.zero_grad()
-        return losses[0]
+        return loss
 
     def barrier():
         if world > 1:
@@ -420,14 +443,15 @@ def run_ours(a):
         # launch), only reported for the workload it was taken on
         traffic = None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01c_gemm_dram_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02q_gemm_dram_traffic.json")))
             if a.workload == "vit_base_128" and B == 4 and abs(a.mask_ratio - 0.75) < 1e-9 and tj["gemm_launches"] == len(rec.calls):
                 traffic = tj["gemm_dram_bytes"]
         except (OSError, KeyError, ValueError):
             pass
         roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": achieved, "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
-                    "traffic_note": "bytes per step over the same launches, ncu dram__bytes_read+write (profiles/r01c_gemm_dram_traffic.json)",
+                    "traffic_note": "bytes per step over the same launches, ncu dram__bytes_read+write with cold caches per launch "
+                                    "(profiles/r02q_gemm_dram_traffic.json; in situ, caches kept: r02q_gemm_dram_traffic_in_situ.json)",
                     "launches_per_step": len(rec.calls), "avg_launch_us": 1e3 * gemm_ms / len(rec.calls),
                     "gemm_ms_per_step": gemm_ms, "gemm_flops_per_step": rec.flops, "peak_source": peak_src}
 
@@ -441,7 +465,15 @@ def run_ours(a):
 
     if rank == 0:
         from oracle import mae_oracle as O
-        f_fwd, f_step = O.flops_per_volume(O.CONFIGS[w["oracle"]], a.mask_ratio, kept_only_embed=True)
+        ocfg = O.CONFIGS[w["oracle"]]
+        f_fwd, f_step = O.flops_per_volume(ocfg, a.mask_ratio, kept_only_embed=True)
+        if contrastive:       # + the second view's encoder pass and the predictor on both views (two D x D Linear layers)
+            _, Lp, Pp = O.geometry(ocfg)
+            keep_p = int(Lp * (1 - a.mask_ratio))
+            Dp, Ne = ocfg["embed_dim"], keep_p + 1
+            embed = 2 * keep_p * Pp * Dp
+            enc = ocfg["depth"] * (24 * Ne * Dp * Dp + 4 * Ne * Ne * Dp)
+            f_step += 3 * (embed + enc) - embed + 3 * 2 * (2 * 2 * Ne * Dp * Dp)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -1803,13 +1803,17 @@ extern "C" int vitae_debug_set_attn_trace(void* buf) {
 }
 #endif
 
-static bool use_legacy() {
-    static const bool on = [] { const char* e = getenv("VITAE_ATTN_LEGACY"); return e && e[0] == '1'; }();
-    return on;
+// VITAE_ATTN_LEGACY=1: the round-1 mma.sync kernels for forward and backward; =bwd: for the backward only (A/B timing)
+static bool use_legacy(bool backward) {
+    static const int mode = [] {
+        const char* e = getenv("VITAE_ATTN_LEGACY");
+        return !e ? 0 : (e[0] == '1' ? 3 : (e[0] == 'b' ? 2 : (e[0] == 'f' ? 1 : 0)));
+    }();
+    return backward ? (mode & 2) != 0 : (mode & 1) != 0;
 }
 
 extern "C" int vitae_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, int hd, float scale, void* stream) {
-    if (use_legacy()) return attention_fwd_legacy(qkv, out, lse, B, N, H, hd, scale, stream);
+    if (use_legacy(false)) return attention_fwd_legacy(qkv, out, lse, B, N, H, hd, scale, stream);
     VITAE_REQUIRE(qkv && out && lse, "attention_fwd: null pointer");
     VITAE_REQUIRE(B > 0 && N > 0 && H > 0 && (hd == 16 || hd == 32 || hd == 64), "attention_fwd: unsupported shape B=%d N=%d H=%d hd=%d", B, N, H, hd);
     VITAE_REQUIRE((H * hd) % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
@@ -1840,7 +1844,7 @@ extern "C" int vitae_attention_fwd(const void* qkv, void* out, float* lse, int B
 
 extern "C" int vitae_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
                                    void* dqkv, int B, int N, int H, int hd, float scale, void* stream) {
-    if (use_legacy()) return attention_bwd_legacy(qkv, out, dout, lse, delta, dqkv, B, N, H, hd, scale, stream);
+    if (use_legacy(true)) return attention_bwd_legacy(qkv, out, dout, lse, delta, dqkv, B, N, H, hd, scale, stream);
     VITAE_REQUIRE(qkv && out && dout && lse && delta && dqkv, "attention_bwd: null pointer");
     VITAE_REQUIRE(B > 0 && N > 0 && H > 0 && (hd == 16 || hd == 32 || hd == 64), "attention_bwd: unsupported shape B=%d N=%d H=%d hd=%d", B, N, H, hd);
     VITAE_REQUIRE((H * hd) % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&

@@ -75,7 +75,7 @@ struct EpiLite {
     // EPI_PRED_MSE (decoder_pred GEMM + masked patch-reconstruction loss, vitae_gemm_pred_mse)
     const float* mse_vol;             // fp32 volume [B, 4, V, V, V], read in place
     const float* mse_mask;            // fp32 [B, L], 1 = removed patch
-    float* mse_part;                  // [2 * ceil(N / BN)][M] partial sums of squared errors per output row
+    float* mse_part;                  // [CTAs][epilogue warps] partial sums of squared errors
     int mse_V, mse_p, mse_g, mse_L;
     float mse_coef;                   // 2 / (P * sum(mask)): d recon / d pred before the upstream gradient
 };
@@ -450,8 +450,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             if (box_done) ++nbox;
         }
-        if (KIND == EPI_PRED_MSE && mrow < M)      // partial of this row over this warp's columns (0 for rows without loss)
-            ep.mse_part[(static_cast<size_t>(blockIdx.x) * 2 + half) * M + mrow] = active ? mse_rs : 0.f;
+        if (KIND == EPI_PRED_MSE) {                // one partial per epilogue warp: its 32 rows over its columns, fixed order
+            float r = (active && mrow < M) ? mse_rs : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+            if (lane == 0)
+                ep.mse_part[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * VITAE_EPI_WARPS + warp] = r;
+        }
         if (lane == 0) tma_store_wait_read<0>();   // the engine must have read our staging buffers before the CTA exits
         __syncwarp();
         tc_fence_before();
@@ -875,7 +880,7 @@ pred_mse_finalize_kernel(const float* __restrict__ part, long long n, float inv_
 }
 
 extern "C" size_t vitae_pred_mse_partial_floats(int M, int P, int tile_n) {
-    return static_cast<size_t>(2) * ceil_div(P, tile_n) * M;
+    return static_cast<size_t>(ceil_div(M, BM)) * ceil_div(P, tile_n) * VITAE_EPI_WARPS;
 }
 
 extern "C" int vitae_gemm_pred_mse(const void* hN, const void* W, const float* bias, int B, int L, int Dd, const float* vol,

@@ -842,7 +842,7 @@ class MAEEngine:
         # encoder blocks in groups of (about) 3, top first: the first group shares a stage with the decoder embed / encoder
         # norm, every further group is a stage of its own (finer slices near the end of backward leave less of the
         # gradient exchange exposed after the last kernel)
-        gsz = 3
+        gsz = max(1, int(os.environ.get("VITAE_DP_GROUP", "3")))
         enc_desc = list(reversed(range(self.enc.depth)))
         enc_groups = [enc_desc[k:k + gsz] for k in range(0, len(enc_desc), gsz)] or [[]]
         enc_hi, enc_rest = enc_groups[0], enc_groups[1:]
@@ -946,7 +946,8 @@ class MAEEngine:
 
         starts = [o for _, o in parts] + [self.flat.total]
         assert starts[0] == 0 and all(a < b for a, b in zip(starts, starts[1:])), "stage slices must tile the gradient buffer"
-        norm_parts = self.use_side_lane and not split and not encoder_only and len(parts) <= 16
+        norm_parts = (self.use_side_lane and not split and not encoder_only and len(parts) <= 16
+                      and os.environ.get("VITAE_NORM_PARTS", "0") == "1")   # opt-in: measured time-neutral (profiles/r02o_ab.txt)
 
         def joined(fns, with_norm=False):
             def run():

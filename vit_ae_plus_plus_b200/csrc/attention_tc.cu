@@ -383,6 +383,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __r
 // The two halves of a row exchange their maxima / sums through shared memory once per pass.  The linear block index is
 // decoded tile-major, so the ragged last query tile of every head is scheduled after all full tiles.
 constexpr int AT8_THREADS = 64 + 256;
+// backward kernels: eight softmax warps, the TMA producer, and one issuing thread PER MMA STREAM (an issuing thread pays
+// 100-200 cycles per tcgen05.mma / commit / barrier wait: with one thread for everything the dQ kernel needed ~15 such
+// operations per 64-column tile and was bound by them)
+constexpr int ATB_DQ_THREADS = 256 + 3 * 32;      // + producer, S/dP issuer, dQ issuer
+constexpr int ATB_DKV_THREADS = 256 + 4 * 32;     // + producer, S^T/dP^T issuer, dV issuer, dK issuer
 constexpr int KT8 = 128;
 struct Fwd8Smem {
     static constexpr int NSLOT = 3;                               // ring of 128-row kv tiles
@@ -1198,7 +1203,7 @@ struct DqSmem {
 };
 
 template <int HD>
-__global__ void __launch_bounds__(AT8_THREADS, 2)
+__global__ void __launch_bounds__(ATB_DQ_THREADS, 2)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                       const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                       const float* __restrict__ lse, float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int N, int H,
@@ -1230,13 +1235,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         const __nv_bfloat16* qkv_b = qkv + static_cast<size_t>(b) * N * pitch;
         for (int i = 0; i < tail_rows; ++i) {
             const size_t r = static_cast<size_t>(b) * N + q0 + i;
-            tail_row_dq<HD, AT8_THREADS>(qkv_b, pitch, qcol, kcol, vcol, out + r * D + h * HD, dout + r * D + h * HD,
+            tail_row_dq<HD, ATB_DQ_THREADS>(qkv_b, pitch, qcol, kcol, vcol, out + r * D + h * HD, dout + r * D + h * HD,
                                          lse[(static_cast<size_t>(b) * H + h) * N + q0 + i], q0 + i, N, scale, scale_log2,
                                          dqkv + r * pitch + qcol, delta + (static_cast<size_t>(b) * H + h) * N + q0 + i);
         }
         return;
     }
-    constexpr int PROD_WARP = 8, MMA_WARP = 9;      // after the eight softmax warps: the scheduler prefers high warp ids
+    constexpr int PROD_WARP = 8, MMA_WARP = 9, DQ_WARP = 10;   // after the eight softmax warps: the scheduler prefers high warp ids
     if (warp == PROD_WARP && lane == 0) {
         tma_prefetch_desc(&tmQKV);
         tma_prefetch_desc(&tmDO);
@@ -1286,7 +1291,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     } else if (warp == MMA_WARP) {
         if (lane == 0) {
             const uint32_t subq = (qcol & 63) * 2, subk = (kcol & 63) * 2, subv = (vcol & 63) * 2;
-            constexpr uint32_t idesc_dq = umma_idesc_bf16(QT, 64, 0u, 1u);
             uint32_t seq = 0;
             auto kv_wait = [&]() -> uint32_t {
                 const uint32_t slot = seq % S::NSLOT;
@@ -1294,19 +1298,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
                 ++seq;
                 return slot;
             };
-            auto issue_dq = [&](int u, uint32_t slot_k) {            // dQ += dS_u K_u
-                mbar_wait(ds_full, u & 1);
-                tc_fence_after();
-                const int nk = (u == T - 1 ? n16_last : KT) / 16;
-                const uint32_t sk = base + S::KV + slot_k * BOX_BYTES;
-#pragma unroll 1
-                for (int kk = 0; kk < nk; ++kk)
-                    umma_bf16(tmem_base + 128, desc_kmajor(base + S::DS, 0, kk), desc_mnmajor(sk, kk), idesc_dq, (u | kk) != 0);
-                umma_commit(kv_empty + slot_k * 8);
-                umma_commit(ds_free);
-            };
             mbar_wait(qdo_full, 0);
-            uint32_t prev_k = 0;
             for (int t = 0; t < T; ++t) {
                 const uint32_t slot_k = kv_wait();
                 const uint32_t slot_v = kv_wait();
@@ -1322,12 +1314,34 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
                     umma_bf16(tmem_base + 64, desc_kmajor(base + S::DO, subq, kk), desc_kmajor(sv, subv, kk), idesc, kk != 0);
                 umma_commit(kv_empty + slot_v * 8);
                 umma_commit(sdp_full);
-                if (t >= 1) issue_dq(t - 1, prev_k);
-                prev_k = slot_k;
             }
-            issue_dq(T - 1, prev_k);
-            umma_commit(dq_full);
             PDL_TRIGGER_LATE();
+        }
+        __syncwarp();
+    } else if (warp == DQ_WARP) {
+        // ---------------------------------------------------------------- second issuer: dQ += dS_t K_t
+        if (lane == 0) {
+            constexpr uint32_t idesc_dq = umma_idesc_bf16(QT, 64, 0u, 1u);
+            const uint64_t d_ds = desc_kmajor(base + S::DS, 0, 0);
+            for (int t = 0; t < T; ++t) {
+                const uint32_t slot_k = (2 * t) % S::NSLOT;              // K_t is the (2 t)-th box of the ring
+                mbar_wait(ds_full, t & 1);                               // implies S_t completed, i.e. K_t has landed
+                tc_fence_after();
+                const int nk = (t == T - 1 ? n16_last : KT) / 16;
+                const uint64_t d_k = desc_mnmajor(base + S::KV + slot_k * BOX_BYTES, 0);
+                if (nk == 4) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tmem_base + 128, d_ds + ((kk * 32) >> 4), d_k + ((kk * 2048) >> 4), idesc_dq, (t | kk) != 0);
+                } else {
+#pragma unroll 1
+                    for (int kk = 0; kk < nk; ++kk)
+                        umma_bf16(tmem_base + 128, d_ds + ((kk * 32) >> 4), d_k + ((kk * 2048) >> 4), idesc_dq, (t | kk) != 0);
+                }
+                umma_commit(kv_empty + slot_k * 8);
+                umma_commit(ds_free);
+            }
+            umma_commit(dq_full);
         }
         __syncwarp();
     } else {
@@ -1362,36 +1376,44 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
             const int nch = last ? n16_last / 16 : 4;
             mbar_wait(sdp_full, t & 1);
             tc_fence_after();
-            mbar_wait(ds_free, (t & 1) ^ 1);                 // dQ MMA of the previous tile has read the dS buffer
             {
-                uint32_t sv[2][16], dv[2][16];
-                if (warp_valid) {
+                // chunk-serial (a 16-column chunk of S and of dP at a time: 80 registers per thread with 352 threads x 2 CTAs):
+                // chunk 0 is reduced to eight packed registers before chunk 1 is read, and the score tiles are released to the
+                // S/dP issuer as soon as chunk 1 is in registers
+                uint32_t pk[2][8];
+                bool have[2] = {false, false};
 #pragma unroll
-                    for (int c = 0; c < 2; ++c)
-                        if (2 * half + c < nch) {
-                            tmem_ld_32x16(t_lane + (2 * half + c) * 16, sv[c]);
-                            tmem_ld_32x16(t_lane + 64 + (2 * half + c) * 16, dv[c]);
+                for (int c = 0; c < 2; ++c) {
+                    const int cc = 2 * half + c;
+                    have[c] = warp_valid && cc < nch;
+                    uint32_t sv[16], dv[16];
+                    if (have[c]) {
+                        tmem_ld_32x16(t_lane + cc * 16, sv);
+                        tmem_ld_32x16(t_lane + 64 + cc * 16, dv);
+                        tmem_ld_wait();
+                    }
+                    if (c == 1) {
+                        tc_fence_before();
+                        mbar_arrive(sdp_free);                   // this thread's part of both score tiles is in registers
+                    }
+                    if (have[c]) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            float p0 = ex2_approx(fmaf(__uint_as_float(sv[j]), scale_log2, -lse2));
+                            float p1 = ex2_approx(fmaf(__uint_as_float(sv[j + 1]), scale_log2, -lse2));
+                            if (last && cc * 16 + j >= nv_last) p0 = 0.f;
+                            if (last && cc * 16 + j + 1 >= nv_last) p1 = 0.f;
+                            pk[c][j >> 1] = pack_bf16(p0 * (__uint_as_float(dv[j]) - dl), p1 * (__uint_as_float(dv[j + 1]) - dl));
                         }
-                    tmem_ld_wait();
+                    }
                 }
-                tc_fence_before();
-                mbar_arrive(sdp_free);                       // this thread's part of both score tiles is in registers
-                if (warp_valid) {
+                mbar_wait(ds_free, (t & 1) ^ 1);                 // dQ MMA of the previous tile has read the dS buffer
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int cc = 2 * half + c;
-                        if (cc >= nch) continue;
-                        float ds[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float p = ex2_approx(fmaf(__uint_as_float(sv[c][j]), scale_log2, -lse2));
-                            if (last && cc * 16 + j >= nv_last) p = 0.f;
-                            ds[j] = p * (__uint_as_float(dv[c][j]) - dl);
-                        }
-                        at_sts128(base + S::DS + at_swz(row, 2 * cc), pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]),
-                                  pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
-                        at_sts128(base + S::DS + at_swz(row, 2 * cc + 1), pack_bf16(ds[8], ds[9]), pack_bf16(ds[10], ds[11]),
-                                  pack_bf16(ds[12], ds[13]), pack_bf16(ds[14], ds[15]));
+                for (int c = 0; c < 2; ++c) {
+                    const int cc = 2 * half + c;
+                    if (have[c]) {
+                        at_sts128(base + S::DS + at_swz(row, 2 * cc), pk[c][0], pk[c][1], pk[c][2], pk[c][3]);
+                        at_sts128(base + S::DS + at_swz(row, 2 * cc + 1), pk[c][4], pk[c][5], pk[c][6], pk[c][7]);
                     }
                 }
             }
@@ -1450,7 +1472,7 @@ struct DkvSmem {
 };
 
 template <int HD>
-__global__ void __launch_bounds__(AT8_THREADS, 2)
+__global__ void __launch_bounds__(ATB_DKV_THREADS, 2)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                        const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
                        const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int N, int H, int B, int tail_rows,
@@ -1484,13 +1506,13 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         const __nv_bfloat16* qkv_b = qkv + static_cast<size_t>(b) * N * pitch;
         for (int i = 0; i < tail_rows; ++i) {
             const size_t r = static_cast<size_t>(b) * N + kv0 + i;
-            tail_row_dkv<HD, AT8_THREADS>(qkv_b, pitch, qcol, kcol, vcol, dout + static_cast<size_t>(b) * N * D, D,
+            tail_row_dkv<HD, ATB_DKV_THREADS>(qkv_b, pitch, qcol, kcol, vcol, dout + static_cast<size_t>(b) * N * D, D,
                                           lse + (static_cast<size_t>(b) * H + h) * N, delta + (static_cast<size_t>(b) * H + h) * N,
                                           kv0 + i, N, scale, scale_log2, dqkv + r * pitch + kcol, dqkv + r * pitch + vcol, h * HD);
         }
         return;
     }
-    constexpr int PROD_WARP = 8, MMA_WARP = 9;      // after the eight softmax warps: the scheduler prefers high warp ids
+    constexpr int PROD_WARP = 8, MMA_WARP = 9, DV_WARP = 10, DK_WARP = 11;   // after the eight softmax warps
     if (warp == PROD_WARP && lane == 0) {
         tma_prefetch_desc(&tmQKV);
         tma_prefetch_desc(&tmDO);
@@ -1501,8 +1523,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         mbar_init(sdp_full, 1);
         mbar_init(sdp_free, 256);
         mbar_init(pds_full, 256);
-        mbar_init(pds_free, 1);
-        mbar_init(dkv_full, 1);
+        mbar_init(pds_free, 2);      // the dV and the dK issuer
+        mbar_init(dkv_full, 2);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -1540,7 +1562,6 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     } else if (warp == MMA_WARP) {
         if (lane == 0) {
             const uint32_t subq = (qcol & 63) * 2, subk = (kcol & 63) * 2, subv = (vcol & 63) * 2;
-            constexpr uint32_t idesc_acc = umma_idesc_bf16(QT, 64, 0u, 1u);
             uint32_t seq = 0;
             auto r_wait = [&]() -> uint32_t {
                 const uint32_t slot = seq % S::NSLOT;
@@ -1548,23 +1569,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
                 ++seq;
                 return slot;
             };
-            auto issue_dkv = [&](int u, uint32_t slot_q, uint32_t slot_do) {     // dV += P_u^T dO_u, dK += dS_u^T Q_u
-                mbar_wait(pds_full, u & 1);
-                tc_fence_after();
-                const int nk = (u == T - 1 ? n16_last : KT) / 16;
-                const uint32_t sq = base + S::RING + slot_q * BOX_BYTES, sdo = base + S::RING + slot_do * BOX_BYTES;
-#pragma unroll 1
-                for (int kk = 0; kk < nk; ++kk)
-                    umma_bf16(tmem_base + 192, desc_kmajor(base + S::PT, 0, kk), desc_mnmajor(sdo, kk), idesc_acc, (u | kk) != 0);
-#pragma unroll 1
-                for (int kk = 0; kk < nk; ++kk)
-                    umma_bf16(tmem_base + 128, desc_kmajor(base + S::DST, 0, kk), desc_mnmajor(sq, kk), idesc_acc, (u | kk) != 0);
-                umma_commit(r_empty + slot_q * 8);
-                umma_commit(r_empty + slot_do * 8);
-                umma_commit(pds_free);
-            };
             mbar_wait(kv_full, 0);
-            uint32_t prev_q = 0, prev_do = 0;
             for (int t = 0; t < T; ++t) {
                 const uint32_t slot_q = r_wait();
                 const uint32_t slot_do = r_wait();
@@ -1579,13 +1584,36 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
                 for (int kk = 0; kk < HD / 16; ++kk)     // dP^T = V dO_t^T
                     umma_bf16(tmem_base + 64, desc_kmajor(base + S::V, subv, kk), desc_kmajor(sdo, subq, kk), idesc, kk != 0);
                 umma_commit(sdp_full);
-                if (t >= 1) issue_dkv(t - 1, prev_q, prev_do);
-                prev_q = slot_q;
-                prev_do = slot_do;
             }
-            issue_dkv(T - 1, prev_q, prev_do);
-            umma_commit(dkv_full);
             PDL_TRIGGER_LATE();
+        }
+        __syncwarp();
+    } else if (warp == DV_WARP || warp == DK_WARP) {
+        // ---------------------------------------------------------------- dV += P_t^T dO_t   |   dK += dS_t^T Q_t
+        if (lane == 0) {
+            constexpr uint32_t idesc_acc = umma_idesc_bf16(QT, 64, 0u, 1u);
+            const bool is_dv = warp == DV_WARP;
+            const uint64_t d_a = desc_kmajor(base + (is_dv ? S::PT : S::DST), 0, 0);
+            const uint32_t acc = tmem_base + (is_dv ? 192 : 128);
+            for (int t = 0; t < T; ++t) {
+                const uint32_t slot = (2 * t + (is_dv ? 1 : 0)) % S::NSLOT;     // ring order: Q_t, dO_t
+                mbar_wait(pds_full, t & 1);                // implies S^T_t / dP^T_t completed, i.e. Q_t and dO_t have landed
+                tc_fence_after();
+                const int nk = (t == T - 1 ? n16_last : KT) / 16;
+                const uint64_t d_b = desc_mnmajor(base + S::RING + slot * BOX_BYTES, 0);
+                if (nk == 4) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(acc, d_a + ((kk * 32) >> 4), d_b + ((kk * 2048) >> 4), idesc_acc, (t | kk) != 0);
+                } else {
+#pragma unroll 1
+                    for (int kk = 0; kk < nk; ++kk)
+                        umma_bf16(acc, d_a + ((kk * 32) >> 4), d_b + ((kk * 2048) >> 4), idesc_acc, (t | kk) != 0);
+                }
+                umma_commit(r_empty + slot * 8);
+                umma_commit(pds_free);
+            }
+            umma_commit(dkv_full);
         }
         __syncwarp();
     } else {
@@ -1613,26 +1641,24 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
             const float* sd = s_del + (t & 1) * 64;
             mbar_wait(sdp_full, t & 1);
             tc_fence_after();
-            mbar_wait(pds_free, (t & 1) ^ 1);            // the dK / dV MMAs of the previous tile have read P^T / dS^T
             {
-                uint32_t sv[2][16], dv[2][16];
-                if (warp_valid) {
+                uint32_t pp[2][8], dd8[2][8];      // chunk-serial, as in the dQ kernel
+                bool have[2] = {false, false};
 #pragma unroll
-                    for (int c = 0; c < 2; ++c)
-                        if (2 * half + c < nch) {
-                            tmem_ld_32x16(t_lane + (2 * half + c) * 16, sv[c]);
-                            tmem_ld_32x16(t_lane + 64 + (2 * half + c) * 16, dv[c]);
-                        }
-                    tmem_ld_wait();
-                }
-                tc_fence_before();
-                mbar_arrive(sdp_free);
-                if (warp_valid) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int cc = 2 * half + c;
-                        if (cc >= nch) continue;
-                        uint32_t pp[8], dd8[8];
+                for (int c = 0; c < 2; ++c) {
+                    const int cc = 2 * half + c;
+                    have[c] = warp_valid && cc < nch;
+                    uint32_t sv[16], dv[16];
+                    if (have[c]) {
+                        tmem_ld_32x16(t_lane + cc * 16, sv);
+                        tmem_ld_32x16(t_lane + 64 + cc * 16, dv);
+                        tmem_ld_wait();
+                    }
+                    if (c == 1) {
+                        tc_fence_before();
+                        mbar_arrive(sdp_free);
+                    }
+                    if (have[c]) {
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
                             const float4 l4 = *reinterpret_cast<const float4*>(sl + cc * 16 + 4 * j4);
@@ -1642,16 +1668,23 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const int j = 4 * j4 + e;
-                                p[e] = ex2_approx(fmaf(__uint_as_float(sv[c][j]), scale_log2, -lv[e]));
-                                ds[e] = p[e] * (__uint_as_float(dv[c][j]) - dd[e]);
+                                p[e] = ex2_approx(fmaf(__uint_as_float(sv[j]), scale_log2, -lv[e]));
+                                ds[e] = p[e] * (__uint_as_float(dv[j]) - dd[e]);
                             }
-                            pp[2 * j4] = pack_bf16(p[0], p[1]); pp[2 * j4 + 1] = pack_bf16(p[2], p[3]);
-                            dd8[2 * j4] = pack_bf16(ds[0], ds[1]); dd8[2 * j4 + 1] = pack_bf16(ds[2], ds[3]);
+                            pp[c][2 * j4] = pack_bf16(p[0], p[1]); pp[c][2 * j4 + 1] = pack_bf16(p[2], p[3]);
+                            dd8[c][2 * j4] = pack_bf16(ds[0], ds[1]); dd8[c][2 * j4 + 1] = pack_bf16(ds[2], ds[3]);
                         }
-                        at_sts128(base + S::PT + at_swz(row, 2 * cc), pp[0], pp[1], pp[2], pp[3]);
-                        at_sts128(base + S::PT + at_swz(row, 2 * cc + 1), pp[4], pp[5], pp[6], pp[7]);
-                        at_sts128(base + S::DST + at_swz(row, 2 * cc), dd8[0], dd8[1], dd8[2], dd8[3]);
-                        at_sts128(base + S::DST + at_swz(row, 2 * cc + 1), dd8[4], dd8[5], dd8[6], dd8[7]);
+                    }
+                }
+                mbar_wait(pds_free, (t & 1) ^ 1);        // the dK / dV MMAs of the previous tile have read P^T / dS^T
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int cc = 2 * half + c;
+                    if (have[c]) {
+                        at_sts128(base + S::PT + at_swz(row, 2 * cc), pp[c][0], pp[c][1], pp[c][2], pp[c][3]);
+                        at_sts128(base + S::PT + at_swz(row, 2 * cc + 1), pp[c][4], pp[c][5], pp[c][6], pp[c][7]);
+                        at_sts128(base + S::DST + at_swz(row, 2 * cc), dd8[c][0], dd8[c][1], dd8[c][2], dd8[c][3]);
+                        at_sts128(base + S::DST + at_swz(row, 2 * cc + 1), dd8[c][4], dd8[c][5], dd8[c][6], dd8[c][7]);
                     }
                 }
             }
@@ -1774,11 +1807,11 @@ static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const void*
     int q_tiles, tail_rows;
     res_tiling(N, &q_tiles, &tail_rows);
     const dim3 grid((q_tiles + (tail_rows ? 1 : 0)) * H * B);
-    launch_kernel(attn_bwd_dq_tc_kernel<HD>, grid, dim3(AT8_THREADS), DqSmem::TOTAL, st, tq, tdo,
+    launch_kernel(attn_bwd_dq_tc_kernel<HD>, grid, dim3(ATB_DQ_THREADS), DqSmem::TOTAL, st, tq, tdo,
                   static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(out),
                   static_cast<const __nv_bfloat16*>(dout), lse, delta, static_cast<__nv_bfloat16*>(dqkv), N, H, B, tail_rows, scale, sl2);
     VITAE_CHECK_LAUNCH("attention_bwd_dq");
-    launch_kernel(attn_bwd_dkv_tc_kernel<HD>, grid, dim3(AT8_THREADS), DkvSmem::TOTAL, st, tq, tdo,
+    launch_kernel(attn_bwd_dkv_tc_kernel<HD>, grid, dim3(ATB_DKV_THREADS), DkvSmem::TOTAL, st, tq, tdo,
                   static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), lse,
                   static_cast<const float*>(delta), static_cast<__nv_bfloat16*>(dqkv), N, H, B, tail_rows, scale, sl2);
     VITAE_CHECK_LAUNCH("attention_bwd_dkv");

@@ -278,6 +278,9 @@ def run_ours(a):
                                     [torch.rand(2, 64, generator=gchk) for _ in range(4)], opt_steps=4)
         assert dp_check["ok"], f"data-parallel self-check failed: {dp_check}"
         del chk
+        import gc
+        gc.collect()                 # the throw-away model (graphs, peer mappings) goes away here, not inside a later capture
+        torch.cuda.synchronize()
 
     contrastive = bool(w.get("contrastive"))
     if contrastive:
@@ -333,6 +336,13 @@ def run_ours(a):
     ms_total = t.item()
     value = eff_batch * a.steps / (ms_total / 1e3)
     final_loss = last.item()
+    # how the replicas exchanged gradients: sharded step over NVLink peer memory (dp.ShardedStep) or all-reduce + replicated AdamW
+    dp_mode = None
+    if world > 1:
+        from vit_ae_plus_plus_b200 import dp
+        sh = model.engine().flat.sharded
+        dp_mode = "sharded step (owner-side reduce + AdamW shard + fused all-gather over peer memory)" \
+            if sh is not None and sh.steps > 0 else f"all-reduce ({dp.exchange_dtype()}) + replicated AdamW"
 
     # ---- e2e: host buffers; every step's batch crosses PCIe (pinned host memory -> device, prefetched one step ahead on
     # a copy stream by the package's DevicePrefetcher, the same wrapper train_one_stage_epoch puts around the DataLoader)
@@ -484,7 +494,7 @@ def run_ours(a):
                        "algorithmic_gflop_per_volume": f_step / 1e9,
                        "step_tflops": value * f_step / 1e12},
             "final_loss": final_loss, "e2e": e2e, "e2e_f32_ingest": e2e_f32, "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": roofline, "cpu_baseline": cpu, "dp_check": dp_check,
+            "roofline": roofline, "cpu_baseline": cpu, "dp_check": dp_check, "dp_mode": dp_mode,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

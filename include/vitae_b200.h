@@ -277,6 +277,39 @@ int vitae_adamw_flat(float* param, const float* grad, float* exp_avg, float* exp
                      long long n, const unsigned char* group_of_chunk, const float* hyper, int ngroups,
                      const float* ctl, int max_blocks, void* stream);
 
+/* Data parallel, sharded optimizer step over NVLink peer memory (replaces "all-reduce the gradients, then run
+ * the same AdamW on every rank" -- the reference itself has no distributed step: its scripts never wrap the model in DDP,
+ * k_fold_cross_valid_combined_brats.py:154).  The flat gradient / master / shadow buffers of all ranks are symmetric
+ * allocations mapped into every rank's address space; *_ptrs[r] = rank r's base address of the buffer (2 <= world <= 8).
+ * Ownership is block-cyclic and never changes: granule q = elements [q << granule_shift, (q + 1) << granule_shift) belongs to
+ * rank q % world, so every slice [lo, hi) of the flat index space (multiples of 64; the backward's stage slices) splits
+ * evenly.  All calls below work on rank `rank`'s part of [lo, hi):
+ *   vitae_dp_owned_elems: how many elements that is;
+ *   vitae_dp_reduce_shard: own gradient copy := inv_world * sum over ranks (peer copies pulled with plain loads over NVLink,
+ *     summed in rank order); partials[vitae_dp_reduce_shard_blocks(...)] = per-block sums of squares of the result (0 blocks:
+ *     the rank owns nothing of the slice and nothing is launched);
+ *   vitae_sum_partials: out[0] = sum of n partials (accumulated in double): each rank publishes one value;
+ *   vitae_optim_finalize_peers: vitae_optim_finalize over npartials values from EACH rank's partial buffer
+ *     (partial_ptrs[r], read over NVLink, summed rank-major in double: every rank computes the same control block);
+ *   vitae_adamw_shard: vitae_adamw_flat (grad / exp_avg / exp_avg_sq / group_of_chunk / f32_chunk: this rank's whole flat
+ *     buffers, element 0), then the all-gather from inside the same kernel: the new bf16 shadow is stored into every rank's
+ *     shadow buffer, the new fp32 master into this rank's and -- for the 64-element chunks with f32_chunk[chunk] != 0 (tensors
+ *     the kernels read in fp32: biases, LayerNorm affine, tokens) -- into every peer's.  The moments, and the fp32 master of
+ *     the other chunks, stay with the owner.
+ * The caller orders these against the other ranks (a cross-rank barrier before the reduce, before the finalize and after
+ * the update). */
+long long vitae_dp_owned_elems(long long lo, long long hi, int granule_shift, int world, int rank);
+int vitae_dp_reduce_shard_blocks(long long lo, long long hi, int granule_shift, int world, int rank, int max_blocks);
+int vitae_dp_reduce_shard(void* const* grad_ptrs, int world, int rank, long long lo, long long hi, int granule_shift,
+                          float inv_world, float* partials, int max_blocks, void* stream);
+int vitae_sum_partials(const float* partials, int n, float* out, void* stream);
+int vitae_optim_finalize_peers(void* const* partial_ptrs, int world, int npartials, float* ctl, float growth_factor,
+                               float backoff_factor, int growth_interval, int use_scaler, void* stream);
+int vitae_adamw_shard(void* const* param_ptrs, void* const* param_bf16_ptrs, int world, int rank, long long lo, long long hi,
+                      int granule_shift, const float* grad, float* exp_avg, float* exp_avg_sq,
+                      const unsigned char* group_of_chunk, const unsigned char* f32_chunk, const float* hyper, int ngroups,
+                      const float* ctl, int max_blocks, void* stream);
+
 /* decoder_pred (model/vit_autoenc.py:198) with the masked patch-reconstruction loss (:226-227, utils/custom_loss.py's role in
  * the north star) fused into its epilogue.  hN bf16 [B*(L+1), Dd] (decoder_norm output, cls row first per sample), W bf16
  * [P, Dd], bias fp32 [P], P = p^3 * C with C == 4 and p % 8 == 0; vol fp32 [B, C, V, V, V] read in place; mask fp32 [B, L];

@@ -100,6 +100,13 @@ SIGNATURES = {
     "vitae_optim_finalize": (c_int, [c_void_p, c_int, c_void_p, c_float, c_float, c_int, c_int, c_void_p]),
     "vitae_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_int,
                                  c_void_p, c_int, c_void_p]),
+    "vitae_dp_owned_elems": (c_longlong, [c_longlong, c_longlong, c_int, c_int, c_int]),
+    "vitae_dp_reduce_shard_blocks": (c_int, [c_longlong, c_longlong, c_int, c_int, c_int, c_int]),
+    "vitae_dp_reduce_shard": (c_int, [c_void_p, c_int, c_int, c_longlong, c_longlong, c_int, c_float, c_void_p, c_int, c_void_p]),
+    "vitae_adamw_shard": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_longlong, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "vitae_sum_partials": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "vitae_optim_finalize_peers": (c_int, [c_void_p, c_int, c_int, c_void_p, c_float, c_float, c_int, c_int, c_void_p]),
     "vitae_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "vitae_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "vitae_bn_relu_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,

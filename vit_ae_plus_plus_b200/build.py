@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libvitae_b200.so")
 BUILD_DIR = os.path.join(PKG_DIR, "csrc", "build")
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "layernorm.cu", "token_ops.cu", "loss.cu", "edge_loss.cu", "ingest.cu", "predictor.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention.cu", "attention_tc.cu", "layernorm.cu", "token_ops.cu", "loss.cu", "edge_loss.cu", "ingest.cu", "predictor.cu", "dp_probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-warn-spills"]
 

@@ -153,6 +153,24 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));      // FMNMX3 (sm_100+)
     return r;
 }
+// NVLink SHARP (NVLS) through a multicast mapping: one load returns the SUM over every GPU's copy of the address (the
+// NVSwitch reduces in flight), one store lands in every GPU's copy.
+__device__ __forceinline__ float4 multimem_ld_reduce_add_f32x4(const float* mc_addr) {
+    float4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(mc_addr)
+                 : "memory");
+    return r;
+}
+__device__ __forceinline__ void multimem_st_f32x4(float* mc_addr, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void multimem_st_bf16x4(void* mc_addr, uint32_t lo, uint32_t hi) {
+    asm volatile("multimem.st.relaxed.sys.global.v2.bf16x2 [%0], {%1, %2};" ::"l"(mc_addr), "r"(lo), "r"(hi) : "memory");
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

@@ -348,14 +348,39 @@ grad_sqnorm_kernel(const float* __restrict__ g, long long n, float* __restrict__
     }
 }
 
+// sum of n fp32 partials in double -> out[0] (fp32): the sharded step publishes ONE value per rank to its peers
 __global__ void __launch_bounds__(256)
-optim_finalize_kernel(const float* __restrict__ partials, int nblk, float* __restrict__ ctl, float growth_factor,
+sum_partials_kernel(const float* __restrict__ in, int n, float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += static_cast<double>(in[i]);
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = static_cast<float>(sh[0]);
+}
+
+// nsrc > 1 (data parallel, sharded step): nblk partials from each of the ranks' buffers (peer memory), summed in a fixed
+// order so that every rank arrives at the same control block.
+struct PartialSources {
+    const float* src[8];
+};
+__global__ void __launch_bounds__(256)
+optim_finalize_kernel(const PartialSources ps, int nsrc, int nblk, float* __restrict__ ctl, float growth_factor,
                       float backoff_factor, int growth_interval, int use_scaler) {
     pdl_trigger();
     pdl_wait();
     __shared__ double sh[256];
     double s = 0.0;
-    for (int i = threadIdx.x; i < nblk; i += 256) s += static_cast<double>(partials[i]);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+        if (r < nsrc)
+            for (int i = threadIdx.x; i < nblk; i += 256) s += static_cast<double>(__ldcv(ps.src[r] + i));
     sh[threadIdx.x] = s;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
@@ -394,14 +419,10 @@ optim_finalize_kernel(const float* __restrict__ partials, int nblk, float* __res
 struct AdamHyper {
     float h[8][8];
 };
-__global__ void __launch_bounds__(256)
-adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                  __nv_bfloat16* __restrict__ p16, long long n, const unsigned char* __restrict__ group_of_chunk,
-                  const AdamHyper hyper, int ngroups, const float* __restrict__ ctl) {
-    pdl_trigger();
-    pdl_wait();
-    __shared__ float hs[8][8];   // per group: lr*wd factor, b1, b2, eps, step_size, inv_sqrt_bc2
-    if (ctl[2] != 0.f) return;   // inf / nan gradients: GradScaler skips the step
+struct AdamCoef {
+    float decay, b1, b2, eps, step_size, isb2;
+};
+__device__ __forceinline__ void adam_prologue(float (*hs)[8], const AdamHyper& hyper, int ngroups, const float* ctl) {
     if (threadIdx.x < ngroups) {
         const float* h = hyper.h[threadIdx.x];
         const double step = static_cast<double>(ctl[5]);
@@ -415,27 +436,41 @@ adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
         hs[threadIdx.x][5] = static_cast<float>(1.0 / sqrt(bc2));
     }
     __syncthreads();
+}
+// torch.optim.AdamW update order, four elements
+__device__ __forceinline__ void adam_update4(float4& pp, const float4& gg, float4& mm, float4& vv, const float* c, float is) {
+    const float decay = c[0], b1 = c[1], b2 = c[2], eps = c[3], step_size = c[4], isb2 = c[5];
+    float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float gr = ga[k] * is;
+        pa[k] *= decay;
+        ma[k] = b1 * ma[k] + (1.f - b1) * gr;
+        va[k] = b2 * va[k] + (1.f - b2) * gr * gr;
+        pa[k] -= step_size * ma[k] / (sqrtf(va[k]) * isb2 + eps);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                  __nv_bfloat16* __restrict__ p16, long long n, const unsigned char* __restrict__ group_of_chunk,
+                  const AdamHyper hyper, int ngroups, const float* __restrict__ ctl) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float hs[8][8];   // per group: lr*wd factor, b1, b2, eps, step_size, inv_sqrt_bc2
+    if (ctl[2] != 0.f) return;   // inf / nan gradients: GradScaler skips the step
+    adam_prologue(hs, hyper, ngroups, ctl);
     const float is = ctl[3];
     const long long n4 = n >> 2;   // n is a multiple of 64
     for (long long i4 = blockIdx.x * 256ll + threadIdx.x; i4 < n4; i4 += gridDim.x * 256ll) {
         const long long i = i4 << 2;
         const int grp = group_of_chunk[i >> 6];
         if (grp >= ngroups) continue;           // padding / frozen chunk
-        const float decay = hs[grp][0], b1 = hs[grp][1], b2 = hs[grp][2], eps = hs[grp][3], step_size = hs[grp][4],
-                    isb2 = hs[grp][5];
         float4 pp = *reinterpret_cast<float4*>(p + i);
         const float4 gg = __ldcs(reinterpret_cast<const float4*>(g + i));
         float4 mm = *reinterpret_cast<float4*>(m + i);
         float4 vv = *reinterpret_cast<float4*>(v + i);
-        float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float gr = ga[k] * is;
-            pa[k] *= decay;
-            ma[k] = b1 * ma[k] + (1.f - b1) * gr;
-            va[k] = b2 * va[k] + (1.f - b2) * gr * gr;
-            pa[k] -= step_size * ma[k] / (sqrtf(va[k]) * isb2 + eps);
-        }
+        adam_update4(pp, gg, mm, vv, hs[grp], is);
         *reinterpret_cast<float4*>(p + i) = pp;
         *reinterpret_cast<float4*>(m + i) = mm;
         *reinterpret_cast<float4*>(v + i) = vv;
@@ -444,6 +479,129 @@ adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
             pk.x = pack_bf16(pp.x, pp.y);
             pk.y = pack_bf16(pp.z, pp.w);
             *reinterpret_cast<uint2*>(p16 + i) = pk;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Data parallel, sharded optimizer step over NVLink peer memory (dp.ShardedStep).  Every rank's flat gradient / master /
+// shadow buffers are symmetric allocations mapped into every other rank's address space; DpPeers carries the ranks' base
+// addresses of one such buffer (index = rank).  Ownership is block-cyclic and fixed for the life of the buffers: granule q
+// (2^gshift elements) belongs to rank q % world, so any slice [lo, hi) of the flat index space -- the backward's stage
+// slices -- splits evenly and an element never changes its owner.
+// ---------------------------------------------------------------------------------------------------------------
+struct DpPeers {
+    void* base[8];
+};
+struct DpRange {          // this rank's part of the slice [lo, hi): granules q0, q0 + world, ... (nq of them)
+    long long lo, hi, q0, nq;
+    int gshift, world;
+};
+// element index of vector `t` (VEC elements each) of this rank's part, or -1 outside [lo, hi)
+template <int VEC>
+__device__ __forceinline__ long long dp_elem(const DpRange& rg, long long t) {
+    const int vshift = rg.gshift - (VEC == 8 ? 3 : 2);
+    const long long q = rg.q0 + (t >> vshift) * rg.world;
+    const long long e = (q << rg.gshift) + ((t & ((1ll << vshift) - 1)) * VEC);
+    return (e >= rg.lo && e < rg.hi) ? e : -1;
+}
+
+// this rank's part of the MEAN gradient: own copy + the peers' copies, pulled over NVLink with plain loads in rank order
+// (every element is reduced by exactly one rank, so the replicas cannot diverge); the result replaces this rank's copy; its
+// per-block sums of squares go to partials (vitae_optim_finalize_peers' input).
+template <int W>
+__global__ void __launch_bounds__(256)
+dp_reduce_shard_kernel(const DpPeers peers, float* __restrict__ own, const DpRange rg, float inv_world,
+                       float* __restrict__ partials) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float sh[8];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const long long nt = rg.nq << (rg.gshift - 2);
+    constexpr int U = W <= 2 ? 4 : 2;      // elements in flight per thread: U * W 16-byte loads
+    const long long stride = gridDim.x * 256ll;
+    for (long long t0 = blockIdx.x * 256ll + threadIdx.x; t0 < nt; t0 += stride * U) {
+        float4 x[U][W];
+        long long e[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long t = t0 + u * stride;
+            e[u] = t < nt ? dp_elem<4>(rg, t) : -1;
+            if (e[u] >= 0) {
+#pragma unroll
+                for (int r = 0; r < W; ++r)
+                    x[u][r] = __ldcs(reinterpret_cast<const float4*>(static_cast<const float*>(peers.base[r]) + e[u]));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (e[u] >= 0) {
+                float4 s = x[u][0];
+#pragma unroll
+                for (int r = 1; r < W; ++r) { s.x += x[u][r].x; s.y += x[u][r].y; s.z += x[u][r].z; s.w += x[u][r].w; }
+                s.x *= inv_world; s.y *= inv_world; s.z *= inv_world; s.w *= inv_world;
+                *reinterpret_cast<float4*>(own + e[u]) = s;
+                a0 += s.x * s.x; a1 += s.y * s.y; a2 += s.z * s.z; a3 += s.w * s.w;
+            }
+        }
+    }
+    float t = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float r = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) r += sh[w];
+        partials[blockIdx.x] = r;
+    }
+}
+
+// AdamW over this rank's part of [lo, hi) (moments local to the owner), then the all-gather in the same kernel: the new
+// bf16 shadow goes to every rank; the fp32 master goes to the peers only for the chunks flagged in f32_chunk (tensors the
+// kernels read in fp32 on every rank: biases, LayerNorm affine, tokens) -- the peers' masters of the big GEMM weights go
+// stale and are pulled from their owner on demand (dp.ShardedStep.sync_master).  Eight elements per thread: 16-byte
+// NVLink stores of the shadow.
+template <int W>
+__global__ void __launch_bounds__(256)
+adamw_shard_kernel(const DpPeers p32s, const DpPeers p16s, int rank, float* __restrict__ p, const DpRange rg,
+                   const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                   const unsigned char* __restrict__ group_of_chunk, const unsigned char* __restrict__ f32_chunk,
+                   const AdamHyper hyper, int ngroups, const float* __restrict__ ctl) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float hs[8][8];
+    if (ctl[2] != 0.f) return;   // skipped step: nothing changes on any rank
+    adam_prologue(hs, hyper, ngroups, ctl);
+    const float is = ctl[3];
+    const long long nt = rg.nq << (rg.gshift - 3);
+    for (long long t = blockIdx.x * 256ll + threadIdx.x; t < nt; t += gridDim.x * 256ll) {
+        const long long i = dp_elem<8>(rg, t);
+        if (i < 0) continue;
+        const long long chunk = i >> 6;
+        const int grp = group_of_chunk[chunk];
+        if (grp >= ngroups) continue;
+        float4 pa = *reinterpret_cast<float4*>(p + i), pb = *reinterpret_cast<float4*>(p + i + 4);
+        const float4 ga = __ldcs(reinterpret_cast<const float4*>(g + i)), gb = __ldcs(reinterpret_cast<const float4*>(g + i + 4));
+        float4 ma = *reinterpret_cast<float4*>(m + i), mb = *reinterpret_cast<float4*>(m + i + 4);
+        float4 va = *reinterpret_cast<float4*>(v + i), vb = *reinterpret_cast<float4*>(v + i + 4);
+        adam_update4(pa, ga, ma, va, hs[grp], is);
+        adam_update4(pb, gb, mb, vb, hs[grp], is);
+        *reinterpret_cast<float4*>(m + i) = ma; *reinterpret_cast<float4*>(m + i + 4) = mb;
+        *reinterpret_cast<float4*>(v + i) = va; *reinterpret_cast<float4*>(v + i + 4) = vb;
+        uint4 pk;
+        pk.x = pack_bf16(pa.x, pa.y); pk.y = pack_bf16(pa.z, pa.w);
+        pk.z = pack_bf16(pb.x, pb.y); pk.w = pack_bf16(pb.z, pb.w);
+        const bool wide = f32_chunk[chunk] != 0;
+#pragma unroll
+        for (int r = 0; r < W; ++r) {
+            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p16s.base[r]) + i) = pk;
+            if (r == rank || wide) {
+                float* q = static_cast<float*>(p32s.base[r]) + i;
+                *reinterpret_cast<float4*>(q) = pa;
+                *reinterpret_cast<float4*>(q + 4) = pb;
+            }
         }
     }
 }
@@ -637,7 +795,9 @@ extern "C" int vitae_optim_prepare(const float* grad, long long n, const float* 
         VITAE_CHECK_LAUNCH("grad_sqnorm");
         blocks += blocks2;
     }
-    launch_kernel(optim_finalize_kernel, dim3(1), dim3(256), 0, as_stream(stream), static_cast<const float*>(workspace), blocks, ctl, growth_factor, backoff_factor, growth_interval, use_scaler);
+    PartialSources ps{};
+    ps.src[0] = workspace;
+    launch_kernel(optim_finalize_kernel, dim3(1), dim3(256), 0, as_stream(stream), ps, 1, blocks, ctl, growth_factor, backoff_factor, growth_interval, use_scaler);
     VITAE_CHECK_LAUNCH("optim_finalize");
     return 0;
 }
@@ -661,9 +821,32 @@ extern "C" int vitae_grad_sqnorm(const float* grad, long long n, float* partials
 extern "C" int vitae_optim_finalize(const float* partials, int npartials, float* ctl, float growth_factor, float backoff_factor,
                                     int growth_interval, int use_scaler, void* stream) {
     VITAE_REQUIRE(partials && ctl && npartials > 0, "optim_finalize: bad arguments");
-    launch_kernel(optim_finalize_kernel, dim3(1), dim3(256), 0, as_stream(stream), partials, npartials, ctl, growth_factor,
+    PartialSources ps{};
+    ps.src[0] = partials;
+    launch_kernel(optim_finalize_kernel, dim3(1), dim3(256), 0, as_stream(stream), ps, 1, npartials, ctl, growth_factor,
                   backoff_factor, growth_interval, use_scaler);
     VITAE_CHECK_LAUNCH("optim_finalize");
+    return 0;
+}
+
+extern "C" int vitae_sum_partials(const float* partials, int n, float* out, void* stream) {
+    VITAE_REQUIRE(partials && out && n > 0, "sum_partials: bad arguments");
+    launch_kernel(sum_partials_kernel, dim3(1), dim3(256), 0, as_stream(stream), partials, n, out);
+    VITAE_CHECK_LAUNCH("sum_partials");
+    return 0;
+}
+
+extern "C" int vitae_optim_finalize_peers(void* const* partial_ptrs, int world, int npartials, float* ctl, float growth_factor,
+                                          float backoff_factor, int growth_interval, int use_scaler, void* stream) {
+    VITAE_REQUIRE(partial_ptrs && ctl && npartials > 0 && world >= 1 && world <= 8, "optim_finalize_peers: bad arguments");
+    PartialSources ps{};
+    for (int r = 0; r < world; ++r) {
+        VITAE_REQUIRE(partial_ptrs[r], "optim_finalize_peers: null pointer for rank %d", r);
+        ps.src[r] = static_cast<const float*>(partial_ptrs[r]);
+    }
+    launch_kernel(optim_finalize_kernel, dim3(1), dim3(256), 0, as_stream(stream), ps, world, npartials, ctl, growth_factor,
+                  backoff_factor, growth_interval, use_scaler);
+    VITAE_CHECK_LAUNCH("optim_finalize_peers");
     return 0;
 }
 
@@ -680,5 +863,116 @@ extern "C" int vitae_adamw_flat(float* param, const float* grad, float* exp_avg,
     launch_kernel(adamw_flat_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), param, grad, exp_avg, exp_avg_sq, static_cast<__nv_bfloat16*>(param_bf16), n,
                                                              group_of_chunk, hy, ngroups, ctl);
     VITAE_CHECK_LAUNCH("adamw_flat");
+    return 0;
+}
+
+template <int W>
+static void launch_dp_reduce(int blocks, cudaStream_t st, const DpPeers& peers, int rank, const DpRange& rg, float inv_world,
+                             float* partials) {
+    launch_kernel(dp_reduce_shard_kernel<W>, dim3(blocks), dim3(256), 0, st, peers, static_cast<float*>(peers.base[rank]), rg,
+                  inv_world, partials);
+}
+template <int W>
+static void launch_adamw_shard(int blocks, cudaStream_t st, const DpPeers& p32s, const DpPeers& p16s, int rank, const DpRange& rg,
+                               const float* g, float* m, float* v, const unsigned char* goc, const unsigned char* f32c,
+                               const AdamHyper& hy, int ngroups, const float* ctl) {
+    launch_kernel(adamw_shard_kernel<W>, dim3(blocks), dim3(256), 0, st, p32s, p16s, rank, static_cast<float*>(p32s.base[rank]), rg,
+                  g, m, v, goc, f32c, hy, ngroups, ctl);
+}
+#define DP_DISPATCH_WORLD(world, CALL)                                                            \
+    switch (world) {                                                                                \
+        case 2: CALL(2); break;                                                                     \
+        case 3: CALL(3); break;                                                                     \
+        case 4: CALL(4); break;                                                                     \
+        case 5: CALL(5); break;                                                                     \
+        case 6: CALL(6); break;                                                                     \
+        case 7: CALL(7); break;                                                                     \
+        case 8: CALL(8); break;                                                                     \
+        default: return set_error(-1, "data-parallel shard kernels: world size %d not in 2..8", world); \
+    }
+
+static int fill_peers(DpPeers& d, void* const* ptrs, int world, size_t align, const char* what) {
+    memset(&d, 0, sizeof(d));
+    for (int r = 0; r < world; ++r) {
+        if (!ptrs[r] || (reinterpret_cast<uintptr_t>(ptrs[r]) & (align - 1)))
+            return set_error(-1, "%s: peer pointer %d is null or not %zu-byte aligned", what, r, align);
+        d.base[r] = ptrs[r];
+    }
+    return 0;
+}
+
+// this rank's granules inside [lo, hi); false when it owns none
+static bool dp_range(DpRange& rg, long long lo, long long hi, int gshift, int world, int rank) {
+    rg.lo = lo; rg.hi = hi; rg.gshift = gshift; rg.world = world;
+    const long long qa = lo >> gshift, qb = (hi - 1) >> gshift;        // first / last granule touched
+    long long q0 = qa + ((rank - qa % world) % world + world) % world;
+    rg.q0 = q0;
+    rg.nq = q0 > qb ? 0 : (qb - q0) / world + 1;
+    return rg.nq > 0;
+}
+
+extern "C" long long vitae_dp_owned_elems(long long lo, long long hi, int granule_shift, int world, int rank) {
+    if (hi <= lo || world < 1 || rank < 0 || rank >= world || granule_shift < 6) return 0;
+    DpRange rg;
+    if (!dp_range(rg, lo, hi, granule_shift, world, rank)) return 0;
+    long long n = 0;
+    for (long long k = 0; k < rg.nq; ++k) {
+        const long long a = std::max(lo, (rg.q0 + k * world) << granule_shift);
+        const long long b = std::min(hi, ((rg.q0 + k * world) + 1) << granule_shift);
+        n += b - a;
+    }
+    return n;
+}
+
+extern "C" int vitae_dp_reduce_shard_blocks(long long lo, long long hi, int granule_shift, int world, int rank, int max_blocks) {
+    DpRange rg;
+    if (hi <= lo || !dp_range(rg, lo, hi, granule_shift, world, rank)) return 0;
+    const int cap = max_blocks > 0 ? std::min(max_blocks, OPT_NORM_BLOCKS) : OPT_NORM_BLOCKS;
+    return static_cast<int>(std::max<long long>(1, std::min<long long>(ceil_div<long long>(rg.nq << granule_shift, 2048), cap)));
+}
+
+extern "C" int vitae_dp_reduce_shard(void* const* grad_ptrs, int world, int rank, long long lo, long long hi, int granule_shift,
+                                     float inv_world, float* partials, int max_blocks, void* stream) {
+    VITAE_REQUIRE(grad_ptrs && partials && world >= 2 && world <= 8 && rank >= 0 && rank < world, "dp_reduce_shard: bad arguments");
+    VITAE_REQUIRE(hi > lo && lo >= 0 && lo % 64 == 0 && hi % 64 == 0 && granule_shift >= 6 && granule_shift <= 30,
+                  "dp_reduce_shard: [%lld, %lld) must be 64-aligned, granule shift %d in 6..30", lo, hi, granule_shift);
+    DpPeers peers;
+    if (int rc = fill_peers(peers, grad_ptrs, world, 16, "dp_reduce_shard")) return rc;
+    DpRange rg;
+    if (!dp_range(rg, lo, hi, granule_shift, world, rank)) return 0;       // nothing of this slice belongs to this rank
+    const int blocks = vitae_dp_reduce_shard_blocks(lo, hi, granule_shift, world, rank, max_blocks);
+    cudaStream_t st = as_stream(stream);
+#define CALL(W) launch_dp_reduce<W>(blocks, st, peers, rank, rg, inv_world, partials)
+    DP_DISPATCH_WORLD(world, CALL)
+#undef CALL
+    VITAE_CHECK_LAUNCH("dp_reduce_shard");
+    return 0;
+}
+
+extern "C" int vitae_adamw_shard(void* const* param_ptrs, void* const* param_bf16_ptrs, int world, int rank, long long lo,
+                                 long long hi, int granule_shift, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                 const unsigned char* group_of_chunk, const unsigned char* f32_chunk, const float* hyper,
+                                 int ngroups, const float* ctl, int max_blocks, void* stream) {
+    VITAE_REQUIRE(param_ptrs && param_bf16_ptrs && grad && exp_avg && exp_avg_sq && group_of_chunk && f32_chunk && hyper && ctl,
+                  "adamw_shard: null pointer");
+    VITAE_REQUIRE(world >= 2 && world <= 8 && rank >= 0 && rank < world, "adamw_shard: world=%d rank=%d", world, rank);
+    VITAE_REQUIRE(hi > lo && lo >= 0 && lo % 64 == 0 && hi % 64 == 0 && granule_shift >= 6 && granule_shift <= 30 && ngroups > 0 &&
+                      ngroups <= 8,
+                  "adamw_shard: [%lld, %lld) must be 64-aligned, granule shift %d in 6..30, 1..8 groups", lo, hi, granule_shift);
+    DpPeers p32s, p16s;
+    if (int rc = fill_peers(p32s, param_ptrs, world, 16, "adamw_shard(master)")) return rc;
+    if (int rc = fill_peers(p16s, param_bf16_ptrs, world, 16, "adamw_shard(shadow)")) return rc;
+    DpRange rg;
+    if (!dp_range(rg, lo, hi, granule_shift, world, rank)) return 0;
+    const int cap = max_blocks > 0 ? max_blocks : 148 * 8;
+    const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>(ceil_div<long long>(rg.nq << granule_shift, 2048), cap)));
+    AdamHyper hy;
+    memset(&hy, 0, sizeof(hy));
+    memcpy(hy.h, hyper, sizeof(float) * 8 * ngroups);
+    cudaStream_t st = as_stream(stream);
+#define CALL(W) launch_adamw_shard<W>(blocks, st, p32s, p16s, rank, rg, grad, exp_avg, exp_avg_sq, group_of_chunk, f32_chunk, hy, ngroups, ctl)
+    DP_DISPATCH_WORLD(world, CALL)
+#undef CALL
+    VITAE_CHECK_LAUNCH("adamw_shard");
     return 0;
 }

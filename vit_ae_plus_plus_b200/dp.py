@@ -117,6 +117,225 @@ class GradReducer:
         self.pending = []
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Sharded step over NVLink peer memory
+# ---------------------------------------------------------------------------------------------------------------------
+GRANULE_SHIFT = 16          # ownership granule: 2^16 elements (256 KB of fp32); granule q belongs to rank q % world
+# Symmetric allocations (and the rendezvous handles that map them into the peers) must not be destroyed at an arbitrary
+# moment: unmapping while some stream is being captured into a CUDA graph aborts the process.  Everything allocated here is
+# therefore kept alive in this registry together with a weak reference to its owner (the FlatParams object), and entries of
+# dead owners are dropped at the next allocation -- a point where this package is certainly not capturing.
+_symmetric_ptrs = set()
+_registry = []              # [weakref to the owner, [tensors / handles]]
+
+
+def _purge_registry() -> None:
+    dead = [e for e in _registry if e[0]() is None]
+    if not dead:
+        return
+    torch.cuda.synchronize()
+    for e in dead:
+        for obj in e[1]:
+            if isinstance(obj, torch.Tensor):
+                _symmetric_ptrs.discard(obj.data_ptr())
+        _registry.remove(e)
+    del dead
+
+
+def keep_alive(owner, objects) -> None:
+    """Ties symmetric tensors / rendezvous handles to ``owner``: they live at least as long as it does and are released
+    at a safe point afterwards."""
+    import weakref
+    for e in _registry:
+        if e[0]() is owner:
+            e[1].extend(objects)
+            return
+    _registry.append([weakref.ref(owner), list(objects)])
+
+
+def sharded_enabled() -> bool:
+    """The sharded step needs every rank of the job on one NVLink domain: an NCCL process group of 2..8 ranks on one node
+    (torchrun's LOCAL_WORLD_SIZE == WORLD_SIZE).  VITAE_DP_SHARDED=0 keeps the all-reduce + replicated AdamW path."""
+    if os.environ.get("VITAE_DP_SHARDED", "1") == "0":
+        return False
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_backend() != "nccl":
+        return False
+    w = dist.get_world_size()
+    if w < 2 or w > 8:
+        return False
+    return os.environ.get("LOCAL_WORLD_SIZE", str(w)) == str(w)
+
+
+def alloc_flat(n: int, dtype: torch.dtype, device, owner=None) -> torch.Tensor:
+    """Zero-filled flat buffer.  With the sharded step available it comes from torch's symmetric-memory allocator
+    (cuMemCreate + a mapping into every peer after ShardedStep's rendezvous: plumbing, like torch.empty) and is tied to
+    ``owner`` (keep_alive); else torch.zeros."""
+    device = torch.device(device)
+    if device.type == "cuda" and sharded_enabled() and owner is not None:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            _purge_registry()
+            t = symm_mem.empty(n, dtype=dtype, device=device)
+            t.zero_()
+            _symmetric_ptrs.add(t.data_ptr())
+            keep_alive(owner, [t])
+            return t
+        except Exception as e:      # noqa: BLE001 -- allocator not usable on this system: the NCCL path still works
+            import warnings
+            warnings.warn(f"symmetric allocation failed ({type(e).__name__}: {e}); using the all-reduce path")
+    return torch.zeros(n, dtype=dtype, device=device)
+
+
+def is_symmetric(t: torch.Tensor) -> bool:
+    return t.data_ptr() in _symmetric_ptrs
+
+
+class ShardedStep:
+    """Data-parallel optimizer step without an all-reduce and without replicated optimizer work.
+
+    all-reduce path:  backward || all-reduce(grads)  ->  every rank: AdamW over ALL parameters (0.69 ms for ViT-B)
+    sharded path:     backward || reduce of the OWNED part of each finished slice (vitae_dp_reduce_shard pulls the peers'
+                      copies over NVLink)  ->  barrier  ->  AdamW over the owned 1/world of the parameters with the
+                      all-gather fused in (vitae_adamw_shard stores the new bf16 shadow into every rank's buffer, fp32 only
+                      for the small tensors the kernels read in fp32)  ->  barrier.
+    NVLink bytes per rank and step: (world-1)/world * (4 + 2) bytes per parameter, against 2 * (world-1)/world * 4 for an
+    fp32 all-reduce; optimizer HBM traffic drops by the factor world.
+
+    What differs from a replicated step, by design: between steps the fp32 master of the large matrices and the Adam
+    moments are current only on their owner.  ``sync_master()`` / ``sync_moments()`` pull the missing parts from the owners
+    (peer reads, no collective; the model's / optimizer's ``state_dict()`` and ``FlatParams.refresh_shadow`` call them), and
+    ``.grad`` holds the mean gradient only in the owned part after ``backward``.
+
+    Cross-rank ordering uses the signal-pad barrier of the symmetric allocation (torch plumbing, one small kernel)."""
+
+    PART_CAP = 148 * 4            # partial sums per slice (vitae_dp_reduce_shard_blocks' cap)
+    MAX_SLICES = 24
+
+    def __init__(self, flat, m: torch.Tensor, v: torch.Tensor, group_map: torch.Tensor):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import ops
+        self.ops = ops
+        self.flat, self.m, self.v, self.group_map = flat, m, v, group_map
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        dev = flat.g32.device
+        # per-slice partial sums of squares, then (last 64 floats) their total: the one value the peers read
+        self.part = symm_mem.empty(self.MAX_SLICES * self.PART_CAP + 64, dtype=torch.float32, device=dev)
+        self.part.zero_()
+        self.part_total = self.part[self.MAX_SLICES * self.PART_CAP:]
+        group = dist.group.WORLD
+        self.h = {name: symm_mem.rendezvous(t, group) for name, t in
+                  (("g32", flat.g32), ("p32", flat.p32), ("p16", flat.p16), ("m", m), ("v", v), ("part", self.part))}
+        keep_alive(flat, [self.part, *self.h.values()])
+        self.peers = {name: ops.peer_table(h.buffer_ptrs) for name, h in self.h.items()}
+        self.peers["part_total"] = ops.peer_table([p + 4 * self.MAX_SLICES * self.PART_CAP for p in self.h["part"].buffer_ptrs])
+        # chunks whose fp32 master every rank needs: everything but the large matrices (only their bf16 shadow is read)
+        wide = torch.ones(flat.total // 64, dtype=torch.uint8)
+        for n in flat.order:
+            o, k, shp = flat.offsets[n]
+            if len(shp) >= 2 and k >= (1 << 16):
+                wide[o // 64:(o + k + 63) // 64] = 0
+        self.f32_chunk = wide.to(dev)
+        self.comm = torch.cuda.Stream(device=dev, priority=-1)
+        self.overlap_blocks = int(os.environ.get("VITAE_DP_REDUCE_BLOCKS", "96"))   # grid of a reduce that runs beside the backward
+        self.slices: List[Tuple[int, int]] = []      # slices reduced since the last step, in order
+        self.cursor = 0                              # partial sums written so far (PART_CAP per slice)
+        self.master_stale = False
+        self.moments_stale = False
+        self.steps = 0
+
+    # ---- reduce ----------------------------------------------------------------------------------------------------
+    def begin(self) -> None:
+        """Start of a backward whose gradients this object will reduce."""
+        self.slices, self.cursor = [], 0
+
+    def launch(self, t: torch.Tensor, overlap: bool = True, final: bool = False) -> None:
+        """Gradient slice ``t`` (a view of the flat gradient buffer) is final on the current stream: reduce the owned part.
+        overlap=True: on the communication stream with a small grid (the backward keeps running on the current stream);
+        final=True: nothing runs beside it any more, full grid."""
+        a = (t.data_ptr() - self.flat.g32.data_ptr()) // 4
+        b = a + t.numel()
+        k = len(self.slices)
+        if k >= self.MAX_SLICES:
+            raise RuntimeError("ShardedStep: too many gradient slices")
+        self.slices.append((a, b))
+        part = self.part[k * self.PART_CAP:(k + 1) * self.PART_CAP]
+        main = torch.cuda.current_stream()
+        if overlap:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(ev)
+                self._reduce(a, b, part, k, 0 if final else self.overlap_blocks)
+        else:
+            self._reduce(a, b, part, k, 0)
+
+    def _reduce(self, a: int, b: int, part: torch.Tensor, k: int, max_blocks: int) -> None:
+        part.zero_()                                  # ranks that own nothing of a slice contribute zeros
+        self.h["g32"].barrier(channel=k)              # every rank's copy of this slice is final
+        self.ops.dp_reduce_shard(self.peers["g32"], self.world, self.rank, a, b, GRANULE_SHIFT, 1.0 / self.world, part,
+                                 max_blocks)
+
+    def wait(self) -> None:
+        torch.cuda.current_stream().wait_stream(self.comm)
+
+    def reduce_all(self) -> None:
+        """Not overlapped: the whole gradient buffer at once, on the current stream."""
+        self.begin()
+        self.launch(self.flat.g32, overlap=False)
+
+    # ---- step ------------------------------------------------------------------------------------------------------
+    def step(self, ctl: torch.Tensor, rows, growth_factor: float, backoff_factor: float, growth_interval: int,
+             use_scaler: bool) -> None:
+        """GradScaler.unscale_/update + AdamW on the gradients reduced since begin(); on return (stream order) every rank's
+        bf16 shadow and small fp32 tensors are current."""
+        if not self.slices:
+            self.reduce_all()
+        covered = sum(b - a for a, b in self.slices)
+        if covered != self.flat.total:
+            raise RuntimeError(f"ShardedStep: reduced slices cover {covered} of {self.flat.total} gradient elements")
+        ops, W, r = self.ops, self.world, self.rank
+        ops.sum_partials(self.part, len(self.slices) * self.PART_CAP, self.part_total)
+        self.h["part"].barrier(channel=self.MAX_SLICES)          # every rank's total is written
+        ops.optim_finalize_peers(self.peers["part_total"], W, 1, ctl, growth_factor, backoff_factor, growth_interval,
+                                 use_scaler)
+        # one launch: ownership does not depend on how the backward sliced the buffer
+        ops.adamw_shard(self.peers["p32"], self.peers["p16"], W, r, 0, self.flat.total, GRANULE_SHIFT, self.flat.g32, self.m,
+                        self.v, self.group_map, self.f32_chunk, rows, ctl)
+        self.h["p16"].barrier(channel=self.MAX_SLICES + 1)       # every owner's stores have landed everywhere
+        self.slices, self.cursor = [], 0
+        self.master_stale = self.moments_stale = True
+        self.steps += 1
+
+    # ---- on-demand completion of the replicas ----------------------------------------------------------------------------
+    def _pull(self, name: str, local: torch.Tensor) -> None:
+        """local[granules owned by peers] := the owner's copy (peer reads over NVLink; the owners are not involved -- their
+        copies cannot change before this rank enters the next step's barriers)."""
+        h, W, G = self.h[name], self.world, 1 << GRANULE_SHIFT
+        total = local.numel()
+        nfull = total // G
+        for src in range(W):
+            if src == self.rank:
+                continue
+            remote = h.get_buffer(src, (total,), local.dtype, 0)
+            if nfull > src:
+                local[:nfull * G].view(nfull, G)[src::W].copy_(remote[:nfull * G].view(nfull, G)[src::W])
+            if total > nfull * G and nfull % W == src:      # the ragged last granule
+                local[nfull * G:].copy_(remote[nfull * G:])
+
+    def sync_master(self) -> None:
+        """fp32 master of the large matrices: fetch the parts other ranks own (they were updated there, only their bf16
+        shadow came here)."""
+        if self.master_stale:
+            self._pull("p32", self.flat.p32)
+            self.master_stale = False
+
+    def sync_moments(self) -> None:
+        if self.moments_stale:
+            self._pull("m", self.m)
+            self._pull("v", self.v)
+            self.moments_stale = False
+
+
 def replica_check(model, volumes, noises, opt_steps: int = 4) -> dict:
     """Self-check of the data-parallel path on the live process group (tests/dp_check.py under torchrun; bench.py runs it
     before the timed region of every N > 1 run and prints the result in its JSON line):
@@ -124,7 +343,9 @@ def replica_check(model, volumes, noises, opt_steps: int = 4) -> dict:
       2. ``backward`` with the staged, overlapped gradient exchange leaves in every rank's ``.grad`` the mean over ranks
          of the local gradients (compared with a ``no_sync`` backward + one explicit all-reduce), three times: eager
          launches, graph capture, graph replay;
-      3. after ``opt_steps`` fused GradScaler + AdamW steps on rank-local data the replicas are still bit-identical.
+      3. after ``opt_steps`` fused GradScaler + AdamW steps on rank-local data the replicas are still bit-identical (bf16
+         shadow and, after ``sync_master``, fp32 master); when those steps ran sharded (ShardedStep) the same steps are
+         repeated through all-reduce + replicated AdamW and the two results compared.
     ``volumes``: rank-local device batches; ``noises``: rank-local mask noise, one per step.  Restores nothing: call it
     on a throw-away model.  Returns the measured spreads / errors (all must be 0 except ``exchange_rel_err`` <= 1e-6)."""
     from .utils import misc
@@ -154,18 +375,42 @@ def replica_check(model, volumes, noises, opt_steps: int = 4) -> dict:
         out["exchange_rel_err"] = max(out["exchange_rel_err"],
                                       (got - ref).abs().max().item() / (ref.abs().max().item() + 1e-30))
         out["grad_spread_after_exchange"] = max(out["grad_spread_after_exchange"], spread(got))
-    opt = torch.optim.AdamW(misc.add_weight_decay(model, 0.05), lr=1e-3, betas=(0.9, 0.95))
-    scaler = misc.NativeScalerWithGradNormCount()
-    for i in range(opt_steps):
-        losses = model(volumes[i % len(volumes)], noise=noises[i % len(noises)])[0]
-        scaler(losses[0], opt, parameters=model.parameters(), update_grad=True)
-        opt.zero_grad()
+    p0 = eng.flat.p32.clone()
+
+    def run_steps(allow_sharded: bool):
+        opt = torch.optim.AdamW(misc.add_weight_decay(model, 0.05), lr=1e-3, betas=(0.9, 0.95))
+        scaler = misc.NativeScalerWithGradNormCount()
+        scaler.allow_sharded = allow_sharded
+        for i in range(opt_steps):
+            losses = model(volumes[i % len(volumes)], noise=noises[i % len(noises)])[0]
+            scaler(losses[0], opt, parameters=model.parameters(), update_grad=True)
+            opt.zero_grad()
+        return scaler, losses[0].item()
+
+    scaler, final_loss = run_steps(True)
+    sh = eng.flat.sharded
+    out["sharded"] = bool(sh is not None and sh.steps > 0)
+    out["shadow_spread_after_steps"] = spread(eng.flat.p16.float())      # what the kernels compute with
+    eng.sync_master()                                                    # sharded: complete the fp32 master first
     out["param_spread_after_steps"] = spread(eng.flat.p32)
     out["fused_optimizer"] = scaler._fused is not None
-    out["final_loss"] = losses[0].item()
+    out["final_loss"] = final_loss
     out["exchange_dtype"] = exchange_dtype()
+    out["sharded_vs_allreduce"] = None
+    if out["sharded"]:
+        # the same steps from the same start through all-reduce + replicated AdamW: mean |difference| of the parameters
+        # relative to the mean |update| (the reductions add in a different order, Adam normalises: not bit-identical)
+        p_sh = eng.flat.p32.clone()
+        with torch.no_grad():
+            eng.flat.p32.copy_(p0)
+        run_steps(False)
+        upd = (eng.flat.p32 - p0).abs().mean().item()
+        out["sharded_vs_allreduce"] = (p_sh - eng.flat.p32).abs().mean().item() / (upd + 1e-30)
+        out["param_spread_after_steps"] = max(out["param_spread_after_steps"], spread(eng.flat.p32))
     # fp32 exchange reproduces the explicit fp32 mean; bf16 exchange rounds every rank's slice to bf16 first (2^-9 relative)
     tol = 1e-6 if out["exchange_dtype"] == "fp32" else 1e-2
     out["ok"] = (out["param_spread_after_broadcast"] == 0.0 and out["grad_spread_after_exchange"] == 0.0
-                 and out["param_spread_after_steps"] == 0.0 and out["exchange_rel_err"] <= tol)
+                 and out["param_spread_after_steps"] == 0.0 and out["shadow_spread_after_steps"] == 0.0
+                 and out["exchange_rel_err"] <= tol
+                 and (out["sharded_vs_allreduce"] is None or out["sharded_vs_allreduce"] <= 1e-2))
     return out

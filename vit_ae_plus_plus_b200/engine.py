@@ -29,6 +29,7 @@ loss / gradients of parameters (BASELINE.json north_star tolerance for this mode
 """
 from __future__ import annotations
 
+import gc
 import math
 import os
 import weakref
@@ -93,9 +94,11 @@ class FlatParams:
             self.offsets[n] = (off, p.numel(), p.shape)
             off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         self.total = off
-        self.p32 = torch.zeros(off, dtype=_F32, device=device)
-        self.p16 = torch.zeros(off, dtype=_BF16, device=device)
-        self.g32 = torch.zeros(off, dtype=_F32, device=device)
+        # (data parallel on one NVLink domain: symmetric allocations, see dp.ShardedStep; plain torch.zeros otherwise)
+        self.p32 = dp.alloc_flat(off, _F32, device, owner=self)
+        self.p16 = dp.alloc_flat(off, _BF16, device, owner=self)
+        self.g32 = dp.alloc_flat(off, _F32, device, owner=self)
+        self.sharded = None           # dp.ShardedStep once the fused optimizer has set it up
         self.params = named_params
         self.v32: Dict[str, torch.Tensor] = {}
         self.v16: Dict[str, torch.Tensor] = {}
@@ -128,6 +131,8 @@ class FlatParams:
         the shadow was produced (the fused optimizer writes both copies itself)."""
         v = self._version()
         if self.shadow_version != v:
+            if self.sharded is not None:      # something wrote the master through torch: complete it first (the parts other
+                self.sharded.sync_master()    # ranks own are stale here), then every rank recasts its full copy
             ops.cast_params_bf16(self.cast_table, 1, self.p16, self.total)
             self.shadow_version = v
 
@@ -446,6 +451,12 @@ class MAEEngine:
         self._waited = set()               # groups the pass being enqueued has already waited for
         self.grad_buckets = None
         self.bucket_elems = 32 << 20       # 128 MB of fp32 gradients per all-reduce bucket
+        # data parallel, sharded step (dp.ShardedStep): utils.misc.NativeScalerWithGradNormCount announces before the
+        # backward whether its fused optimizer step follows ("reduce": the backward reduces each finished slice into its
+        # owner) or not ("skip": gradient accumulation, nothing is exchanged yet); None = all-reduce inside backward
+        self.supports_sharded = True
+        self.defer_exchange: Optional[str] = None
+        self.grads_local = False           # the flat gradient buffer holds rank-local sums that still need the exchange
         # squared-norm partials of the gradient slices, computed per backward part on a stream of their own underneath the
         # later parts (FusedAdamW.step then starts with the tiny finalize instead of an 80 us pass over all gradients)
         self.norm_stream = torch.cuda.Stream(device=dev, priority=0)
@@ -604,8 +615,16 @@ class MAEEngine:
             lib = ops._lib.load()
             n0 = lib.vitae_launch_count()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=self._capture_stream()):
-                fn()
+            # no cyclic garbage collection while capturing: destructors with CUDA side effects (graphs, symmetric-memory
+            # mappings of a model that died earlier) invalidate the capture; torch.cuda.graph collects once on entry
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g, stream=self._capture_stream()):
+                    fn()
+            finally:
+                if gc_was_on:
+                    gc.enable()
             slot.launches = lib.vitae_launch_count() - n0
             self.graph_replayed_launches -= slot.launches    # the capture pass enqueued them without executing
             slot.graph = g
@@ -809,7 +828,13 @@ class MAEEngine:
         staged = sync_grads and dp.world_size() > 1
         stages = self._backward_stages(pl, dpred_extra, accumulate, split=staged, with_dlatent=dlatent is not None,
                                        encoder_only=encoder_only, with_edge=dedge is not None)
-        reducer = self._grad_reducer() if staged else None
+        reducer = None
+        if staged:
+            if self.defer_exchange == "reduce" and self.flat.sharded is not None:
+                reducer = self.flat.sharded      # owner-side reduce of each slice instead of an all-reduce
+                reducer.begin()
+            else:
+                reducer = self._grad_reducer()
         self._norm_count = 0
         self.norm_partials = 0
         for i, (fn, (a, b)) in enumerate(stages):
@@ -819,7 +844,10 @@ class MAEEngine:
                 self._run(pl, ("bwd", i, len(stages), pl.vol.data_ptr(), bool(accumulate), dlatent is not None,
                                encoder_only, dedge is not None, pl.fused_loss), fn)
             if reducer is not None:
-                reducer.launch(self.flat.g32[a:b])
+                if reducer is self.flat.sharded:
+                    reducer.launch(self.flat.g32[a:b], final=i == len(stages) - 1)
+                else:
+                    reducer.launch(self.flat.g32[a:b])
         if reducer is not None:
             reducer.wait()
         if len(stages) == 1 and not staged and not encoder_only and dpred_extra is None:
@@ -1152,6 +1180,13 @@ class MAEEngine:
                 offs = [(self.flat.offsets[n][0], self.flat.offsets[n][1]) for n in self.flat.order]
                 self.grad_buckets = dp.bucket_slices(offs, self.flat.total, self.bucket_elems)
             dp.allreduce_mean_bucketed_(self.flat.g32, self.grad_buckets)
+        self.grads_local = False
+
+    def sync_master(self) -> None:
+        """After sharded optimizer steps the fp32 master of the large matrices is current only on its owner: complete
+        this rank's copy (peer reads; called by the model's state_dict())."""
+        if self.flat.sharded is not None:
+            self.flat.sharded.sync_master()
 
     # ------------------------------------------------------------------------------------------------ optimizer
     def fused_optimizer(self) -> "FusedAdamW":
@@ -1170,8 +1205,9 @@ class FusedAdamW:
     def __init__(self, eng: MAEEngine):
         flat, dev = eng.flat, eng.device
         self.eng = eng
-        self.m = torch.zeros(flat.total, dtype=_F32, device=dev)
-        self.v = torch.zeros(flat.total, dtype=_F32, device=dev)
+        self.m = dp.alloc_flat(flat.total, _F32, dev, owner=flat)
+        self.v = dp.alloc_flat(flat.total, _F32, dev, owner=flat)
+        self._sharded_tried = False
         self.ctl = torch.zeros(8, dtype=_F32, device=dev)
         self.ws = torch.empty(ops.optim_workspace_bytes(), dtype=torch.uint8, device=dev)
         self.group_map = torch.full((flat.total // _ALIGN,), 255, dtype=torch.uint8, device=dev)
@@ -1222,6 +1258,8 @@ class FusedAdamW:
                     if st["exp_avg"].data_ptr() != mv.data_ptr():
                         mv.copy_(st["exp_avg"]); vv.copy_(st["exp_avg_sq"])
                     steps.append(float(st["step"]))
+                else:                   # a fresh optimizer starts from zero moments, whatever an earlier one left here
+                    mv.zero_(); vv.zero_()
                 optimizer.state[p] = {"step": torch.tensor(0.0), "exp_avg": mv, "exp_avg_sq": vv}
         steps += self.ex_steps
         self.group_map.copy_(gm)
@@ -1236,6 +1274,25 @@ class FusedAdamW:
         self.bound = id(optimizer)
         self.bound_sig = tuple(tuple(p.data_ptr() for p in g["params"]) for g in optimizer.param_groups)
         return True
+
+    def sharded(self) -> Optional["dp.ShardedStep"]:
+        """The sharded data-parallel step (dp.ShardedStep), set up on first use -- a COLLECTIVE call: every rank must reach
+        it (utils.misc.NativeScalerWithGradNormCount does, before the first backward of the fused path).  None when the job
+        is not a single-node NCCL group of 2..8 ranks, the flat buffers are not symmetric allocations (engine built before
+        init_process_group), or some optimizer parameters live outside the flat buffers."""
+        eng, flat = self.eng, self.eng.flat
+        if self._sharded_tried:
+            return flat.sharded
+        self._sharded_tried = True
+        if not dp.sharded_enabled():
+            return None
+        ok = (getattr(eng, "supports_sharded", False) and not self.ex_total
+              and all(dp.is_symmetric(t) for t in (flat.g32, flat.p32, flat.p16, self.m, self.v)))
+        agree = torch.tensor([1.0 if ok else 0.0], device=eng.device)
+        torch.distributed.all_reduce(agree, op=torch.distributed.ReduceOp.MIN)
+        if agree.item() == 1.0:
+            flat.sharded = dp.ShardedStep(flat, self.m, self.v, self.group_map)
+        return flat.sharded
 
     def _state_aliased(self, optimizer) -> bool:
         """False once the optimizer's moments stopped being views of the flat buffers (``optimizer.load_state_dict``
@@ -1297,6 +1354,20 @@ class FusedAdamW:
         gf, bf, gi = (scaler.get_growth_factor(), scaler.get_backoff_factor(), scaler.get_growth_interval()) \
             if use_scaler else (2.0, 0.5, 2000)
         eng.wait_params()
+        if getattr(eng, "grads_local", False):
+            sh = flat.sharded
+            if sh is None or self.ex_total:
+                eng.allreduce_gradients()        # the exchange was deferred to a sharded step that cannot run
+            else:
+                rows = [(g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"]) for g in optimizer.param_groups]
+                sh.step(self.ctl, rows, gf, bf, gi, use_scaler)
+                eng.grads_local = False
+                eng.norm_partials = 0
+                norm = self.ctl[4].clone()
+                flat.stamp_shadow()
+                flat.overwrite_grads = True
+                self.host_steps += 1
+                return norm
         if self.ex_total:      # gradients of the extras come from torch autograd: gather them into their flat buffer
             have = [(dst, p.grad) for p, dst in self.ex_items if p.grad is not None]
             if len(have) != len(self.ex_items):
@@ -1337,6 +1408,8 @@ class FusedAdamW:
         """Writes the device-side step count (skipped steps excluded) into the optimizer's per-parameter state (one
         device read): call before ``optimizer.state_dict()`` / switching to ``optimizer.step()``."""
         self.eng.wait_params()
+        if self.eng.flat.sharded is not None:      # moments of the parts other ranks own
+            self.eng.flat.sharded.sync_moments()
         steps = float(self.ctl[5].item())
         self.host_steps = int(steps)
         for group in optimizer.param_groups:

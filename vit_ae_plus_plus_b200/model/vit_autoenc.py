@@ -272,6 +272,13 @@ class MaskedAutoencoderViT(nn.Module):
         # the gradient exchange overlaps the backward stages, except when foreign gradients or a second (encoder-only,
         # contrastive view 2) backward still have to be added first
         sync = self.require_backward_grad_sync
+        if sync and eng.defer_exchange is not None:
+            # the caller's fused optimizer step exchanges the gradients itself (dp.ShardedStep): "reduce" = it follows this
+            # backward (overlap the owner-side reduce with the stages when nothing else has to be added first), "skip" =
+            # gradient accumulation, no exchange yet
+            eng.grads_local = True
+            if eng.defer_exchange == "skip" or saved is not None or second is not None:
+                sync = False
         overlap_sync = sync and saved is None and second is None
         eng.backward(pl, drecon, dpred_extra=dpred, accumulate=acc, sync_grads=overlap_sync, dlatent=dlatent, dedge=dedge)
         if second is not None and second[1] is not None:
@@ -296,6 +303,7 @@ class MaskedAutoencoderViT(nn.Module):
     def state_dict(self, *args, **kwargs):
         if self._engine is not None:
             self._engine.wait_params()       # an overlapped optimizer step may still be writing the parameters
+            self._engine.sync_master()       # sharded data-parallel steps: fetch the master of the parts other ranks own
         return super().state_dict(*args, **kwargs)
 
     # frozen helper modules of the reference model whose buffers / weights ride along in its checkpoints

@@ -473,6 +473,67 @@ def adamw_flat(param, grad, exp_avg, exp_avg_sq, param_bf16, n: int, group_of_ch
           "vitae_adamw_flat")
 
 
+def peer_table(ptrs) -> "ctypes.Array":
+    """Host array of the ranks' base addresses of one symmetric buffer (index = rank), as the dp_* entry points take it."""
+    arr = (ctypes.c_void_p * 8)()
+    for i, p in enumerate(ptrs):
+        arr[i] = int(p)
+    return arr
+
+
+def dp_owned_elems(lo: int, hi: int, granule_shift: int, world: int, rank: int) -> int:
+    return int(_lib.load().vitae_dp_owned_elems(lo, hi, granule_shift, world, rank))
+
+
+def dp_reduce_shard_blocks(lo: int, hi: int, granule_shift: int, world: int, rank: int, max_blocks: int = 0) -> int:
+    return int(_lib.load().vitae_dp_reduce_shard_blocks(lo, hi, granule_shift, world, rank, max_blocks))
+
+
+def dp_reduce_shard(grad_peers, world: int, rank: int, lo: int, hi: int, granule_shift: int, inv_world: float, partials,
+                    max_blocks: int = 0) -> int:
+    """This rank's part (granules q with q % world == rank) of flat gradient elements [lo, hi) := mean over ranks (peer
+    copies read over NVLink, ``grad_peers`` = peer_table of the gradient buffers); per-block sums of squares of the result
+    -> ``partials`` (fp32 view).  Returns the number of partials written (0: the rank owns nothing of the slice)."""
+    _req(partials, _F32, "partials")
+    lib = _lib.load()
+    nb = int(lib.vitae_dp_reduce_shard_blocks(lo, hi, granule_shift, world, rank, max_blocks))
+    assert partials.numel() >= nb
+    check(lib.vitae_dp_reduce_shard(grad_peers, world, rank, lo, hi, granule_shift, float(inv_world), partials.data_ptr(),
+                                    max_blocks, _stream()), "vitae_dp_reduce_shard")
+    return nb
+
+
+def adamw_shard(param_peers, param_bf16_peers, world: int, rank: int, lo: int, hi: int, granule_shift: int, grad, exp_avg,
+                exp_avg_sq, group_of_chunk, f32_chunk, hyper_rows, ctl, max_blocks: int = 0) -> None:
+    """adamw_flat over this rank's part of [lo, hi) (grad / exp_avg / exp_avg_sq / group_of_chunk / f32_chunk: whole flat
+    buffers), with the all-gather of the result fused in: bf16 shadow to every rank, fp32 master to the peers for the
+    chunks flagged in ``f32_chunk`` (uint8 per 64 elements)."""
+    lib = _lib.load()
+    ng = len(hyper_rows)
+    host = (ctypes.c_float * (8 * ng))()
+    for i, row in enumerate(hyper_rows):
+        for j, val in enumerate(row):
+            host[8 * i + j] = float(val)
+    check(lib.vitae_adamw_shard(param_peers, param_bf16_peers, world, rank, lo, hi, granule_shift, grad.data_ptr(),
+                                exp_avg.data_ptr(), exp_avg_sq.data_ptr(), group_of_chunk.data_ptr(), f32_chunk.data_ptr(),
+                                ctypes.cast(host, ctypes.c_void_p), ng, ctl.data_ptr(), max_blocks, _stream()),
+          "vitae_adamw_shard")
+
+
+def sum_partials(partials, n: int, out) -> None:
+    _req(partials, _F32, "partials"); _req(out, _F32, "out")
+    check(_lib.load().vitae_sum_partials(partials.data_ptr(), n, out.data_ptr(), _stream()), "vitae_sum_partials")
+
+
+def optim_finalize_peers(partial_peers, world: int, count: int, ctl, growth_factor: float, backoff_factor: float,
+                         growth_interval: int, use_scaler: bool) -> None:
+    """optim_finalize over ``count`` partial sums of squares from EVERY rank (peer_table of the ranks' partial buffers,
+    summed rank-major in double: every rank computes the same control block)."""
+    check(_lib.load().vitae_optim_finalize_peers(partial_peers, world, count, ctl.data_ptr(), float(growth_factor),
+                                                 float(backoff_factor), int(growth_interval), int(bool(use_scaler)), _stream()),
+          "vitae_optim_finalize_peers")
+
+
 def cast_f32_to_bf16(src, dst, max_blocks: int = 0) -> None:
     _req(src, _F32, "cast src"); _req(dst, _BF16, "cast dst")
     check(_lib.load().vitae_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), max_blocks, _stream()),

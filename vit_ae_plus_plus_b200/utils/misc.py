@@ -317,6 +317,7 @@ class NativeScalerWithGradNormCount:
         self._scaler = torch.amp.GradScaler("cuda")
         self._fused = None
         self.allow_fused = True
+        self.allow_sharded = True      # data parallel: dp.ShardedStep instead of all-reduce + replicated AdamW when available
         # True: the fused AdamW pass runs per layer group on its own stream and the next forward waits group by group
         # (engine.FusedAdamW.step).  Only for callers that do not touch parameters / gradients / optimizer state between
         # this call and the next forward.  Off by default: measured on B200 (ViT-B, batch 4) the overlapped pair takes as
@@ -353,12 +354,22 @@ class NativeScalerWithGradNormCount:
     def __call__(self, loss, optimizer, clip_grad=None, parameters=None, create_graph=False, update_grad=True):
         fo = self._fused_for(optimizer, clip_grad, create_graph)
         if fo is not None:
-            (loss * fo.ctl[0]).backward()
+            eng = fo.eng
+            # data parallel on one NVLink domain: the step below reduces + updates shard-wise (dp.ShardedStep), so the
+            # backward must not all-reduce; it reduces each finished slice into its owner when the step follows
+            sharded = fo.sharded() if self.allow_sharded else None
+            eng.defer_exchange = None if sharded is None else ("reduce" if update_grad else "skip")
+            try:
+                (loss * fo.ctl[0]).backward()
+            finally:
+                eng.defer_exchange = None
             if not update_grad:
                 return None
             return fo.step(optimizer, self._scaler, overlap=self.overlap_optimizer)
         if self._fused is not None:    # leaving the fused path: give the scale state back to torch's scaler
             self._scaler.load_state_dict(self.state_dict())
+            if getattr(self._fused.eng, "grads_local", False):      # accumulated, not yet exchanged gradients
+                self._fused.eng.allreduce_gradients()
             self._fused.sync_state(optimizer)
             self._fused = None
         self._scaler.scale(loss).backward(create_graph=create_graph)

@@ -8,8 +8,7 @@ run() { # n, name, flags, env...
   grep '^{' gpurun_out/r02y_$name.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$name', round(d['value'],1), round(d['ms_per_step'],3), d.get('e2e') and round(d['e2e']['value'],1), d.get('dp_mode'), d['dp_check'])" || grep -v "^\[W\|^W1\|^\*\*\*\|^frame" gpurun_out/r02y_$name.err | tail -12
 }
 run 8 n8_sharded '' A=1
-run 8 n8_allreduce --no-e2e VITAE_DP_SHARDED=0
-run 4 n4_sharded --no-e2e CUDA_VISIBLE_DEVICES=0,1,2,3
 run 8 n8_sharded_blocks48 --no-e2e VITAE_DP_REDUCE_BLOCKS=48
+run 4 n4_sharded --no-e2e CUDA_VISIBLE_DEVICES=0,1,2,3
 timeout 300 $TR --nproc-per-node 8 --master-port 29541 tools/dp_timeline.py 2> gpurun_out/r02y_tl.err | grep '^{' > gpurun_out/r02y_dp_timeline_8gpu.txt
 cat gpurun_out/r02y_dp_timeline_8gpu.txt

@@ -385,15 +385,19 @@ def replica_check(model, volumes, noises, opt_steps: int = 4) -> dict:
             losses = model(volumes[i % len(volumes)], noise=noises[i % len(noises)])[0]
             scaler(losses[0], opt, parameters=model.parameters(), update_grad=True)
             opt.zero_grad()
-        return scaler, losses[0].item()
+        return scaler, losses[0].item(), opt
 
-    scaler, final_loss = run_steps(True)
+    scaler, final_loss, opt = run_steps(True)
     sh = eng.flat.sharded
     out["sharded"] = bool(sh is not None and sh.steps > 0)
     out["shadow_spread_after_steps"] = spread(eng.flat.p16.float())      # what the kernels compute with
     eng.sync_master()                                                    # sharded: complete the fp32 master first
     out["param_spread_after_steps"] = spread(eng.flat.p32)
     out["fused_optimizer"] = scaler._fused is not None
+    out["moment_spread_after_state_dict"] = 0.0
+    if scaler._fused is not None:
+        opt.state_dict()                   # its pre-hook completes the moments (sharded: peer reads from the owners)
+        out["moment_spread_after_state_dict"] = max(spread(scaler._fused.m), spread(scaler._fused.v))
     out["final_loss"] = final_loss
     out["exchange_dtype"] = exchange_dtype()
     out["sharded_vs_allreduce"] = None
@@ -411,6 +415,7 @@ def replica_check(model, volumes, noises, opt_steps: int = 4) -> dict:
     tol = 1e-6 if out["exchange_dtype"] == "fp32" else 1e-2
     out["ok"] = (out["param_spread_after_broadcast"] == 0.0 and out["grad_spread_after_exchange"] == 0.0
                  and out["param_spread_after_steps"] == 0.0 and out["shadow_spread_after_steps"] == 0.0
+                 and out["moment_spread_after_state_dict"] == 0.0
                  and out["exchange_rel_err"] <= tol
                  and (out["sharded_vs_allreduce"] is None or out["sharded_vs_allreduce"] <= 1e-2))
     return out

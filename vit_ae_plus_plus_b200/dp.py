@@ -237,6 +237,8 @@ class ShardedStep:
         self.f32_chunk = wide.to(dev)
         self.comm = torch.cuda.Stream(device=dev, priority=-1)
         self.overlap_blocks = int(os.environ.get("VITAE_DP_REDUCE_BLOCKS", "96"))   # grid of a reduce that runs beside the backward
+        self.gather_blocks = int(os.environ.get("VITAE_DP_GATHER_BLOCKS", "296"))   # grid of an update that runs beside the forward
+        self.overlap_gather = os.environ.get("VITAE_DP_OVERLAP_GATHER", "1") != "0"
         self.slices: List[Tuple[int, int]] = []      # slices reduced since the last step, in order
         self.cursor = 0                              # partial sums written so far (PART_CAP per slice)
         self.master_stale = False
@@ -285,9 +287,15 @@ class ShardedStep:
 
     # ---- step ------------------------------------------------------------------------------------------------------
     def step(self, ctl: torch.Tensor, rows, growth_factor: float, backoff_factor: float, growth_interval: int,
-             use_scaler: bool) -> None:
+             use_scaler: bool, overlap=None) -> bool:
         """GradScaler.unscale_/update + AdamW on the gradients reduced since begin(); on return (stream order) every rank's
-        bf16 shadow and small fp32 tensors are current."""
+        bf16 shadow and small fp32 tensors are current.
+
+        ``overlap`` = (stream, [(start, end) per parameter group in FORWARD order], [event per group]): the update + all-gather
+        is issued group by group on ``stream``, each followed by its own cross-rank barrier and event; the next forward waits
+        for a group right before its first use (engine._need), so the all-gather of the later layers -- NVLink-bound, not
+        HBM-bound -- hides behind the forward of the earlier ones.  Returns True when issued that way (the caller's stream is
+        then NOT ordered after the update until engine.wait_params())."""
         if not self.slices:
             self.reduce_all()
         covered = sum(b - a for a, b in self.slices)
@@ -298,13 +306,26 @@ class ShardedStep:
         self.h["part"].barrier(channel=self.MAX_SLICES)          # every rank's total is written
         ops.optim_finalize_peers(self.peers["part_total"], W, 1, ctl, growth_factor, backoff_factor, growth_interval,
                                  use_scaler)
-        # one launch: ownership does not depend on how the backward sliced the buffer
-        ops.adamw_shard(self.peers["p32"], self.peers["p16"], W, r, 0, self.flat.total, GRANULE_SHIFT, self.flat.g32, self.m,
-                        self.v, self.group_map, self.f32_chunk, rows, ctl)
-        self.h["p16"].barrier(channel=self.MAX_SLICES + 1)       # every owner's stores have landed everywhere
+        if overlap is None:
+            # one launch: ownership does not depend on how the backward sliced the buffer
+            ops.adamw_shard(self.peers["p32"], self.peers["p16"], W, r, 0, self.flat.total, GRANULE_SHIFT, self.flat.g32,
+                            self.m, self.v, self.group_map, self.f32_chunk, rows, ctl)
+            self.h["p16"].barrier(channel=self.MAX_SLICES + 1)       # every owner's stores have landed everywhere
+        else:
+            stream, ranges, events = overlap
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            with torch.cuda.stream(stream):
+                stream.wait_event(ev)
+                for g, (a, b) in enumerate(ranges):
+                    ops.adamw_shard(self.peers["p32"], self.peers["p16"], W, r, a, b, GRANULE_SHIFT, self.flat.g32, self.m,
+                                    self.v, self.group_map, self.f32_chunk, rows, ctl, max_blocks=self.gather_blocks)
+                    self.h["p16"].barrier(channel=self.MAX_SLICES + 2 + g)
+                    events[g].record(stream)
         self.slices, self.cursor = [], 0
         self.master_stale = self.moments_stale = True
         self.steps += 1
+        return overlap is not None
 
     # ---- on-demand completion of the replicas ----------------------------------------------------------------------------
     def _pull(self, name: str, local: torch.Tensor) -> None:
@@ -390,6 +411,7 @@ def replica_check(model, volumes, noises, opt_steps: int = 4) -> dict:
     scaler, final_loss, opt = run_steps(True)
     sh = eng.flat.sharded
     out["sharded"] = bool(sh is not None and sh.steps > 0)
+    eng.wait_params()                                                    # (an overlapped update may still be in flight)
     out["shadow_spread_after_steps"] = spread(eng.flat.p16.float())      # what the kernels compute with
     eng.sync_master()                                                    # sharded: complete the fp32 master first
     out["param_spread_after_steps"] = spread(eng.flat.p32)
@@ -408,6 +430,7 @@ def replica_check(model, volumes, noises, opt_steps: int = 4) -> dict:
         with torch.no_grad():
             eng.flat.p32.copy_(p0)
         run_steps(False)
+        eng.wait_params()
         upd = (eng.flat.p32 - p0).abs().mean().item()
         out["sharded_vs_allreduce"] = (p_sh - eng.flat.p32).abs().mean().item() / (upd + 1e-30)
         out["param_spread_after_steps"] = max(out["param_spread_after_steps"], spread(eng.flat.p32))

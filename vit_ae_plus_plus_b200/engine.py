@@ -811,6 +811,7 @@ class MAEEngine:
         ``dlatent`` fp32 [B*Ne, D]: an additional upstream gradient of the normalised encoder output (the contrastive
         predictor consumes it, model/vit_autoenc.py:280-283).  ``encoder_only``: reverse of forward_encoder_only() -- the
         only upstream gradient is ``dlatent``; decoder parameters are not touched."""
+        self.wait_params()         # an overlapped optimizer step of parameter groups this step's forward did not touch
         if dloss is None:
             pl.dloss.zero_()
         else:
@@ -1360,7 +1361,10 @@ class FusedAdamW:
                 eng.allreduce_gradients()        # the exchange was deferred to a sharded step that cannot run
             else:
                 rows = [(g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"]) for g in optimizer.param_groups]
-                sh.step(self.ctl, rows, gf, bf, gi, use_scaler)
+                lap = (eng.opt_stream, eng.group_ranges, eng.param_ready) if sh.overlap_gather and hasattr(eng, "param_ready") \
+                    else None
+                if sh.step(self.ctl, rows, gf, bf, gi, use_scaler, overlap=lap):
+                    eng.params_in_flight = True
                 eng.grads_local = False
                 eng.norm_partials = 0
                 norm = self.ctl[4].clone()

@@ -45,7 +45,10 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_eager"],
+                    help="ours: this package; reference: the reference's CPU implementation (the driver's baseline arm); "
+                         "torch_eager: DIAGNOSTIC, the reference algorithm as plain PyTorch ops (cuBLAS / ATen, bf16 autocast, "
+                         "fused torch AdamW) on this GPU -- what the hand-written path has to beat on the same box")
     ap.add_argument("--workload", default="vit_base_128", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=4, help="volumes per GPU per step")
     ap.add_argument("--mask-ratio", type=float, default=0.75)
@@ -144,6 +147,49 @@ def unmodified_reference_rate(workload: dict, mask_ratio: float, batch: int, ste
             times.append(time.perf_counter() - t0)
     total = sum(times)
     return batch * len(times) / total, 1000.0 * total / len(times)
+
+
+def run_torch_eager(a):
+    """Diagnostic (evidence hygiene): the oracle's functional restatement of the reference step executed by
+    PyTorch eager on cuda:0 -- bf16 autocast over cuBLAS / ATen kernels, torch's fused AdamW -- on the own arm's config.
+    Nothing of this package runs here; it is neither the product nor the driver's reference arm."""
+    from oracle import mae_oracle as O
+    w = WORKLOADS[a.workload]
+    dev = torch.device("cuda", 0)
+    cfg = O.CONFIGS[w["oracle"]]
+    P = {k: v.to(dev) for k, v in O.init_params(cfg, 0).items()}
+    leaves = {k: v.clone().requires_grad_(k not in O.FROZEN) for k, v in P.items()}
+    opt = torch.optim.AdamW(O.weight_decay_groups(list(leaves.items()), 0.05), lr=1e-4, betas=(0.9, 0.95), fused=True)
+    V, C = cfg["volume_size"], cfg["in_chans"]
+    _, L, _ = O.geometry(cfg)
+    xs = [torch.randn(a.batch, C, V, V, V, device=dev) for _ in range(3)]
+
+    def step(x):
+        noise = torch.rand(a.batch, L, device=dev)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            losses, _, _, _ = O.forward(x, leaves, cfg, a.mask_ratio, noise, 0.0, with_edge=False)
+        opt.zero_grad(set_to_none=True)
+        losses[0].backward()
+        opt.step()
+        return losses[0]
+
+    for i in range(max(3, a.warmup)):
+        step(xs[i % 3])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        last = step(xs[i % 3])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({"impl": "torch_eager", "diagnostic": True, "metric": METRIC, "value": a.batch * a.steps / (ms / 1e3),
+                      "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms / a.steps,
+                      "higher_is_better": True, "dtype": "bf16 autocast", "data": "synthetic", "final_loss": float(last),
+                      "config": {"workload": workload_name(w, a, 1),
+                                 "note": "oracle/mae_oracle.py (the reference algorithm as torch ops) on cuda:0: PyTorch eager, "
+                                         "cuBLAS / ATen kernels, explicit softmax attention as in the reference, "
+                                         "torch.optim.AdamW(fused=True); no kernel of this package"}}), flush=True)
 
 
 def run_reference(a):
@@ -506,6 +552,8 @@ def main():
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "torch_eager":
+        run_torch_eager(a)
     else:
         run_ours(a)
 

@@ -157,7 +157,7 @@ def random_masking(x, mask_ratio: float, noise: torch.Tensor):
     ids_restore = torch.argsort(ids_shuffle, dim=1)                        # :143
     ids_keep = ids_shuffle[:, :len_keep]                                   # :146
     x_masked = torch.gather(x, 1, ids_keep.unsqueeze(-1).expand(-1, -1, D))  # :147
-    mask = torch.ones(N, L, dtype=x.dtype)
+    mask = torch.ones(N, L, dtype=x.dtype, device=x.device)
     mask[:, :len_keep] = 0                                                 # :150-151
     mask = torch.gather(mask, 1, ids_restore)                              # :153
     return x_masked, mask, ids_restore
@@ -303,8 +303,8 @@ def forward(x, P: Params, cfg, mask_ratio: float, noise: torch.Tensor, edge_map_
     if with_edge:
         raw_edge = edge_map_mse(pred, target, cfg["patch_size"])
     else:
-        raw_edge = torch.zeros((), dtype=pred.dtype)
-    percep = torch.zeros((), dtype=pred.dtype)
+        raw_edge = torch.zeros((), dtype=pred.dtype, device=pred.device)
+    percep = torch.zeros((), dtype=pred.dtype, device=pred.device)
     loss = edge_map_weight * raw_edge + recon + percep
     return [loss, raw_edge, recon, percep], pred, mask, ids_restore
 
@@ -368,8 +368,8 @@ def forward_contrastive(x1, x2, P: Params, cfg, mask_ratio: float, noise1: torch
     pred = forward_decoder(latent1, P, cfg, ids_restore)
     target = patchify(x1, cfg["patch_size"])
     recon = masked_mse(pred, target, mask)
-    raw_edge = edge_map_mse(pred, target, cfg["patch_size"]) if with_edge else torch.zeros((), dtype=pred.dtype)
-    percep = torch.zeros((), dtype=pred.dtype)
+    raw_edge = edge_map_mse(pred, target, cfg["patch_size"]) if with_edge else torch.zeros((), dtype=pred.dtype, device=pred.device)
+    percep = torch.zeros((), dtype=pred.dtype, device=pred.device)
     latent2, _, _ = forward_encoder(x2, P, cfg, mask_ratio, noise2)
     z1 = latent1.reshape(-1, latent1.shape[2])
     z2 = latent2.reshape(-1, latent2.shape[2])

@@ -239,7 +239,7 @@ class ShardedStep:
         self.overlap_blocks = int(os.environ.get("VITAE_DP_REDUCE_BLOCKS", "96"))   # grid of a reduce that runs beside the backward
         self.gather_blocks = int(os.environ.get("VITAE_DP_GATHER_BLOCKS", "296"))   # grid of an update that runs beside the forward
         # opt-in: on 2 GPUs the resident step is unchanged (4.085 vs 4.098 ms) and the end-to-end step gets slower and noisy
-        # (27 more enqueues per step on a host that also feeds the copy stream; profiles/r03d_*); not measured at 8
+        # (27 more enqueues per step on a host that also feeds the copy stream; profiles/r02zd_*); not measured at 8
         self.overlap_gather = os.environ.get("VITAE_DP_OVERLAP_GATHER", "0") == "1"
         self.slices: List[Tuple[int, int]] = []      # slices reduced since the last step, in order
         self.cursor = 0                              # partial sums written so far (PART_CAP per slice)
